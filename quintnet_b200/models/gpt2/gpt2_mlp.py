@@ -1,0 +1,45 @@
+"""Tensor-parallel GPT-2 MLP (reference ``utils/GPT2/gpt2_mlp.py:51-162``):
+column-parallel ``c_fc`` with the exact-erf GELU fused into the GEMM epilogue,
+row-parallel ``c_proj``."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from ... import ops
+from ...parallel.tensor_parallel.layers import ColumnParallelLinear, RowParallelLinear
+
+
+class GPT2MLP(nn.Module):
+    def __init__(self, config, tp_rank: int, tp_size: int, tp_group, device,
+                 c_fc_weight: Optional[torch.Tensor] = None, c_fc_bias: Optional[torch.Tensor] = None,
+                 c_proj_weight: Optional[torch.Tensor] = None, c_proj_bias: Optional[torch.Tensor] = None,
+                 dtype=None):
+        super().__init__()
+        self.embed_dim = config.n_embd
+        self.inner_dim = config.n_inner if config.n_inner is not None else 4 * config.n_embd
+        if self.inner_dim % tp_size:
+            raise ValueError(f"n_inner={self.inner_dim} not divisible by tp={tp_size}")
+        self.inner_dim_local = self.inner_dim // tp_size
+        self.tp_rank, self.tp_size, self.tp_group, self.device = tp_rank, tp_size, tp_group, device
+        sp = bool(getattr(config, "sequence_parallel", False)) and tp_size > 1
+        if c_fc_bias is None and c_fc_weight is not None:
+            c_fc_bias = torch.zeros(self.inner_dim_local)
+        self.c_fc = ColumnParallelLinear(device, tp_group, self.embed_dim, self.inner_dim_local,
+                                         weight_slice=c_fc_weight, bias_slice=c_fc_bias,
+                                         gather_output=False, sequence_parallel=sp,
+                                         activation="gelu", dtype=dtype)
+        if c_proj_bias is None and c_proj_weight is None:
+            c_proj_bias = torch.zeros(self.embed_dim)
+        self.c_proj = RowParallelLinear(device, tp_group, self.inner_dim_local, self.embed_dim,
+                                        weight_slice=c_proj_weight, bias_slice=c_proj_bias,
+                                        input_is_parallel=True, sequence_parallel=sp, dtype=dtype)
+        self.resid_pdrop = config.resid_pdrop
+        self.dropout = nn.Dropout(config.resid_pdrop)
+
+    def forward(self, hidden_states: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        h = self.c_fc(hidden_states)          # bias + GELU fused
+        h = self.c_proj(h)
+        return ops.dropout_add(h, residual, self.resid_pdrop, self.training)

@@ -1,0 +1,99 @@
+"""Op layer: every hot op of the framework goes through here.
+
+CUDA tensors are served by the hand-written sm_100a kernels in
+``quintnet_b200/csrc`` (loaded from the in-tree ``lib/libquintnet_b200.so`` by
+:mod:`.native`); CPU tensors by the plain-PyTorch references in
+:mod:`.reference`.  There is no silent fallback on a GPU: if the native library
+is missing the op raises, unless ``QUINTNET_ALLOW_FALLBACK=1`` is set
+(debugging only).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import reference
+from . import native
+
+
+def _use_native(name: str, *tensors) -> bool:
+    t = tensors[0]
+    if not t.is_cuda:
+        return False
+    return native.op_enabled(name)
+
+
+# ----------------------------------------------------------------- linear
+def linear(x, w, b=None, act: Optional[str] = None):
+    """y = act(x @ w.T + b);  w is [out, in] (nn.Linear layout)."""
+    if _use_native("gemm", x) and x.dtype == torch.bfloat16:
+        from . import cuda_ops
+        return cuda_ops.linear(x, w, b, act)
+    return reference.linear(x, w, b, act)
+
+
+def layer_norm(x, w, b, eps: float = 1e-5):
+    if _use_native("layernorm", x) and x.dtype in (torch.bfloat16, torch.float32):
+        from . import cuda_ops
+        return cuda_ops.layer_norm(x, w, b, eps)
+    return reference.layer_norm(x, w, b, eps)
+
+
+def add_layer_norm(x, residual, w, b, eps: float = 1e-5):
+    if _use_native("layernorm", x) and x.dtype in (torch.bfloat16, torch.float32):
+        from . import cuda_ops
+        return cuda_ops.add_layer_norm(x, residual, w, b, eps)
+    return reference.add_layer_norm(x, residual, w, b, eps)
+
+
+def gelu(x):
+    if _use_native("gelu", x) and x.dtype == torch.bfloat16:
+        from . import cuda_ops
+        return cuda_ops.gelu(x)
+    return reference.gelu(x)
+
+
+def attention(q, k, v, causal: bool, dropout_p: float = 0.0, scale=None, training: bool = True):
+    """q,k,v: [B, H, T, d] -> [B, H, T, d]"""
+    if _use_native("attention", q) and q.dtype == torch.bfloat16:
+        from . import cuda_ops
+        return cuda_ops.attention(q, k, v, causal, dropout_p if training else 0.0, scale)
+    if q.is_cuda:
+        # library attention (cuDNN/flash SDPA) until the native kernel is enabled
+        import torch.nn.functional as F
+        return F.scaled_dot_product_attention(q, k, v, is_causal=causal, scale=scale,
+                                              dropout_p=dropout_p if training else 0.0)
+    return reference.attention(q, k, v, causal, dropout_p, scale, training)
+
+
+def cross_entropy_sum(logits, labels, ignore_index: int = -100):
+    if _use_native("cross_entropy", logits):
+        from . import cuda_ops
+        return cuda_ops.cross_entropy_sum(logits, labels, ignore_index)
+    return reference.cross_entropy_sum(logits, labels, ignore_index)
+
+
+def linear_cross_entropy(h, w, labels, ignore_index: int = -100):
+    """Fused lm_head + CE: never materialises fp32 [N, V] logits on GPU."""
+    if _use_native("cross_entropy", h) and h.dtype == torch.bfloat16:
+        from . import cuda_ops
+        return cuda_ops.linear_cross_entropy(h, w, labels, ignore_index)
+    return reference.linear_cross_entropy(h, w, labels, ignore_index)
+
+
+def dropout_add(x, residual, p: float, training: bool):
+    if _use_native("dropout", x) and x.dtype == torch.bfloat16 and p > 0.0 and training:
+        from . import cuda_ops
+        return cuda_ops.dropout_add(x, residual, p)
+    return reference.dropout_add(x, residual, p, training)
+
+
+def rope(x, cos, sin):
+    if _use_native("rope", x) and x.dtype == torch.bfloat16:
+        from . import cuda_ops
+        return cuda_ops.rope(x, cos, sin)
+    return reference.rope(x, cos, sin)
+
+
+rope_tables = reference.rope_tables

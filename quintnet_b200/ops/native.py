@@ -1,0 +1,167 @@
+"""Loader for the in-tree native library (``quintnet_b200/lib/libquintnet_b200.so``).
+
+The kernels are plain CUDA C++ with a C ABI (no torch headers → seconds to
+compile, one ``nvcc -gencode arch=compute_100a,code=sm_100a`` invocation per
+file); Python calls them through ctypes with raw device pointers and the
+current CUDA stream.  ``build()`` compiles them; ``lib()`` loads them.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+from pathlib import Path
+from typing import List, Optional
+
+import torch
+
+PKG = Path(__file__).resolve().parent.parent
+CSRC = PKG / "csrc"
+LIBDIR = PKG / "lib"
+LIBNAME = "libquintnet_b200.so"
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "--use_fast_math",
+]
+
+_lib: Optional[ctypes.CDLL] = None
+_load_error: Optional[str] = None
+
+# ops whose native kernel is used on CUDA tensors.  Env override:
+#   QUINTNET_NATIVE=all | none | comma-separated list
+_DEFAULT_ENABLED = {
+    "layernorm", "gelu", "adamw", "dropout", "rope", "cross_entropy", "gemm", "attention",
+    "allreduce", "zero1", "tp_fused",
+}
+
+
+def _enabled_set():
+    v = os.environ.get("QUINTNET_NATIVE", "").strip()
+    if not v or v == "all":
+        dis = {s for s in os.environ.get("QUINTNET_NATIVE_DISABLE", "").split(",") if s}
+        return _DEFAULT_ENABLED - dis
+    if v == "none":
+        return set()
+    return {s.strip() for s in v.split(",") if s.strip()}
+
+
+def nvcc_path() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def sources() -> List[Path]:
+    return sorted(CSRC.glob("*.cu"))
+
+
+def build(force: bool = False, verbose: bool = True, jobs: int = 8) -> Path:
+    """Compile every ``csrc/*.cu`` for sm_100a and link the shared library."""
+    LIBDIR.mkdir(exist_ok=True)
+    objdir = LIBDIR / "obj"
+    objdir.mkdir(exist_ok=True)
+    out = LIBDIR / LIBNAME
+    srcs = sources()
+    hdrs = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h"))
+    newest_hdr = max([h.stat().st_mtime for h in hdrs], default=0.0)
+    procs, objs = [], []
+    for s in srcs:
+        o = objdir / (s.stem + ".o")
+        objs.append(o)
+        if not force and o.exists() and o.stat().st_mtime > max(s.stat().st_mtime, newest_hdr):
+            continue
+        cmd = [nvcc_path(), *NVCC_FLAGS, "-I", str(CSRC), "-c", str(s), "-o", str(o)]
+        if verbose:
+            print("[quintnet_b200.build]", " ".join(cmd), flush=True)
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        if len(procs) >= jobs:
+            _wait(procs)
+    _wait(procs)
+    need_link = force or not out.exists() or any(o.stat().st_mtime > out.stat().st_mtime for o in objs)
+    if need_link:
+        cmd = [nvcc_path(), "-shared", "-o", str(out), *[str(o) for o in objs], "-lcudart"]
+        if verbose:
+            print("[quintnet_b200.build]", " ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+    return out
+
+
+def _wait(procs):
+    while procs:
+        s, p = procs.pop(0)
+        outp = p.communicate()[0].decode()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {s}:\n{outp}")
+        if outp.strip():
+            print(outp)
+
+
+def lib_path() -> Path:
+    return LIBDIR / LIBNAME
+
+
+def available() -> bool:
+    return lib() is not None
+
+
+def lib() -> Optional[ctypes.CDLL]:
+    global _lib, _load_error
+    if _lib is not None or _load_error is not None:
+        return _lib
+    p = lib_path()
+    if not p.exists():
+        _load_error = f"{p} does not exist (run `python -c 'import __graft_entry__ as g; g.build()'`)"
+        return None
+    try:
+        _lib = ctypes.CDLL(str(p))
+    except OSError as e:  # e.g. no libcudart on a CPU-only box
+        _load_error = str(e)
+        return None
+    return _lib
+
+
+def require() -> ctypes.CDLL:
+    l = lib()
+    if l is None:
+        raise RuntimeError(f"quintnet_b200 native library unavailable: {_load_error}")
+    return l
+
+
+def op_enabled(name: str) -> bool:
+    """True if CUDA tensors should use the native kernel for ``name``."""
+    if name not in _enabled_set():
+        return False
+    if lib() is None:
+        if os.environ.get("QUINTNET_ALLOW_FALLBACK", "0") == "1":
+            return False
+        raise RuntimeError(
+            f"native op '{name}' requested on a CUDA tensor but the native library is not "
+            f"loadable: {_load_error}.  Build it (graft build()) or set QUINTNET_ALLOW_FALLBACK=1."
+        )
+    return True
+
+
+# ------------------------------------------------------------- ctypes helpers
+def ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def stream() -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(code: int, what: str) -> None:
+    if code != 0:
+        raise RuntimeError(f"{what} failed with CUDA error {code}")
+
+
+# launch counter (bench.py reports gpu_launches)
+launch_count = 0
+
+
+def count(n: int = 1) -> None:
+    global launch_count
+    launch_count += n

@@ -1,0 +1,103 @@
+"""Plain-PyTorch reference implementations of every op in :mod:`quintnet_b200.ops`.
+
+These are (a) the CPU path used by the gloo plumbing tests and (b) the fp32
+oracle the sm_100a kernels are tested against (tests/test_kernels_gpu.py).
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+
+def linear(x, w, b=None, act: Optional[str] = None):
+    y = F.linear(x, w, b)
+    if act == "gelu":
+        y = F.gelu(y)
+    elif act == "relu":
+        y = F.relu(y)
+    elif act is not None:
+        raise ValueError(f"unknown activation {act}")
+    return y
+
+
+def layer_norm(x, w, b, eps: float = 1e-5):
+    return F.layer_norm(x, (x.shape[-1],), w, b, eps)
+
+
+def add_layer_norm(x, residual, w, b, eps: float = 1e-5):
+    """returns (LN(x + residual), x + residual)"""
+    s = x + residual
+    return F.layer_norm(s, (s.shape[-1],), w, b, eps), s
+
+
+def gelu(x):
+    return F.gelu(x)
+
+
+def attention(q, k, v, causal: bool, dropout_p: float = 0.0, scale: Optional[float] = None,
+              training: bool = True):
+    """q,k,v: [B, H, T, d].  Explicit softmax(QK^T*scale)V."""
+    d = q.shape[-1]
+    scale = (1.0 / math.sqrt(d)) if scale is None else scale
+    s = torch.matmul(q.float(), k.float().transpose(-1, -2)) * scale
+    if causal:
+        Tq, Tk = s.shape[-2], s.shape[-1]
+        mask = torch.ones(Tq, Tk, dtype=torch.bool, device=s.device).tril(diagonal=Tk - Tq)
+        s = s.masked_fill(~mask, float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    if dropout_p > 0.0 and training:
+        p = F.dropout(p, dropout_p, True)
+    return torch.matmul(p, v.float()).to(q.dtype)
+
+
+def cross_entropy_sum(logits, labels, ignore_index: int = -100):
+    """returns (sum of token losses fp32, number of valid tokens)"""
+    loss = F.cross_entropy(logits.float(), labels, ignore_index=ignore_index, reduction="sum")
+    n = (labels != ignore_index).sum()
+    return loss, n
+
+
+def linear_cross_entropy(h, w, labels, ignore_index: int = -100):
+    """h: [N, E], w: [V, E], labels: [N] -> (loss_sum, n_valid)"""
+    return cross_entropy_sum(F.linear(h, w), labels, ignore_index)
+
+
+def dropout_add(x, residual, p: float, training: bool):
+    if p > 0.0 and training:
+        x = F.dropout(x, p, True)
+    return x + residual if residual is not None else x
+
+
+def rope(x, cos, sin):
+    """x: [B, H, T, d] (rotate-half convention); cos/sin: [T, d/2]."""
+    d2 = x.shape[-1] // 2
+    x1, x2 = x[..., :d2].float(), x[..., d2:].float()
+    c, s = cos[None, None].float(), sin[None, None].float()
+    return torch.cat([x1 * c - x2 * s, x2 * c + x1 * s], dim=-1).to(x.dtype)
+
+
+def rope_tables(T: int, d: int, base: float = 10000.0, device=None):
+    inv = 1.0 / (base ** (torch.arange(0, d, 2, device=device, dtype=torch.float32) / d))
+    ang = torch.arange(T, device=device, dtype=torch.float32)[:, None] * inv[None]
+    return ang.cos(), ang.sin()
+
+
+def adamw_step(p, g, m, v, step: int, lr: float, beta1: float, beta2: float, eps: float,
+               weight_decay: float, grad_scale: float = 1.0, master=None):
+    """Single-tensor AdamW (decoupled decay) in fp32; writes p/m/v in place.
+    ``master`` is the optional fp32 master copy of a low-precision ``p``."""
+    w = master if master is not None else p
+    gf = g.float() * grad_scale
+    m.mul_(beta1).add_(gf, alpha=1 - beta1)
+    v.mul_(beta2).addcmul_(gf, gf, value=1 - beta2)
+    bc1 = 1 - beta1 ** step
+    bc2 = 1 - beta2 ** step
+    denom = (v / bc2).sqrt_().add_(eps)
+    wf = w.float()
+    wf.mul_(1 - lr * weight_decay).addcdiv_(m / bc1, denom, value=-lr)
+    w.copy_(wf)
+    if master is not None:
+        p.copy_(wf)

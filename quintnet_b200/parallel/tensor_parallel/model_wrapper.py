@@ -1,0 +1,86 @@
+"""In-place tensor-parallel rewrite of a model's ``nn.Linear`` layers.
+
+API parity: reference ``parallelism/tensor_parallel/model_wrapper.py:37-166``
+(``apply_tensor_parallel(model, tp_size, tp_rank, tp_group, device,
+gather_output, sync_gradients, method_of_parallelism)``).  Additionally offers
+``method_of_parallelism='paired'``: Megatron pairing for the ViT blocks —
+Q/K/V and ``down_proj`` column-parallel *without* gather, ``up_proj``
+row-parallel — which removes 4 of the 5 all-gathers per block the reference
+issues.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from .layers import ColumnParallelLinear, RowParallelLinear
+
+
+def _column(lin: nn.Linear, tp_size, tp_rank, tp_group, device, gather_output, sync_gradients):
+    out_per = lin.out_features // tp_size
+    s, e = tp_rank * out_per, (tp_rank + 1) * out_per
+    return ColumnParallelLinear(
+        device, tp_group, lin.in_features, out_per,
+        weight_slice=lin.weight.data[s:e, :],
+        bias_slice=None if lin.bias is None else lin.bias.data[s:e],
+        gather_output=gather_output, sync_gradients=sync_gradients, dtype=lin.weight.dtype)
+
+
+def _row(lin: nn.Linear, tp_size, tp_rank, tp_group, device, input_is_parallel):
+    in_per = lin.in_features // tp_size
+    s, e = tp_rank * in_per, (tp_rank + 1) * in_per
+    return RowParallelLinear(
+        device, tp_group, in_per, lin.out_features,
+        weight_slice=lin.weight.data[:, s:e],
+        bias_slice=None if lin.bias is None else lin.bias.data,
+        input_is_parallel=input_is_parallel, dtype=lin.weight.dtype)
+
+
+def apply_tensor_parallel(model: nn.Module, tp_size: int, tp_rank: int, tp_group, device,
+                          gather_output: bool = True, sync_gradients: bool = True,
+                          method_of_parallelism: str = "column") -> nn.Module:
+    if method_of_parallelism not in ("column", "row", "paired"):
+        raise ValueError(f"unknown method_of_parallelism {method_of_parallelism!r}")
+    if tp_size <= 1:
+        return model.to(device)
+
+    def paired_role(name: str):
+        leaf = name.split(".")[-1]
+        if leaf in ("Q", "K", "V", "down_proj", "c_attn", "c_fc", "fc1") and "classification_head" not in name:
+            return "col"
+        if leaf in ("up_proj", "c_proj", "fc2"):
+            return "row"
+        return None
+
+    def rewrite(module: nn.Module, prefix: str = ""):
+        for name, child in list(module.named_children()):
+            full = f"{prefix}.{name}" if prefix else name
+            if isinstance(child, nn.Linear):
+                new = None
+                if method_of_parallelism == "column":
+                    if child.out_features % tp_size == 0:
+                        new = _column(child, tp_size, tp_rank, tp_group, device, gather_output,
+                                      sync_gradients)
+                elif method_of_parallelism == "row":
+                    if child.in_features % tp_size == 0:
+                        new = _row(child, tp_size, tp_rank, tp_group, device, False)
+                else:
+                    role = paired_role(full)
+                    if role == "col" and child.out_features % tp_size == 0:
+                        new = _column(child, tp_size, tp_rank, tp_group, device, False, sync_gradients)
+                    elif role == "row" and child.in_features % tp_size == 0:
+                        new = _row(child, tp_size, tp_rank, tp_group, device, True)
+                if new is not None:
+                    setattr(module, name, new)
+            else:
+                rewrite(child, full)
+
+    rewrite(model)
+    model.to(device)
+    if dist.is_initialized():
+        dist.barrier()
+    return model
+
+
+TensorParallel = apply_tensor_parallel

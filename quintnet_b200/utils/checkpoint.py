@@ -1,0 +1,122 @@
+"""Checkpoint save / load / resume.
+
+Shard files keep the reference's naming and top-level keys
+(``GPT2_Trainer.py:453-507``): ``{dir}/{name}_pp{p}_tp{t}.pt`` holding
+``model_state_dict``, ``optimizer_state_dict``, ``config``, ``parallelism_info``.
+Only dp-rank 0 writes the model shard (the reference lets all DP replicas
+overwrite the same file); under ZeRO-1 every dp rank additionally writes its
+optimizer shard ``…_dp{d}.opt.pt``.  Resume (absent from the reference,
+SURVEY §5.4) restores model, optimizer (incl. ZeRO shards), step/epoch and RNG.
+"""
+from __future__ import annotations
+
+import os
+import random
+from typing import Optional
+
+import numpy as np
+import torch
+
+
+def _names(out_dir: str, filename: str, pg_manager):
+    base, ext = os.path.splitext(filename)
+    pp, tp, dp = pg_manager.axis_rank("pp"), pg_manager.axis_rank("tp"), pg_manager.axis_rank("dp")
+    shard = os.path.join(out_dir, f"{base}_pp{pp}_tp{tp}{ext or '.pt'}")
+    opt = os.path.join(out_dir, f"{base}_pp{pp}_tp{tp}_dp{dp}.opt{ext or '.pt'}")
+    return shard, opt
+
+
+def rng_state():
+    st = {"python": random.getstate(), "numpy": np.random.get_state(), "torch": torch.get_rng_state()}
+    if torch.cuda.is_available():
+        st["cuda"] = torch.cuda.get_rng_state()
+    return st
+
+
+def set_rng_state(st):
+    random.setstate(st["python"])
+    np.random.set_state(st["numpy"])
+    torch.set_rng_state(st["torch"])
+    if "cuda" in st and torch.cuda.is_available():
+        torch.cuda.set_rng_state(st["cuda"])
+
+
+def save_shard(out_dir: str, filename: str, stage_module, optimizer, config, pg_manager,
+               extra: Optional[dict] = None) -> str:
+    os.makedirs(out_dir, exist_ok=True)
+    shard, opt_path = _names(out_dir, filename, pg_manager)
+    sharded_opt = getattr(optimizer, "handles_grad_clipping", False) and hasattr(optimizer, "shards")
+    info = {"pp_rank": pg_manager.axis_rank("pp"), "tp_rank": pg_manager.axis_rank("tp"),
+            "pp_size": pg_manager.axis_size("pp"), "tp_size": pg_manager.axis_size("tp"),
+            "dp_size": pg_manager.axis_size("dp"), "zero_stage": 1 if sharded_opt else 0}
+    if pg_manager.axis_rank("dp") == 0:
+        payload = {
+            "model_state_dict": {k: v.detach().cpu() for k, v in stage_module.state_dict().items()},
+            "optimizer_state_dict": None if (optimizer is None or sharded_opt) else optimizer.state_dict(),
+            "config": _plain(config),
+            "parallelism_info": info,
+            "extra": extra or {},
+            "rng_state": rng_state(),
+        }
+        torch.save(payload, shard)
+    if sharded_opt:
+        torch.save({"optimizer_state_dict": optimizer.state_dict(), "parallelism_info": info}, opt_path)
+    return shard
+
+
+def load_shard(prefix_path: str, stage_module, optimizer, pg_manager, map_location="cpu",
+               strict: bool = True) -> dict:
+    out_dir, filename = os.path.split(prefix_path)
+    shard, opt_path = _names(out_dir or ".", filename, pg_manager)
+    payload = torch.load(shard, map_location="cpu", weights_only=False)
+    info = payload["parallelism_info"]
+    if info["pp_size"] != pg_manager.axis_size("pp") or info["tp_size"] != pg_manager.axis_size("tp"):
+        raise ValueError(f"checkpoint was written for pp={info['pp_size']} tp={info['tp_size']}")
+    stage_module.load_state_dict(payload["model_state_dict"], strict=strict)
+    if optimizer is not None:
+        if info.get("zero_stage", 0) >= 1 and os.path.exists(opt_path):
+            optimizer.load_state_dict(torch.load(opt_path, map_location="cpu", weights_only=False)
+                                      ["optimizer_state_dict"])
+        elif payload.get("optimizer_state_dict") is not None:
+            optimizer.load_state_dict(payload["optimizer_state_dict"])
+        _refresh_masters(optimizer)
+    if payload.get("rng_state") is not None:
+        try:
+            set_rng_state(payload["rng_state"])
+        except Exception:
+            pass
+    return payload.get("extra", {})
+
+
+def _refresh_masters(optimizer) -> None:
+    """fp32 master copies are part of the optimizer state; nothing to do unless
+    the optimizer was freshly built from loaded low-precision parameters."""
+    return None
+
+
+def _plain(obj):
+    if isinstance(obj, dict):
+        return {k: _plain(v) for k, v in obj.items()}
+    if isinstance(obj, (list, tuple)):
+        return [_plain(v) for v in obj]
+    if isinstance(obj, torch.dtype):
+        return str(obj).replace("torch.", "")
+    if hasattr(obj, "to_dict"):
+        return obj.to_dict()
+    return obj
+
+
+# ---- single-process helpers (reference utils/utils.py:58-96) ----------------
+def save_checkpoint(model, optimizer, epoch: int, loss: float, path: str) -> None:
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    torch.save({"epoch": epoch, "model_state_dict": model.state_dict(),
+                "optimizer_state_dict": None if optimizer is None else optimizer.state_dict(),
+                "loss": loss}, path)
+
+
+def load_checkpoint(model, optimizer, path: str, map_location="cpu"):
+    ck = torch.load(path, map_location=map_location, weights_only=False)
+    model.load_state_dict(ck["model_state_dict"])
+    if optimizer is not None and ck.get("optimizer_state_dict") is not None:
+        optimizer.load_state_dict(ck["optimizer_state_dict"])
+    return ck.get("epoch", 0), ck.get("loss", None)
