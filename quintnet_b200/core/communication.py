@@ -62,10 +62,10 @@ def all_gather_cat(x: torch.Tensor, group, dim: int = -1) -> torch.Tensor:
         out = x.new_empty((n * x.shape[0],) + tuple(x.shape[1:]))
         dist.all_gather_into_tensor(out, x, group=group)
         return out
-    out = x.new_empty((n,) + tuple(x.shape))
+    out = x.new_empty((n * x.shape[0],) + tuple(x.shape[1:]))
     dist.all_gather_into_tensor(out, x, group=group)
-    # [n, ..., d, ...] -> concat along `dim`
-    return torch.cat(out.unbind(0), dim=dim)
+    # [n*d0, ...] -> n chunks concatenated along `dim`
+    return torch.cat(out.chunk(n, dim=0), dim=dim)
 
 
 def reduce_scatter_chunk(x: torch.Tensor, group, dim: int = -1) -> torch.Tensor:
@@ -75,15 +75,31 @@ def reduce_scatter_chunk(x: torch.Tensor, group, dim: int = -1) -> torch.Tensor:
     dim = dim % x.dim()
     if x.shape[dim] % n != 0:
         raise ValueError(f"dim {dim} of size {x.shape[dim]} is not divisible by group size {n}")
-    if dim == 0:
-        x = x.contiguous()
-        out = x.new_empty((x.shape[0] // n,) + tuple(x.shape[1:]))
-        dist.reduce_scatter_tensor(out, x, group=group)
-        return out
-    chunks = torch.stack([c.contiguous() for c in x.chunk(n, dim=dim)], dim=0)
-    out = chunks.new_empty(chunks.shape[1:])
-    dist.reduce_scatter_tensor(out, chunks, group=group)
+    if dim != 0:
+        x = torch.cat([c for c in x.chunk(n, dim=dim)], dim=0)   # chunk r -> rows of rank r
+    x = x.contiguous()
+    out = x.new_empty((x.shape[0] // n,) + tuple(x.shape[1:]))
+    _reduce_scatter_tensor(out, x, group)
     return out
+
+
+_RS_UNSUPPORTED = set()
+
+
+def _reduce_scatter_tensor(out: torch.Tensor, x: torch.Tensor, group) -> None:
+    """reduce_scatter_tensor with an all-reduce+slice fallback for backends
+    (older gloo) that lack the primitive."""
+    backend = dist.get_backend(group)
+    if backend not in _RS_UNSUPPORTED:
+        try:
+            dist.reduce_scatter_tensor(out, x, group=group)
+            return
+        except (RuntimeError, NotImplementedError):
+            _RS_UNSUPPORTED.add(backend)
+    full = x.clone()
+    dist.all_reduce(full, group=group)
+    n, r = dist.get_world_size(group), dist.get_rank(group)
+    out.copy_(full.chunk(n, dim=0)[r])
 
 
 # --------------------------------------------------------------------------

@@ -26,6 +26,7 @@ class Attention(nn.Module):
         self.Q = nn.Linear(hidden_dim, hidden_dim)
         self.K = nn.Linear(hidden_dim, hidden_dim)
         self.V = nn.Linear(hidden_dim, hidden_dim)
+        self.tp_group = None   # set for the 'paired' TP rewrite (local heads, one gather)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         B, T, _ = x.shape
@@ -37,7 +38,11 @@ class Attention(nn.Module):
         k = k.view(B, T, h, self.head_dim).transpose(1, 2)
         v = v.view(B, T, h, self.head_dim).transpose(1, 2)
         o = ops.attention(q, k, v, causal=False, dropout_p=0.0, training=self.training)
-        return o.transpose(1, 2).reshape(B, T, h * self.head_dim)
+        o = o.transpose(1, 2).reshape(B, T, h * self.head_dim)
+        if o.shape[-1] != self.hidden_dim and self.tp_group is not None:
+            from ..core.communication import All_Gather
+            o = All_Gather.apply(o, self.tp_group, "slice", -1)
+        return o
 
 
 class MLP(nn.Module):

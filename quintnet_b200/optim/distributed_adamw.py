@@ -94,7 +94,8 @@ class DistributedAdamW(torch.optim.Optimizer):
             return
         if self.dp_size > 1:
             src = b.flat_grad if b.flat_grad.dtype == torch.float32 else b.flat_grad.float()
-            dist.reduce_scatter_tensor(st["grad"], src, group=self.group)
+            from ..core.communication import _reduce_scatter_tensor
+            _reduce_scatter_tensor(st["grad"], src, self.group)
             st["grad"].mul_(scale)
         else:
             st["grad"].copy_(b.flat_grad)

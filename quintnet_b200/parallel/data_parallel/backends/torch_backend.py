@@ -19,6 +19,11 @@ class _WorkHandle(Handle):
                 self.tensor.mul_(self.scale)
 
 
+def _scaled(out, scale):
+    out.mul_(scale)
+    return Handle()
+
+
 class TorchDistributedBackend(DistributedBackend):
     def is_initialized(self) -> bool:
         return dist.is_available() and dist.is_initialized()
@@ -51,5 +56,6 @@ class TorchDistributedBackend(DistributedBackend):
             return Handle()
         if inp.dtype != out.dtype:
             inp = inp.to(out.dtype)
-        work = dist.reduce_scatter_tensor(out, inp, op=dist.ReduceOp.SUM, group=group, async_op=True)
-        return _WorkHandle(work, out, scale)
+        from ....core.communication import _reduce_scatter_tensor
+        _reduce_scatter_tensor(out, inp, group)
+        return _WorkHandle(None, out, 1.0) if scale == 1.0 else _scaled(out, scale)

@@ -1,0 +1,184 @@
+"""GPT-2: schema, TP (plain + sequence-parallel) == single device, PP schedules ==
+single process (loss AND post-step parameters), 3-D 2x2x2 parity."""
+import copy
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+
+from tests._dist import run_distributed
+from quintnet_b200 import init_process_groups, get_strategy, GPT2Trainer
+from quintnet_b200.models.gpt2 import GPT2Config, GPT2Model, GPT2Stage
+from quintnet_b200.core.distributed_loading import random_gpt2_state_dict
+from quintnet_b200.utils.data import SyntheticTokens, make_loader
+
+CFG = dict(vocab_size=96, n_positions=16, n_embd=32, n_layer=4, n_head=4,
+           resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+
+
+def test_state_dict_schema():
+    cfg = GPT2Config(**CFG)
+    m = GPT2Model(cfg)
+    keys = set(m.state_dict().keys())
+    for k in ["embedding.wte.weight", "embedding.wpe.weight", "blocks.0.ln_1.weight",
+              "blocks.0.attn.c_attn.proj.weight", "blocks.0.attn.c_attn.proj.bias",
+              "blocks.0.attn.c_proj.proj.weight", "blocks.0.attn.c_proj.bias",
+              "blocks.3.mlp.c_fc.proj.weight", "blocks.3.mlp.c_proj.proj.weight",
+              "blocks.3.mlp.c_proj.bias", "ln_f.weight", "ln_f.bias"]:
+        assert k in keys, k
+    assert m.state_dict()["blocks.0.attn.c_attn.proj.weight"].shape == (96, 32)
+    ids = torch.randint(0, 96, (2, 16))
+    logits = m(ids)
+    assert logits.shape == (2, 16, 96)
+    # fused loss == CE on shifted logits
+    ls, n = m(ids, labels=ids)
+    ref = nn.functional.cross_entropy(logits[:, :-1].reshape(-1, 96), ids[:, 1:].reshape(-1), reduction="sum")
+    assert torch.allclose(ls, ref, atol=1e-4) and int(n) == 2 * 15
+    out = m.generate(ids[:, :4], max_new_tokens=3)
+    assert out.shape == (2, 7)
+
+
+def test_hf_equivalence():
+    """Our GPT-2 computes the HuggingFace GPT-2 function (exact-erf GELU)."""
+    transformers = __import__("pytest").importorskip("transformers")
+    from quintnet_b200.core.distributed_loading import hf_shapes, random_hf_tensor
+    cfg = GPT2Config(**CFG)
+    hf_cfg = transformers.GPT2Config(vocab_size=96, n_positions=16, n_embd=32, n_layer=4, n_head=4,
+                                     resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0,
+                                     activation_function="gelu")
+    hf = transformers.GPT2LMHeadModel(hf_cfg).eval()
+    sd = {("transformer." + n): random_hf_tensor(n, s, cfg, 0, torch.device("cpu"))
+          for n, s in hf_shapes(cfg).items()}
+    sd["lm_head.weight"] = sd["transformer.wte.weight"]
+    hf.load_state_dict(sd, strict=False)
+    ours = GPT2Model(cfg, seed=0).eval()
+    ids = torch.randint(0, 96, (2, 16))
+    with torch.no_grad():
+        assert torch.allclose(ours(ids), hf(ids).logits, atol=2e-4)
+
+
+def _tp_equals_single(rank, world):
+    pg = init_process_groups("cpu", [world], ["tp"])
+    g = pg.get_group("tp")
+    for sp in (False, True):
+        cfg = GPT2Config(**CFG, sequence_parallel=sp)
+        ref = GPT2Model(GPT2Config(**CFG), seed=1)
+        tp = GPT2Model(cfg, tp_group=g, tp_rank=rank, tp_size=world, seed=1)
+        ids = torch.randint(0, 96, (4, 16), generator=torch.Generator().manual_seed(3))
+        assert torch.allclose(tp(ids), ref(ids), atol=1e-4), f"logits sp={sp}"
+        ls_r, n_r = ref(ids, labels=ids)
+        ls_t, n_t = tp(ids, labels=ids)
+        assert torch.allclose(ls_t, ls_r, atol=1e-3) and float(n_t) == float(n_r)
+        (ls_r / n_r).backward()
+        (ls_t / n_t).backward()
+        tp.sync_sequence_parallel_grads()
+        assert torch.allclose(tp.embedding.wte.weight.grad, ref.embedding.wte.weight.grad, atol=1e-4), sp
+        assert torch.allclose(tp.blocks[0].ln_1.weight.grad, ref.blocks[0].ln_1.weight.grad, atol=1e-4), sp
+        E = 32
+        w = E // world
+        cols = torch.cat([torch.arange(rank * w, (rank + 1) * w) + j * E for j in range(3)])
+        assert torch.allclose(tp.blocks[1].attn.c_attn.proj.weight.grad,
+                              ref.blocks[1].attn.c_attn.proj.weight.grad[cols], atol=1e-4), sp
+
+
+def test_tp_equals_single():
+    run_distributed(_tp_equals_single, 2)
+
+
+def _train_cfg(mesh_dim, mesh_name, schedule="1f1b", zero=0, sp=False, M=4, batch=8):
+    return {"batch_size": batch, "learning_rate": 1e-2, "num_epochs": 1, "grad_acc_steps": M,
+            "max_grad_norm": 1.0, "model_config": dict(CFG), "device_type": "cpu",
+            "mesh_dim": mesh_dim, "mesh_name": mesh_name, "strategy_name": "3d", "schedule": schedule,
+            "max_seq_length": 16, "zero_stage": zero, "sequence_parallel": sp, "seed": 1,
+            "weight_decay": 0.01, "output_dir": "/tmp/qn_test_ckpt"}
+
+
+def _single_process_reference(steps, M, batch, data):
+    """Plain PyTorch loop: same model, same data order, AdamW, global clip."""
+    cfg = GPT2Config(**CFG)
+    model = GPT2Model(cfg, seed=1)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-2, weight_decay=0.01)
+    losses = []
+    idx = 0
+    mb = batch // M
+    for _ in range(steps):
+        tot, cnt = 0.0, 0
+        for _ in range(M):
+            ids = data.input_ids[idx:idx + mb]
+            lab = data.labels[idx:idx + mb]
+            idx += mb
+            ls, n = model(ids, labels=lab)
+            (ls / n / M).backward()
+            tot, cnt = tot + float(ls), cnt + float(n)
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)
+        opt.step()
+        opt.zero_grad()
+        losses.append(tot / cnt)
+    return losses, model
+
+
+def _run_parallel(rank, world, mesh_dim, mesh_name, schedule, zero, sp, batch=8):
+    M, steps = 4, 3
+    dp = mesh_dim[mesh_name.index("dp")] if "dp" in mesh_name else 1
+    # with dp>1 per-replica token-mean losses only equal the global one without padding
+    data = SyntheticTokens(batch * steps, seq_len=16, vocab_size=96, seed=11, pad_id=0,
+                           min_fill=0.6 if dp == 1 else 1.0)
+    ref_losses, ref_model = _single_process_reference(steps, M, batch, data)
+    cfg = _train_cfg(mesh_dim, mesh_name, schedule, zero, sp, M, batch)
+    pg = init_process_groups("cpu", mesh_dim, mesh_name)
+    model = get_strategy("3d", pg, cfg, checkpoint_path=None, is_staged=True).apply(None)
+    # data order: a global step consumes `batch` samples; dp replica d takes micro-batches
+    # d, d+dp, ... of the step (so the union over replicas is the reference's batch)
+    mb = batch // (M * dp)
+    d = pg.axis_rank("dp")
+    order = []
+    for s in range(steps):
+        for m in range(M):
+            start = s * batch + (m * dp + d) * mb
+            order.extend(range(start, start + mb))
+    sub = torch.utils.data.Subset(data, order)
+    from quintnet_b200.utils.data import dict_collate
+    loader = torch.utils.data.DataLoader(sub, batch_size=mb, shuffle=False, collate_fn=dict_collate)
+    tr = GPT2Trainer(model, loader, None, cfg, pg, GPT2Config(**CFG))
+    got = []
+    for s in range(steps):
+        loss, ppl = tr.train_step()
+        if loss is not None:
+            got.append(loss)
+    # the dp replicas see different halves; average their reported losses
+    if got:
+        t = torch.tensor(got)
+        if dp > 1:
+            dist.all_reduce(t, group=pg.get_group("dp"))
+            t /= dp
+        assert torch.allclose(t, torch.tensor(ref_losses), atol=2e-3), (t, ref_losses)
+    # parameters after 3 optimizer steps
+    stage = tr.gpt2_stage
+    if stage.is_last_stage:
+        assert torch.allclose(stage.ln_f.weight.float(), ref_model.ln_f.weight, atol=3e-3)
+    if stage.is_first_stage:
+        assert torch.allclose(stage.embedding.wpe.weight.float(), ref_model.embedding.wpe.weight, atol=3e-3)
+    from quintnet_b200.parallel.pipeline_parallel.utils import distribute_layers
+    pp = pg.axis_size("pp")
+    lid = distribute_layers(4, pp)[pg.axis_rank("pp")][0]
+    assert torch.allclose(stage.blocks[0].ln_2.bias.float(), ref_model.blocks[lid].ln_2.bias, atol=3e-3)
+
+
+def test_pp2_1f1b():
+    run_distributed(_run_parallel, 2, [2], ["pp"], "1f1b", 0, False)
+
+
+def test_pp2_afab():
+    run_distributed(_run_parallel, 2, [2], ["pp"], "afab", 0, False)
+
+
+def test_pp4_1f1b():
+    run_distributed(_run_parallel, 4, [4], ["pp"], "1f1b", 0, False)
+
+
+def test_3d_2x2x2():
+    run_distributed(_run_parallel, 8, [2, 2, 2], ["dp", "tp", "pp"], "1f1b", 0, False, timeout=400)
+
+
+def test_3d_2x2x2_zero1_sequence_parallel():
+    run_distributed(_run_parallel, 8, [2, 2, 2], ["dp", "tp", "pp"], "1f1b", 1, True, 16, timeout=400)
