@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""Headline benchmark: GPT-2 3-D parallel training throughput (tokens/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this framework
+    python bench.py --impl reference --gpus N ...            # unmodified reference (baseline/_ref)
+
+Metric / config (BASELINE.json): tokens/sec, device-timed, max over ranks, of a full optimizer
+step (forward + backward + gradient sync + clip + AdamW) of GPT-2 (medium by default, the model
+BASELINE.json names for the 3-D run) at global batch 512 x seq 512 (the reference's
+examples/gpt2_config.yaml), micro-batch 32, 1F1B, on synthetic tokens with random-init weights.
+Mesh by GPU count: 1 -> [1,1,1], 2 -> dp2, 4 -> dp2 x pp2, 8 -> dp2 x tp2 x pp2 (override: --mesh d,t,p).
+Total work per step is the same at every N (strong scaling).
+
+Both arms run the same schedule through their own public API:
+  ours      : init_process_groups -> get_strategy('3d', is_staged=True).apply(None) -> GPT2Trainer.train_step()
+  reference : init_process_groups -> get_strategy('3d', ..., is_staged=True).apply(None) -> GPT2Trainer
+              (pipeline_trainer.train_step for pp>1, its standard epoch loop for pp=1), fp32 as shipped.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+import types
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+MODELS = {
+    "gpt2-small": dict(n_embd=768, n_layer=12, n_head=12),
+    "gpt2-medium": dict(n_embd=1024, n_layer=24, n_head=16),
+    "gpt2-large": dict(n_embd=1280, n_layer=36, n_head=20),
+    "gpt2-tiny": dict(n_embd=256, n_layer=4, n_head=4),      # CPU plumbing / debugging only
+}
+DEFAULT_MESH = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 1, 2), 8: (2, 2, 2)}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default=os.environ.get("QN_BENCH_MODEL", "gpt2-medium"), choices=list(MODELS))
+    ap.add_argument("--mesh", default=None, help="dp,tp,pp (default by --gpus)")
+    ap.add_argument("--global-batch", type=int, default=512)
+    ap.add_argument("--micro-batch", type=int, default=32)
+    ap.add_argument("--seq-len", type=int, default=512)
+    ap.add_argument("--vocab", type=int, default=50257)
+    ap.add_argument("--schedule", default="1f1b")
+    ap.add_argument("--zero", type=int, default=None, help="ZeRO stage for our arm (default 1 when dp>1)")
+    ap.add_argument("--sequence-parallel", type=int, default=None)
+    ap.add_argument("--cpu", action="store_true", help="gloo/CPU plumbing run (tiny model)")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, enabled: bool):
+        self.proc, self.lines, self.enabled = None, [], enabled
+
+    def start(self):
+        if not self.enabled:
+            return
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ data
+def make_micro_batches(n_micro, mb, seq, vocab, seed, pin, device=None):
+    """List of micro-batch dicts (input_ids / attention_mask / labels), int64, full-length sequences
+    (the reference's collator pads to max_length; padding does not change the work)."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n_micro):
+        ids = torch.randint(0, vocab, (mb, seq), generator=g)
+        b = {"input_ids": ids, "attention_mask": torch.ones_like(ids), "labels": ids.clone()}
+        if device is not None:
+            b = {k: v.to(device) for k, v in b.items()}
+        elif pin:
+            b = {k: v.pin_memory() for k, v in b.items()}
+        out.append(b)
+    return out
+
+
+class ListLoader:
+    """Minimal DataLoader stand-in: iterates a fixed list of micro-batches."""
+
+    def __init__(self, batches, batch_size):
+        self.batches, self.batch_size, self.sampler, self.dataset = batches, batch_size, None, batches
+
+    def __iter__(self):
+        return iter(self.batches)
+
+    def __len__(self):
+        return len(self.batches)
+
+
+# ----------------------------------------------------------------------------------------- common
+def dist_env(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29511")
+    os.environ.setdefault("RANK", "0")
+    os.environ.setdefault("WORLD_SIZE", "1")
+    os.environ.setdefault("LOCAL_RANK", "0")
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+        args.gpus = world
+    if args.cpu:
+        device = torch.device("cpu")
+        if not dist.is_initialized():
+            dist.init_process_group("gloo", rank=rank, world_size=world)
+    else:
+        torch.cuda.set_device(local)
+        device = torch.device("cuda", local)
+        if not dist.is_initialized():
+            dist.init_process_group("nccl", rank=rank, world_size=world, device_id=device)
+    return rank, world, device
+
+
+def mesh_for(args):
+    if args.mesh:
+        m = tuple(int(x) for x in args.mesh.split(","))
+    else:
+        m = DEFAULT_MESH.get(args.gpus)
+        if m is None:
+            raise SystemExit(f"no default mesh for {args.gpus} GPUs; pass --mesh dp,tp,pp")
+    assert m[0] * m[1] * m[2] == args.gpus, (m, args.gpus)
+    return m
+
+
+def build_config(args, mesh, impl):
+    dp, tp, pp = mesh
+    M = args.global_batch // (args.micro_batch * dp)
+    assert M >= 1 and M * args.micro_batch * dp == args.global_batch
+    mc = dict(vocab_size=args.vocab, n_positions=1024, n_inner=None, attn_pdrop=0.1, embd_pdrop=0.1,
+              resid_pdrop=0.1, layer_norm_epsilon=1e-5, **MODELS[args.model])
+    mc["n_inner"] = 4 * mc["n_embd"]
+    cfg = {
+        "batch_size": args.global_batch, "learning_rate": 5e-5, "num_epochs": 1, "grad_acc_steps": M,
+        "max_grad_norm": 1.0, "num_workers": 0, "model_config": mc, "device_type": "cpu" if args.cpu else "cuda",
+        "mesh_dim": [dp, tp, pp], "mesh_name": ["dp", "tp", "pp"], "strategy_name": "3d",
+        "schedule": args.schedule, "max_seq_length": args.seq_len, "max_target_length": 128,
+        "output_dir": os.path.join(tempfile.gettempdir(), "qn_bench_ckpt"), "vocab_size": args.vocab,
+        "compute_generation_metrics": False,
+    }
+    if impl == "ours":
+        zero = args.zero if args.zero is not None else (1 if dp > 1 else 0)
+        sp = args.sequence_parallel if args.sequence_parallel is not None else 0
+        cfg.update({"dtype": "float32" if args.cpu else "bfloat16", "zero_stage": zero,
+                    "sequence_parallel": bool(sp) and tp > 1, "seed": 0, "weight_decay": 0.01,
+                    "bucket_cap_mb": 128})
+    return cfg, M
+
+
+def timed_region(run_step, steps, device, cpu):
+    """barrier + sync, K steps between two CUDA events, sync + barrier; returns ms (this rank)."""
+    import torch
+    import torch.distributed as dist
+    dist.barrier()
+    if cpu:
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            run_step()
+        dist.barrier()
+        return (time.perf_counter() - t0) * 1e3
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(steps):
+        run_step()
+    e.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    return s.elapsed_time(e)
+
+
+def max_over_ranks(x: float, device):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x: float, device):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def emit(args, mesh, M, ms_total, e2e, clocks, launches, impl, dtype, extra=None):
+    dp, tp, pp = mesh
+    tokens = args.global_batch * args.seq_len
+    ms_step = ms_total / args.steps
+    value = tokens / (ms_step / 1e3)
+    out = {
+        "metric": "tokens/sec (device-timed, max over ranks) GPT-2 3D training step",
+        "value": value, "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": dtype, "data": "synthetic tokens, random-init weights", "impl": impl,
+        "config": {"model": args.model, "global_batch": args.global_batch, "seq_len": args.seq_len,
+                   "micro_batch": args.micro_batch, "grad_acc_steps": M, "parallelism": f"dp{dp}tp{tp}pp{pp}",
+                   "schedule": args.schedule, "optimizer": "AdamW", "vocab": args.vocab,
+                   "l2": "inputs larger than L2: each step streams weights+activations of tens of GB (>> 126 MB)"},
+        "clocks": clocks, "gpu_launches": launches,
+    }
+    if e2e is not None:
+        out["e2e"] = e2e
+    if extra:
+        out["config"].update(extra)
+    print(json.dumps(out), flush=True)
+
+
+# -------------------------------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank, world, device = dist_env(args)
+    mesh = mesh_for(args)
+    from quintnet_b200 import GPT2Trainer, get_strategy, init_process_groups
+    from quintnet_b200.models.gpt2 import GPT2Config
+    from quintnet_b200.ops import native
+    cfg, M = build_config(args, mesh, "ours")
+    pg = init_process_groups("cpu" if args.cpu else "cuda", cfg["mesh_dim"], cfg["mesh_name"])
+    model = get_strategy("3d", pg, cfg, checkpoint_path=None, is_staged=True).apply(None)
+    model_config = GPT2Config.from_dict(cfg["model_config"])
+    dp_rank = pg.axis_rank("dp")
+    n_micro = M * 2
+    dev_batches = make_micro_batches(n_micro, args.micro_batch, args.seq_len, args.vocab, 1000 + dp_rank, False, device)
+    trainer = GPT2Trainer(model, ListLoader(dev_batches, args.micro_batch), None, cfg, pg, model_config)
+
+    last = {}
+
+    def step():
+        last["loss"] = trainer.train_step()
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(rank == 0 and not args.cpu)
+    sampler.start()
+    l0 = native.launch_count
+    ms = timed_region(step, args.steps, device, args.cpu)
+    launches = native.launch_count - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms, device)
+    launches = int(max_over_ranks(float(launches), device))
+
+    e2e = None
+    if not args.no_e2e:
+        # end to end: same public call, micro-batches come from PINNED HOST memory every step and the
+        # step's loss is read back to the host (GPT2Trainer.train_step returns python floats)
+        host_batches = make_micro_batches(n_micro, args.micro_batch, args.seq_len, args.vocab, 2000 + dp_rank,
+                                          not args.cpu)
+        from quintnet_b200.parallel.pipeline_parallel import PipelineDataLoader
+        trainer.micro_loader = PipelineDataLoader(ListLoader(host_batches, args.micro_batch), M, task_type="clm")
+        step()
+        ms_e = timed_region(step, args.steps, device, args.cpu)
+        ms_e = max_over_ranks(ms_e, device)
+        per_mb = args.micro_batch * args.seq_len * 8
+        h2d = (per_mb * M if trainer.is_first_stage else 0) + (per_mb * M if trainer.is_last_stage else 0)
+        d2h = 8 if trainer.is_last_stage else 0
+        h2d, d2h = sum_over_ranks(h2d, device), sum_over_ranks(d2h, device)
+        tokens = args.global_batch * args.seq_len
+        e2e = {"value": tokens / (ms_e / args.steps / 1e3), "unit": "tokens/s", "ms_per_step": ms_e / args.steps,
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+    if rank == 0:
+        extra = {"zero_stage": cfg["zero_stage"], "sequence_parallel": cfg["sequence_parallel"],
+                 "native_ops": sorted(native._enabled_set()) if native.available() else [],
+                 "last_loss": last.get("loss", (None, None))[0]}
+        emit(args, mesh, M, ms, e2e, clocks, launches, "ours", "fp32" if args.cpu else "bf16", extra)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+# --------------------------------------------------------------------------------------- reference
+def run_reference(args):
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "core")) or not os.path.exists(os.path.join(ref_root, "GPT2_Trainer.py")):
+        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref is not installed on this box"}))
+        return
+    try:
+        _run_reference(args, ref_root)
+    except SystemExit:
+        raise
+    except BaseException as e:  # the reference is allowed to be unable to run a config
+        import traceback
+        traceback.print_exc()
+        if int(os.environ.get("RANK", 0)) == 0:
+            print(json.dumps({"impl": "reference", "unavailable": f"{type(e).__name__}: {str(e)[:200]}"}), flush=True)
+
+
+def _run_reference(args, ref_root):
+    import torch
+    import torch.distributed as dist
+    if args.cpu:
+        print(json.dumps({"impl": "reference", "unavailable": "the reference rejects non-cuda device types"}))
+        return
+    rank, world, device = dist_env(args)
+    mesh = mesh_for(args)
+    # the installed tree is flat (setup.py find_packages at repo root): give it the parent package its
+    # relative imports expect, without touching any reference file
+    pkg = types.ModuleType("QuintNet")
+    pkg.__path__ = [ref_root]
+    pkg.__file__ = os.path.join(ref_root, "__init__.py")
+    sys.modules["QuintNet"] = pkg
+    from QuintNet.core import init_process_groups
+    from QuintNet.strategy import get_strategy
+    from QuintNet.GPT2_Trainer import GPT2Trainer
+    from QuintNet.utils.GPT2 import GPT2Config
+    from QuintNet.parallelism import PipelineDataLoader
+
+    cfg, M = build_config(args, mesh, "reference")
+    # random-init HF-layout checkpoint of the named architecture (no network on the box)
+    ckpt = os.path.join(tempfile.gettempdir(), f"qn_ref_{args.model}_{args.vocab}.safetensors")
+    if rank == 0 and not os.path.exists(ckpt):
+        from quintnet_b200.core.distributed_loading import save_random_hf_checkpoint
+        from quintnet_b200.models.gpt2 import GPT2Config as OurCfg
+        save_random_hf_checkpoint(ckpt, OurCfg.from_dict(cfg["model_config"]), seed=0)
+    dist.barrier()
+    cfg["checkpoint_path"] = ckpt
+    pg = init_process_groups(device_type="cuda", mesh_dim=cfg["mesh_dim"], mesh_name=cfg["mesh_name"])
+    model_config = GPT2Config.from_dict(cfg["model_config"])
+    cfg["model_config"] = model_config.to_dict() if hasattr(model_config, "to_dict") else cfg["model_config"]
+    model = get_strategy("3d", pg, cfg, checkpoint_path=ckpt, is_staged=True).apply(None)
+    coords = pg.get_coordinates_tensor_search(rank)
+    dp_rank = coords[0]
+    pp = mesh[2]
+    n_micro = M * 2
+    host_batches = make_micro_batches(n_micro, args.micro_batch, args.seq_len, args.vocab, 1000 + dp_rank, True)
+    loader = ListLoader(host_batches, args.micro_batch)
+    trainer = GPT2Trainer(model, loader, loader, cfg, pg, model_config)
+    model.train()
+
+    if pp > 1:
+        def step():
+            trainer.pipeline_trainer.train_step(trainer.train_loader, trainer.tensor_shapes, trainer.device, torch.float32)
+            if hasattr(trainer.gpt2_stage, "sync_tied_weights_grad"):
+                trainer.gpt2_stage.sync_tied_weights_grad()
+    else:
+        # stock non-pipeline path: GPT2Trainer._train_epoch_standard (one optimizer step per loader batch)
+        one_step = ListLoader(host_batches[:M], args.micro_batch)
+
+        def step():
+            trainer.train_loader = one_step
+            trainer._train_epoch_standard(0)
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(rank == 0)
+    sampler.start()
+    ms = timed_region(step, args.steps, device, False)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms, device)
+    tokens = args.global_batch * args.seq_len
+    per_mb = args.micro_batch * args.seq_len * 8
+    if rank == 0:
+        # the reference's loop already copies every micro-batch from (pinned) host memory and reads the loss
+        # back with .item(): its device-timed number IS its end-to-end number
+        e2e = {"value": tokens / (ms / args.steps / 1e3), "unit": "tokens/s", "ms_per_step": ms / args.steps,
+               "h2d_bytes_per_step": int(per_mb * 3 * M * world), "d2h_bytes_per_step": int(8 * M * world)}
+        emit(args, mesh, M, ms, e2e, clocks, 0, "reference", "fp32",
+             {"note": "reference as shipped: fp32, torch ops (cuBLAS/SDPA) + NCCL; no DP gradient sync (its default)"})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.cpu and args.model != "gpt2-tiny":
+        args.model, args.vocab, args.seq_len, args.micro_batch, args.global_batch = "gpt2-tiny", 1024, 64, 4, 32
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,200 @@
+// quintnet_b200 — fused elementwise kernels (bf16 I/O, fp32 math, 16-byte vectors):
+//   * dropout(x)·1/(1-p) + residual   forward / backward (mask regenerated from a Philox counter)
+//   * GELU (exact erf) forward / backward (+ optional bias add)
+//   * column sum (bias gradient)
+//   * RoPE forward / backward (K7)
+#include "common.cuh"
+
+namespace qn {
+
+constexpr int EW_THREADS = 256;
+
+QN_DEVICE void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+QN_DEVICE void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// keep-mask for 8 consecutive elements starting at element index `i8*8`
+QN_DEVICE uint32_t keep_mask8(const Philox& rng, uint64_t offset, uint64_t i8, uint32_t threshold) {
+  const uint4 a = rng(offset + 2 * i8), b = rng(offset + 2 * i8 + 1);
+  uint32_t m = 0;
+  m |= (a.x >= threshold) << 0; m |= (a.y >= threshold) << 1; m |= (a.z >= threshold) << 2; m |= (a.w >= threshold) << 3;
+  m |= (b.x >= threshold) << 4; m |= (b.y >= threshold) << 5; m |= (b.z >= threshold) << 6; m |= (b.w >= threshold) << 7;
+  return m;
+}
+
+// y = dropout(x) * scale + residual   (residual may be null)
+__global__ void __launch_bounds__(EW_THREADS)
+dropout_add_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
+                       __nv_bfloat16* __restrict__ y, long long n8, uint32_t threshold, float scale, uint64_t seed,
+                       uint64_t offset) {
+  const Philox rng(seed);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8], r[8];
+    load8(x + i * 8, f);
+    const uint32_t m = keep_mask8(rng, offset, i, threshold);
+    if (res != nullptr) load8(res + i * 8, r);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = ((m >> e) & 1 ? f[e] * scale : 0.f) + (res != nullptr ? r[e] : 0.f);
+    store8(y + i * 8, f);
+  }
+}
+// dx = dy * mask * scale
+__global__ void __launch_bounds__(EW_THREADS)
+dropout_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, long long n8,
+                   uint32_t threshold, float scale, uint64_t seed, uint64_t offset) {
+  const Philox rng(seed);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    load8(dy + i * 8, f);
+    const uint32_t m = keep_mask8(rng, offset, i, threshold);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = (m >> e) & 1 ? f[e] * scale : 0.f;
+    store8(dx + i * 8, f);
+  }
+}
+
+__global__ void __launch_bounds__(EW_THREADS)
+gelu_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    load8(x + i * 8, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) f[e] = gelu_erf(f[e]);
+    store8(y + i * 8, f);
+  }
+}
+// dx = dy * gelu'(z)
+__global__ void __launch_bounds__(EW_THREADS)
+gelu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
+                __nv_bfloat16* __restrict__ dx, long long n8) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+    float g[8], zz[8];
+    load8(dy + i * 8, g);
+    load8(z + i * 8, zz);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) g[e] *= gelu_erf_grad(zz[e]);
+    store8(dx + i * 8, g);
+  }
+}
+
+// out[c] = sum_r x[r, c]  (bias gradient).  grid.x tiles columns (64 per CTA: 8 vector-columns of 8 bf16,
+// 32 row-lanes), grid.y splits rows; partial sums are combined with fp32 atomics into `acc`
+// (zeroed by the caller), then converted.
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ acc, int rows, int cols, long long ld) {
+  __shared__ float red[32][65];
+  const int cv = threadIdx.x & 7;          // vector column within the 64-wide tile
+  const int rl = threadIdx.x >> 3;         // row lane 0..31
+  const int c0 = blockIdx.x * 64 + cv * 8;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c0 < cols) {
+    for (int r = blockIdx.y * 32 + rl; r < rows; r += gridDim.y * 32) {
+      float f[8];
+      load8(x + (size_t)r * ld + c0, f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s[e] += f[e];
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < 8; ++e) red[rl][cv * 8 + e] = s[e];
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float t = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) t += red[r][threadIdx.x];
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c < cols) atomicAdd(acc + c, t);
+  }
+}
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16(in[i]);
+}
+
+// RoPE (rotate-half): x viewed as [n_rows, T, d] with arbitrary row/seq strides (elements); cos/sin [T, d/2] fp32.
+// sign = +1 forward, -1 backward (the rotation is orthogonal: the gradient is the inverse rotation)
+__global__ void __launch_bounds__(EW_THREADS)
+rope_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, const float* __restrict__ cosp,
+            const float* __restrict__ sinp, int B, int H, int T, int d, long long sb, long long sh, long long st,
+            float sign) {
+  const int half = d / 2;
+  const long long total = (long long)B * H * T * half;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int j = i % half;
+    long long r = i / half;
+    const int t = r % T; r /= T;
+    const int h = r % H;
+    const int b = r / H;
+    const __nv_bfloat16* xp = x + b * sb + h * sh + t * st;
+    const float x1 = __bfloat162float(xp[j]), x2 = __bfloat162float(xp[j + half]);
+    const float c = cosp[t * half + j], s = sign * sinp[t * half + j];
+    __nv_bfloat16* yp = y + (((long long)b * H + h) * T + t) * d;       // output contiguous [B,H,T,d]
+    yp[j] = __float2bfloat16(x1 * c - x2 * s);
+    yp[j + half] = __float2bfloat16(x2 * c + x1 * s);
+  }
+}
+
+static int ew_grid(long long n) {
+  long long g = (n + EW_THREADS - 1) / EW_THREADS;
+  if (g > 148 * 8) g = 148 * 8;
+  return g < 1 ? 1 : (int)g;
+}
+
+}  // namespace qn
+
+using namespace qn;
+
+extern "C" int qn_dropout_add_fwd(const void* x, const void* res, void* y, long long n, float p,
+                                  unsigned long long seed, unsigned long long offset, cudaStream_t s) {
+  if (n % 8) return 930;
+  const uint32_t thr = (uint32_t)fminf(4294967295.0f, p * 4294967296.0f);
+  dropout_add_fwd_kernel<<<ew_grid(n / 8), EW_THREADS, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res,
+                                                              (__nv_bfloat16*)y, n / 8, thr, 1.0f / (1.0f - p), seed, offset);
+  return (int)cudaGetLastError();
+}
+extern "C" int qn_dropout_bwd(const void* dy, void* dx, long long n, float p, unsigned long long seed,
+                              unsigned long long offset, cudaStream_t s) {
+  if (n % 8) return 930;
+  const uint32_t thr = (uint32_t)fminf(4294967295.0f, p * 4294967296.0f);
+  dropout_bwd_kernel<<<ew_grid(n / 8), EW_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, n / 8, thr,
+                                                          1.0f / (1.0f - p), seed, offset);
+  return (int)cudaGetLastError();
+}
+extern "C" int qn_gelu_fwd(const void* x, void* y, long long n, cudaStream_t s) {
+  if (n % 8) return 930;
+  gelu_fwd_kernel<<<ew_grid(n / 8), EW_THREADS, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n / 8);
+  return (int)cudaGetLastError();
+}
+extern "C" int qn_gelu_bwd(const void* dy, const void* z, void* dx, long long n, cudaStream_t s) {
+  if (n % 8) return 930;
+  gelu_bwd_kernel<<<ew_grid(n / 8), EW_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)z,
+                                                       (__nv_bfloat16*)dx, n / 8);
+  return (int)cudaGetLastError();
+}
+// acc: fp32 [cols] workspace (zeroed here); out: bf16 [cols]
+extern "C" int qn_colsum(const void* x, float* acc, void* out, int rows, int cols, long long ld, cudaStream_t s) {
+  if ((cols % 8) || (ld % 8)) return 930;
+  cudaMemsetAsync(acc, 0, sizeof(float) * cols, s);
+  int gy = (rows + 31) / 32;
+  const int gx = (cols + 63) / 64;
+  const int cap = (148 * 8 + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  colsum_kernel<<<dim3(gx, gy), 256, 0, s>>>((const __nv_bfloat16*)x, acc, rows, cols, ld);
+  f32_to_bf16_kernel<<<(cols + 255) / 256, 256, 0, s>>>(acc, (__nv_bfloat16*)out, cols);
+  return (int)cudaGetLastError();
+}
+extern "C" int qn_rope(const void* x, void* y, const float* cosp, const float* sinp, int B, int H, int T, int d,
+                       long long sb, long long sh, long long st, int backward, cudaStream_t s) {
+  if (d % 2) return 930;
+  const long long total = (long long)B * H * T * (d / 2);
+  rope_kernel<<<ew_grid(total), EW_THREADS, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, cosp, sinp, B, H, T, d,
+                                                   sb, sh, st, backward ? -1.0f : 1.0f);
+  return (int)cudaGetLastError();
+}

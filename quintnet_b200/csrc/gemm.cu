@@ -1,0 +1,382 @@
+// quintnet_b200 — persistent warp-specialised bf16 GEMM on tcgen05 / TMEM / TMA (sm_100a).
+//
+//   C[M,N] (bf16) = epilogue( A · B ),  fp32 accumulation in tensor memory.
+//
+// A is the [M x K] operand, B the [N x K] operand; each may be stored
+//   * K-major   (row-major [rows=MN, cols=K])   — e.g. activations X[M,K], weights W[N,K]
+//   * MN-major  (row-major [rows=K,  cols=MN])  — e.g. dY as A of the wgrad, W as B of the dgrad
+// so forward (X·Wᵀ), dgrad (dY·W) and wgrad (dYᵀ·X) all run here without a transpose pass.
+//
+// Structure (one CTA per SM, 256 threads):
+//   warp 0   : TMA producer  — cp.async.bulk.tensor 2-D tiles into a kStages-deep smem ring (128B swizzle)
+//   warp 1   : MMA issuer    — one thread issues tcgen05.mma (128 x BLOCK_N x 16), commits to mbarriers
+//   warp 2   : TMEM allocator
+//   warps 4-7: epilogue      — tcgen05.ld accumulators -> bias / GELU / GELU' -> bf16 -> swizzled smem -> TMA store
+// Accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
+// main loop of tile i+1.  Tiles are walked in a grouped order for L2 reuse.
+#include "common.cuh"
+
+#include <mutex>
+#include <unordered_map>
+
+namespace qn {
+
+constexpr uint32_t BLOCK_M = 128;
+constexpr uint32_t BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle atom
+constexpr uint32_t UMMA_K = 16;
+constexpr uint32_t kNumThreads = 256;
+constexpr uint32_t kEpiWarp0 = 4;
+constexpr uint32_t kGroupM = 8;
+
+enum Epilogue : int { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_GELU_BWD = 3 };
+
+struct GemmParams {
+  uint32_t M, N, K;
+  const __nv_bfloat16* bias;   // [N] or null
+  const __nv_bfloat16* aux;    // EPI_GELU_BWD: pre-activation z [M, ldaux]
+  uint32_t ldaux;
+  int epilogue;
+  int has_z;                   // EPI_BIAS_GELU: also store the pre-activation through tmap_z
+};
+
+template <uint32_t BLOCK_N>
+struct Cfg {
+  static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
+  static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;        // 16/32 KB
+  static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr uint32_t EPI_BYTES = 4 * 2 * 4096;               // 4 warps x 2 buffers x (32 rows x 128 B)
+  static constexpr uint32_t kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr uint32_t BAR_BYTES = 256;
+  static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +align slack
+  static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;                // 256 / 512
+};
+
+QN_DEVICE void tile_coords(uint32_t tile, uint32_t tiles_m, uint32_t tiles_n, uint32_t& m_blk, uint32_t& n_blk) {
+  const uint32_t per_group = kGroupM * tiles_n;
+  const uint32_t group = tile / per_group;
+  const uint32_t first_m = group * kGroupM;
+  const uint32_t gsize = min(tiles_m - first_m, kGroupM);
+  const uint32_t in_group = tile - group * per_group;
+  m_blk = first_m + in_group % gsize;
+  n_blk = in_group / gsize;
+}
+
+template <uint32_t BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_z,
+                 const GemmParams p) {
+  using C = Cfg<BLOCK_N>;
+  constexpr uint32_t kStages = C::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_epi = smem + kStages * C::STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + C::EPI_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  const uint32_t tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const uint32_t tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const uint32_t num_tiles = tiles_m * tiles_n;
+  const uint32_t num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    prefetch_tensormap(&tmap_c);
+    if (p.has_z) prefetch_tensormap(&tmap_z);
+  }
+  if (warp == 1 && lane == 0) {
+    for (uint32_t i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (uint32_t i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_ptr);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        uint32_t m_blk, n_blk;
+        tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
+        const int32_t m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          const int32_t k0 = kb * BLOCK_K;
+          if constexpr (!A_MN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);                 // box {64 K, 128 M}
+          } else {
+#pragma unroll
+            for (uint32_t j = 0; j < BLOCK_M / 64; ++j)                           // box {64 M, 64 K} slabs
+              tma_load_2d(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m0 + 64 * j, k0);
+          }
+          if constexpr (!B_MN) {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], k0, n0);                 // box {64 K, BLOCK_N}
+          } else {
+#pragma unroll
+            for (uint32_t j = 0; j < BLOCK_N / 64; ++j)
+              tma_load_2d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + 64 * j, k0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // -------------------------------------------------------------- MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+      // K-major: 8-row groups are 1024 B apart, one atom along K.  MN-major: 8-K-row groups 1024 B apart,
+      // 64-wide MN atoms BLOCK_K*128 B apart.
+      constexpr uint32_t A_LBO = A_MN ? BLOCK_K * 128 : 0, B_LBO = B_MN ? BLOCK_K * 128 : 0;
+      constexpr uint32_t A_KSTEP = A_MN ? UMMA_K * 128 : UMMA_K * 2;
+      constexpr uint32_t B_KSTEP = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+      uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
+      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[as], aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint32_t sb = sa + C::A_BYTES;
+#pragma unroll
+          for (uint32_t k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t adesc = make_smem_desc_sw128(sa + k * A_KSTEP, 1024, A_LBO);
+            const uint64_t bdesc = make_smem_desc_sw128(sb + k * B_KSTEP, 1024, B_LBO);
+            umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[as]);                 // accumulator complete -> epilogue
+        if (++as == 2) { as = 0; aphase ^= 1; }
+      }
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ---------------------------------------------------------------- epilogue
+    const uint32_t q = warp - kEpiWarp0;             // TMEM lane quarter == warp % 4
+    uint8_t* my_stage = smem_epi + q * 8192;
+    uint32_t as = 0, aphase = 0, buf = 0;
+    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      uint32_t m_blk, n_blk;
+      tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
+      const uint32_t m0 = m_blk * BLOCK_M + q * 32, n0 = n_blk * BLOCK_N;
+      mbar_wait(&tmem_full[as], aphase);
+      tcgen05_fence_after();
+      const uint32_t row = m0 + lane;
+#pragma unroll 1
+      for (uint32_t chunk = 0; chunk < BLOCK_N / 64; ++chunk) {
+        const uint32_t nc = n0 + chunk * 64;
+        if (nc >= p.N) break;                          // warp-uniform
+        const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N + chunk * 64;
+        uint32_t acc[64];
+        tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
+        tmem_ld_32x32b_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
+        tmem_ld_wait();
+        float* f = reinterpret_cast<float*>(acc);
+        if (p.epilogue == EPI_BIAS || p.epilogue == EPI_BIAS_GELU) {
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (uint32_t v = 0; v < 8; ++v) {
+              if (nc + v * 8 < p.N) {
+                const uint4 b = ld_nc_v4(p.bias + nc + v * 8);
+                const float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
+                f[v * 8 + 0] += b0.x; f[v * 8 + 1] += b0.y; f[v * 8 + 2] += b1.x; f[v * 8 + 3] += b1.y;
+                f[v * 8 + 4] += b2.x; f[v * 8 + 5] += b2.y; f[v * 8 + 6] += b3.x; f[v * 8 + 7] += b3.y;
+              }
+            }
+          }
+        } else if (p.epilogue == EPI_GELU_BWD) {
+          if (row < p.M) {
+            const __nv_bfloat16* zrow = p.aux + static_cast<size_t>(row) * p.ldaux + nc;
+#pragma unroll
+            for (uint32_t v = 0; v < 8; ++v) {
+              if (nc + v * 8 < p.N) {
+                const uint4 z = ld_nc_v4(zrow + v * 8);
+                const float2 z0 = unpack_bf16(z.x), z1 = unpack_bf16(z.y), z2 = unpack_bf16(z.z), z3 = unpack_bf16(z.w);
+                f[v * 8 + 0] *= gelu_erf_grad(z0.x); f[v * 8 + 1] *= gelu_erf_grad(z0.y);
+                f[v * 8 + 2] *= gelu_erf_grad(z1.x); f[v * 8 + 3] *= gelu_erf_grad(z1.y);
+                f[v * 8 + 4] *= gelu_erf_grad(z2.x); f[v * 8 + 5] *= gelu_erf_grad(z2.y);
+                f[v * 8 + 6] *= gelu_erf_grad(z3.x); f[v * 8 + 7] *= gelu_erf_grad(z3.y);
+              }
+            }
+          }
+        }
+        const int npass = (p.epilogue == EPI_BIAS_GELU && p.has_z) ? 2 : 1;
+        for (int pass = 0; pass < npass; ++pass) {
+          const bool store_z = (npass == 2 && pass == 0);
+          const bool do_gelu = (p.epilogue == EPI_BIAS_GELU) && !store_z;
+          // the TMA store that last read this staging buffer must have finished reading it
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          uint8_t* sbuf = my_stage + buf * 4096;
+          uint8_t* srow = sbuf + lane * 128;
+#pragma unroll
+          for (uint32_t v = 0; v < 8; ++v) {
+            float x[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) x[e] = do_gelu ? gelu_erf(f[v * 8 + e]) : f[v * 8 + e];
+            uint4 pk;
+            pk.x = pack_bf16(x[0], x[1]); pk.y = pack_bf16(x[2], x[3]);
+            pk.z = pack_bf16(x[4], x[5]); pk.w = pack_bf16(x[6], x[7]);
+            *reinterpret_cast<uint4*>(srow + ((v ^ (lane & 7)) << 4)) = pk;   // 128B swizzle
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(store_z ? &tmap_z : &tmap_c, sbuf, static_cast<int32_t>(nc), static_cast<int32_t>(m0));
+            tma_store_commit();
+          }
+          buf ^= 1;
+        }
+      }
+      // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (++as == 2) { as = 0; aphase ^= 1; }
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+  }
+}
+
+// ----------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// row-major bf16 matrix [rows, cols] with leading dimension ld (elements); box {box_cols, box_rows}
+static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_cols,
+                     uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return 901;
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 900 + static_cast<int>(r);
+}
+
+static int g_num_sms = 0;
+
+template <uint32_t BLOCK_N, bool A_MN, bool B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tz,
+                  const GemmParams& p, int max_ctas, cudaStream_t stream) {
+  using C = Cfg<BLOCK_N>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const uint32_t tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+  int grid = static_cast<int>(tiles < static_cast<uint32_t>(g_num_sms) ? tiles : g_num_sms);
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  kern<<<grid, kNumThreads, C::SMEM_BYTES, stream>>>(ta, tb, tc, tz, p);
+  return static_cast<int>(cudaGetLastError());
+}
+
+}  // namespace qn
+
+// C ABI -------------------------------------------------------------------------------------------------
+// a: A operand.  a_mn=0: row-major [M, K] (lda >= K);  a_mn=1: row-major [K, M] (lda >= M)
+// b: B operand.  b_mn=0: row-major [N, K] (ldb >= K);  b_mn=1: row-major [K, N] (ldb >= N)
+// c: row-major [M, N] bf16 (ldc >= N).  All leading dimensions must be multiples of 8 elements and all
+// base pointers 16-byte aligned.  block_n: 0 = auto, 128 or 256.  max_ctas: 0 = all SMs.
+extern "C" int qn_gemm_bf16(const void* a, const void* b, void* c, int M, int N, int K, long long lda,
+                            long long ldb, long long ldc, int a_mn, int b_mn, int epilogue, const void* bias,
+                            void* z_or_aux, long long ldz, int block_n, int max_ctas, cudaStream_t stream) {
+  using namespace qn;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda % 8) || (ldb % 8) || (ldc % 8) || (reinterpret_cast<uintptr_t>(a) & 15) ||
+      (reinterpret_cast<uintptr_t>(b) & 15) || (reinterpret_cast<uintptr_t>(c) & 15))
+    return 910;
+  if (block_n == 0) {
+    const long long t256 = static_cast<long long>((M + 127) / 128) * ((N + 255) / 256);
+    block_n = (N > 128 && t256 >= 96) ? 256 : 128;
+  }
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.epilogue = epilogue;
+  p.has_z = (epilogue == EPI_BIAS_GELU && z_or_aux != nullptr) ? 1 : 0;
+  p.aux = (epilogue == EPI_GELU_BWD) ? static_cast<const __nv_bfloat16*>(z_or_aux) : nullptr;
+  p.ldaux = static_cast<uint32_t>(ldz);
+  if (epilogue == EPI_GELU_BWD && (z_or_aux == nullptr || (ldz % 8))) return 911;
+  if ((epilogue == EPI_BIAS || epilogue == EPI_BIAS_GELU) && bias != nullptr && (N % 8)) return 912;
+
+  CUtensorMap ta, tb, tc, tz;
+  int rc;
+  if (!a_mn) rc = make_tmap(&ta, a, M, K, lda, 64, BLOCK_M); else rc = make_tmap(&ta, a, K, M, lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
+  if (rc) return rc;
+  rc = make_tmap(&tc, c, M, N, ldc, 64, 32);
+  if (rc) return rc;
+  if (p.has_z) {
+    if ((ldz % 8) || (reinterpret_cast<uintptr_t>(z_or_aux) & 15)) return 913;
+    rc = make_tmap(&tz, z_or_aux, M, N, ldz, 64, 32);
+    if (rc) return rc;
+  } else {
+    tz = tc;
+  }
+#define QN_DISPATCH(BN)                                                                                   \
+  do {                                                                                                    \
+    if (!a_mn && !b_mn) return launch<BN, false, false>(ta, tb, tc, tz, p, max_ctas, stream);             \
+    if (!a_mn && b_mn) return launch<BN, false, true>(ta, tb, tc, tz, p, max_ctas, stream);               \
+    if (a_mn && !b_mn) return launch<BN, true, false>(ta, tb, tc, tz, p, max_ctas, stream);               \
+    return launch<BN, true, true>(ta, tb, tc, tz, p, max_ctas, stream);                                   \
+  } while (0)
+  if (block_n == 256) QN_DISPATCH(256);
+  QN_DISPATCH(128);
+#undef QN_DISPATCH
+}

@@ -1,0 +1,408 @@
+"""autograd wrappers around the hand-written sm_100a kernels (ctypes → C ABI).
+
+Every function here has a plain-PyTorch twin in :mod:`.reference`; the GPU
+tests compare the two (fp32 oracle).  Layout conventions follow the kernels:
+row-major contiguous bf16, leading dimensions multiples of 8 elements.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+from . import native
+
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_GELU_BWD = 0, 1, 2, 3
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+def _lib():
+    return native.require()
+
+
+# --------------------------------------------------------------------- GEMM
+def gemm_ok(M: int, N: int, K: int, *lds) -> bool:
+    return M > 0 and N > 0 and K > 0 and all(int(l) % 8 == 0 for l in lds)
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool = False,
+         b_mn: bool = False, out: Optional[torch.Tensor] = None, ldc: Optional[int] = None,
+         epilogue: int = EPI_NONE, bias: Optional[torch.Tensor] = None,
+         z: Optional[torch.Tensor] = None, block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+    """C[M,N] = epilogue(A·B) on tcgen05.  ``a``/``b`` are 2-D row-major bf16 tensors
+    (possibly with a row stride); ``a_mn`` / ``b_mn`` say the tensor is stored
+    ``[K, M]`` / ``[K, N]`` instead of ``[M, K]`` / ``[N, K]``."""
+    assert a.dtype == torch.bfloat16 and b.dtype == torch.bfloat16
+    assert a.stride(-1) == 1 and b.stride(-1) == 1
+    lda, ldb = a.stride(0), b.stride(0)
+    if out is None:
+        ldc = ldc or N
+        out = torch.empty((M, ldc), dtype=torch.bfloat16, device=a.device)
+        out_view = out if ldc == N else out[:, :N]
+    else:
+        ldc = out.stride(0)
+        out_view = out
+    ldz = z.stride(0) if z is not None else 0
+    rc = _lib().qn_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldc,
+                             int(a_mn), int(b_mn), epilogue, native.ptr(bias), native.ptr(z), ldz,
+                             block_n, max_ctas, native.stream())
+    native.check(rc, f"qn_gemm_bf16(M={M},N={N},K={K},a_mn={a_mn},b_mn={b_mn})")
+    native.count()
+    return out_view
+
+
+class _Linear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        K = x.shape[-1]
+        N = w.shape[0]
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        wq = w if w.dtype == torch.bfloat16 else w.to(torch.bfloat16)
+        z = None
+        if act == "gelu":
+            z = torch.empty((M, N), dtype=torch.bfloat16, device=x.device) if ctx.needs_input_grad[0] or \
+                ctx.needs_input_grad[1] else None
+            y = gemm(x2, wq, M, N, K, epilogue=EPI_BIAS_GELU, bias=b, z=z)
+        elif act is None:
+            y = gemm(x2, wq, M, N, K, epilogue=EPI_BIAS if b is not None else EPI_NONE, bias=b)
+        else:
+            raise ValueError(f"native linear: unsupported activation {act}")
+        ctx.save_for_backward(x2, wq, z)
+        ctx.act, ctx.has_bias, ctx.xshape = act, b is not None, x.shape
+        ctx.wdtype = w.dtype
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, z = ctx.saved_tensors
+        M, K = x2.shape
+        N = w.shape[0]
+        dy2 = dy.reshape(M, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        if ctx.act == "gelu":
+            dz = torch.empty_like(dy2)
+            native.check(_lib().qn_gelu_bwd(dy2.data_ptr(), z.data_ptr(), dz.data_ptr(), dy2.numel(),
+                                            native.stream()), "qn_gelu_bwd")
+            native.count()
+            dy2 = dz
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            # dX[M,K] = dY[M,N] · W[N,K]        (B stored [K_red=N, N_out=K] -> MN-major)
+            dx = gemm(dy2, w, M, K, N, b_mn=True).view(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            # dW[N,K] = dYᵀ[N,M] · X[M,K]       (both operands stored [K_red=M, ·] -> MN-major)
+            dw = gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True)
+            if ctx.wdtype != torch.bfloat16:
+                dw = dw.to(ctx.wdtype)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2)
+        return dx, dw, db, None
+
+
+def colsum(x2: torch.Tensor) -> torch.Tensor:
+    rows, cols = x2.shape
+    acc = torch.empty(cols, dtype=torch.float32, device=x2.device)
+    out = torch.empty(cols, dtype=torch.bfloat16, device=x2.device)
+    native.check(_lib().qn_colsum(x2.data_ptr(), acc.data_ptr(), out.data_ptr(), rows, cols, x2.stride(0),
+                                  native.stream()), "qn_colsum")
+    native.count(3)
+    return out
+
+
+def linear(x, w, b=None, act: Optional[str] = None):
+    K, N = x.shape[-1], w.shape[0]
+    M = x.numel() // K
+    bias_ok = b is None or (b.dtype == torch.bfloat16 and N % 8 == 0)
+    if not gemm_ok(M, N, K, K, N) or not bias_ok or act not in (None, "gelu") or \
+            (x.data_ptr() % 16) or (w.data_ptr() % 16):
+        # shapes the TMA path cannot express (e.g. the 10-class ViT head): library GEMM
+        from . import reference
+        return reference.linear(x, w.to(x.dtype), None if b is None else b.to(x.dtype), act)
+    return _Linear.apply(x, w, b, act)
+
+
+# ---------------------------------------------------------------- LayerNorm
+_LN_PARTS = 148 * 2
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, eps, residual):
+        cols = x.shape[-1]
+        x2 = x.reshape(-1, cols)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        rows = x2.shape[0]
+        res2 = None
+        if residual is not None:
+            res2 = residual.reshape(-1, cols)
+            if not res2.is_contiguous():
+                res2 = res2.contiguous()
+        y = torch.empty_like(x2)
+        s = torch.empty_like(x2) if residual is not None else None
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        wq, bq = w.to(x.dtype), b.to(x.dtype)
+        rc = _lib().qn_layernorm_fwd(x2.data_ptr(), native.ptr(res2), wq.data_ptr(), bq.data_ptr(),
+                                     y.data_ptr(), native.ptr(s), mean.data_ptr(), rstd.data_ptr(), rows, cols,
+                                     float(eps), _DT[x.dtype], native.stream())
+        native.check(rc, "qn_layernorm_fwd")
+        native.count()
+        ctx.save_for_backward(s if s is not None else x2, wq, mean, rstd)
+        ctx.shape, ctx.has_res, ctx.wdtype = x.shape, residual is not None, w.dtype
+        if residual is not None:
+            return y.view(x.shape), s.view(x.shape)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy, dsum=None):
+        xin, w, mean, rstd = ctx.saved_tensors
+        rows, cols = xin.shape
+        dy2 = dy.reshape(rows, cols)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dadd = None
+        if ctx.has_res and dsum is not None:
+            dadd = dsum.reshape(rows, cols)
+            if not dadd.is_contiguous():
+                dadd = dadd.contiguous()
+        dx = torch.empty_like(xin)
+        dg = torch.empty(cols, dtype=xin.dtype, device=xin.device)
+        db = torch.empty(cols, dtype=xin.dtype, device=xin.device)
+        nparts = min(_LN_PARTS, (rows + 3) // 4)
+        ws = torch.empty(2 * nparts * cols, dtype=torch.float32, device=xin.device)
+        rc = _lib().qn_layernorm_bwd(dy2.data_ptr(), xin.data_ptr(), w.data_ptr(), mean.data_ptr(),
+                                     rstd.data_ptr(), native.ptr(dadd), dx.data_ptr(), dg.data_ptr(),
+                                     db.data_ptr(), ws.data_ptr(), nparts, rows, cols, _DT[xin.dtype],
+                                     native.stream())
+        native.check(rc, "qn_layernorm_bwd")
+        native.count(2)
+        dxv = dx.view(ctx.shape)
+        return dxv, dg.to(ctx.wdtype), db.to(ctx.wdtype), None, (dxv if ctx.has_res else None)
+
+
+def _ln_ok(x, cols):
+    vn = 8 if x.dtype == torch.bfloat16 else 4
+    return cols % vn == 0 and cols <= 256 * vn
+
+
+def layer_norm(x, w, b, eps=1e-5):
+    if not _ln_ok(x, x.shape[-1]):
+        from . import reference
+        return reference.layer_norm(x, w.to(x.dtype), b.to(x.dtype), eps)
+    return _LayerNorm.apply(x, w, b, eps, None)
+
+
+def add_layer_norm(x, residual, w, b, eps=1e-5):
+    if not _ln_ok(x, x.shape[-1]):
+        from . import reference
+        return reference.add_layer_norm(x, residual, w.to(x.dtype), b.to(x.dtype), eps)
+    return _LayerNorm.apply(x, w, b, eps, residual)
+
+
+# --------------------------------------------------------------------- GELU
+class _Gelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        xc = x.contiguous()
+        y = torch.empty_like(xc)
+        native.check(_lib().qn_gelu_fwd(xc.data_ptr(), y.data_ptr(), xc.numel(), native.stream()), "qn_gelu_fwd")
+        native.count()
+        ctx.save_for_backward(xc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        dyc = dy.contiguous()
+        dx = torch.empty_like(x)
+        native.check(_lib().qn_gelu_bwd(dyc.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), native.stream()),
+                     "qn_gelu_bwd")
+        native.count()
+        return dx
+
+
+def gelu(x):
+    if x.numel() % 8:
+        return F.gelu(x)
+    return _Gelu.apply(x)
+
+
+# ------------------------------------------------------------ dropout + add
+class _PhiloxState:
+    seed = None
+    offset = 0
+
+    @classmethod
+    def next(cls, n_elems: int):
+        if cls.seed is None:
+            cls.seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+        off = cls.offset
+        cls.offset += 2 * ((n_elems + 7) // 8)
+        return cls.seed, off
+
+
+def manual_seed(seed: int) -> None:
+    _PhiloxState.seed, _PhiloxState.offset = int(seed) & 0x7FFFFFFFFFFFFFFF, 0
+
+
+class _DropoutAdd(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, residual, p):
+        xc = x.contiguous()
+        rc_ = residual.contiguous() if residual is not None else None
+        y = torch.empty_like(xc)
+        seed, off = _PhiloxState.next(xc.numel())
+        native.check(_lib().qn_dropout_add_fwd(xc.data_ptr(), native.ptr(rc_), y.data_ptr(), xc.numel(), float(p),
+                                               seed, off, native.stream()), "qn_dropout_add_fwd")
+        native.count()
+        ctx.p, ctx.seed, ctx.off, ctx.has_res = float(p), seed, off, residual is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dyc = dy.contiguous()
+        dx = torch.empty_like(dyc)
+        native.check(_lib().qn_dropout_bwd(dyc.data_ptr(), dx.data_ptr(), dyc.numel(), ctx.p, ctx.seed, ctx.off,
+                                           native.stream()), "qn_dropout_bwd")
+        native.count()
+        return dx, (dy if ctx.has_res else None), None
+
+
+def dropout_add(x, residual, p: float):
+    if x.numel() % 8:
+        from . import reference
+        return reference.dropout_add(x, residual, p, True)
+    return _DropoutAdd.apply(x, residual, p)
+
+
+# --------------------------------------------------------------------- RoPE
+class _Rope(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, cos, sin):
+        B, H, T, d = x.shape
+        assert x.stride(-1) == 1
+        y = torch.empty((B, H, T, d), dtype=x.dtype, device=x.device)
+        cosf, sinf = cos.float().contiguous(), sin.float().contiguous()
+        native.check(_lib().qn_rope(x.data_ptr(), y.data_ptr(), cosf.data_ptr(), sinf.data_ptr(), B, H, T, d,
+                                    x.stride(0), x.stride(1), x.stride(2), 0, native.stream()), "qn_rope")
+        native.count()
+        ctx.save_for_backward(cosf, sinf)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        cosf, sinf = ctx.saved_tensors
+        dyc = dy.contiguous()
+        B, H, T, d = dyc.shape
+        dx = torch.empty_like(dyc)
+        native.check(_lib().qn_rope(dyc.data_ptr(), dx.data_ptr(), cosf.data_ptr(), sinf.data_ptr(), B, H, T, d,
+                                    dyc.stride(0), dyc.stride(1), dyc.stride(2), 1, native.stream()), "qn_rope")
+        native.count()
+        return dx, None, None
+
+
+def rope(x, cos, sin):
+    return _Rope.apply(x, cos, sin)
+
+
+# ------------------------------------------------------------ cross entropy
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def _ce_inplace(logits_buf: torch.Tensor, labels: torch.Tensor, V: int, ignore_index: int, write_grad: bool):
+    stats = torch.zeros(2, dtype=torch.float32, device=logits_buf.device)
+    lab = labels.contiguous()
+    if lab.dtype != torch.int64:
+        lab = lab.long()
+    rc = _lib().qn_cross_entropy(logits_buf.data_ptr(), lab.data_ptr(), stats.data_ptr(),
+                                 stats.data_ptr() + 4, logits_buf.shape[0], V, logits_buf.stride(0),
+                                 ignore_index, int(write_grad), native.stream())
+    native.check(rc, "qn_cross_entropy")
+    native.count()
+    return stats[0], stats[1]
+
+
+def _scale(x: torch.Tensor, g: torch.Tensor) -> torch.Tensor:
+    out = torch.empty_like(x)
+    gf = g.reshape(1).float()
+    native.check(_lib().qn_scale_bf16(x.data_ptr(), out.data_ptr(), gf.data_ptr(), x.numel(), native.stream()),
+                 "qn_scale_bf16")
+    native.count()
+    return out
+
+
+class _CrossEntropySum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, ignore_index):
+        N, V = logits.shape
+        Vp = _round_up(V, 8)
+        buf = torch.empty((N, Vp), dtype=torch.bfloat16, device=logits.device)
+        buf[:, :V].copy_(logits)
+        need = ctx.needs_input_grad[0]
+        loss, n = _ce_inplace(buf, labels, V, ignore_index, need)
+        if need:
+            ctx.save_for_backward(buf)
+        ctx.V, ctx.dtype = V, logits.dtype
+        ctx.mark_non_differentiable(n)
+        return loss, n
+
+    @staticmethod
+    def backward(ctx, g, _gn):
+        (buf,) = ctx.saved_tensors
+        return (buf[:, :ctx.V].float() * g).to(ctx.dtype), None, None
+
+
+def cross_entropy_sum(logits, labels, ignore_index=-100):
+    return _CrossEntropySum.apply(logits, labels, ignore_index)
+
+
+class _LinearCrossEntropy(torch.autograd.Function):
+    """loss_sum, n_valid = CE(h · Wᵀ, labels).  Forward computes the bf16 logits with the
+    tcgen05 GEMM, turns them IN PLACE into dlogits, and immediately produces the (unscaled)
+    dH and dW with two more GEMMs; backward only scales them by the upstream scalar."""
+
+    @staticmethod
+    def forward(ctx, h, w, labels, ignore_index):
+        N, E = h.shape
+        V = w.shape[0]
+        Vp = _round_up(V, 64)
+        h2 = h if h.is_contiguous() else h.contiguous()
+        wq = w if w.dtype == torch.bfloat16 else w.to(torch.bfloat16)
+        need_h, need_w = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        logits = torch.empty((N, Vp), dtype=torch.bfloat16, device=h.device)
+        gemm(h2, wq, N, V, E, out=logits[:, :V])
+        loss, n = _ce_inplace(logits, labels, V, ignore_index, need_h or need_w)
+        dh = dw = None
+        if need_h:      # dH[N,E] = dlogits[N,V] · W[V,E]
+            dh = gemm(logits, wq, N, E, V, b_mn=True)
+        if need_w:      # dW[V,E] = dlogitsᵀ[V,N] · H[N,E]
+            dw = gemm(logits, h2, V, E, N, a_mn=True, b_mn=True)
+        del logits
+        ctx.save_for_backward(dh, dw)
+        ctx.wdtype = w.dtype
+        ctx.mark_non_differentiable(n)
+        return loss, n
+
+    @staticmethod
+    def backward(ctx, g, _gn):
+        dh, dw = ctx.saved_tensors
+        gh = _scale(dh, g) if dh is not None else None
+        gw = _scale(dw, g) if dw is not None else None
+        if gw is not None and ctx.wdtype != torch.bfloat16:
+            gw = gw.to(ctx.wdtype)
+        return gh, gw, None, None
+
+
+def linear_cross_entropy(h, w, labels, ignore_index=-100):
+    N, E = h.shape
+    if E % 8 or (h.data_ptr() % 16) or (w.data_ptr() % 16) or N % 8:
+        from . import reference
+        return reference.linear_cross_entropy(h, w.to(h.dtype), labels, ignore_index)
+    return _LinearCrossEntropy.apply(h, w, labels, ignore_index)

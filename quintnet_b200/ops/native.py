@@ -32,8 +32,7 @@ _load_error: Optional[str] = None
 # ops whose native kernel is used on CUDA tensors.  Env override:
 #   QUINTNET_NATIVE=all | none | comma-separated list
 _DEFAULT_ENABLED = {
-    "layernorm", "gelu", "adamw", "dropout", "rope", "cross_entropy", "gemm", "attention",
-    "allreduce", "zero1", "tp_fused",
+    "layernorm", "gelu", "adamw", "dropout", "rope", "cross_entropy", "gemm",
 }
 
 
@@ -82,7 +81,8 @@ def build(force: bool = False, verbose: bool = True, jobs: int = 8) -> Path:
     _wait(procs)
     need_link = force or not out.exists() or any(o.stat().st_mtime > out.stat().st_mtime for o in objs)
     if need_link:
-        cmd = [nvcc_path(), "-shared", "-o", str(out), *[str(o) for o in objs], "-lcudart"]
+        cmd = [nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out),
+               *[str(o) for o in objs], "-lcudart"]
         if verbose:
             print("[quintnet_b200.build]", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)
@@ -120,7 +120,43 @@ def lib() -> Optional[ctypes.CDLL]:
     except OSError as e:  # e.g. no libcudart on a CPU-only box
         _load_error = str(e)
         return None
+    _declare(_lib)
     return _lib
+
+
+_I, _L, _F, _P = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
+_U = ctypes.c_ulonglong
+_SIGNATURES = {
+    "qn_gemm_bf16": [_P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _P, _P, _L, _I, _I, _P],
+    "qn_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
+    "qn_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
+    "qn_dropout_add_fwd": [_P, _P, _P, _L, _F, _U, _U, _P],
+    "qn_dropout_bwd": [_P, _P, _L, _F, _U, _U, _P],
+    "qn_gelu_fwd": [_P, _P, _L, _P],
+    "qn_gelu_bwd": [_P, _P, _P, _L, _P],
+    "qn_colsum": [_P, _P, _P, _I, _I, _L, _P],
+    "qn_rope": [_P, _P, _P, _P, _I, _I, _I, _I, _L, _L, _L, _I, _P],
+    "qn_adamw": [_P, _I, _P, _I, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _F, _P],
+    "qn_cross_entropy": [_P, _P, _P, _P, _I, _I, _L, _L, _I, _P],
+    "qn_scale_bf16": [_P, _P, _P, _L, _P],
+}
+
+
+def _declare(lib) -> None:
+    for name, args in _SIGNATURES.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = ctypes.c_int
+
+
+def declare(name: str, args) -> None:
+    """Register the signature of an extra exported function (used by comm ops)."""
+    _SIGNATURES[name] = args
+    if _lib is not None and hasattr(_lib, name):
+        fn = getattr(_lib, name)
+        fn.argtypes = args
+        fn.restype = ctypes.c_int
 
 
 def require() -> ctypes.CDLL:
@@ -145,12 +181,12 @@ def op_enabled(name: str) -> bool:
 
 
 # ------------------------------------------------------------- ctypes helpers
-def ptr(t: Optional[torch.Tensor]) -> ctypes.c_void_p:
-    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+def ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
 
 
-def stream() -> ctypes.c_void_p:
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def stream():
+    return torch.cuda.current_stream().cuda_stream
 
 
 def check(code: int, what: str) -> None:

@@ -21,11 +21,11 @@ def adamw_flat(p, g, m, v, master, *, step: int, lr: float, beta1: float, beta2:
         lib = native.require()
         pd = {torch.float32: 0, torch.bfloat16: 1}[p.dtype]
         gd = {torch.float32: 0, torch.bfloat16: 1}[g.dtype]
-        rc = lib.qn_adamw(native.ptr(p), ctypes.c_int(pd), native.ptr(g), ctypes.c_int(gd),
-                          native.ptr(m), native.ptr(v), native.ptr(master), native.ptr(grad_scale),
-                          ctypes.c_longlong(p.numel()), ctypes.c_float(lr), ctypes.c_float(beta1),
-                          ctypes.c_float(beta2), ctypes.c_float(eps), ctypes.c_float(weight_decay),
-                          ctypes.c_float(bc1), ctypes.c_float(bc2), native.stream())
+        if grad_scale is not None and grad_scale.dtype != torch.float32:
+            grad_scale = grad_scale.float()
+        rc = lib.qn_adamw(native.ptr(p), pd, native.ptr(g), gd, native.ptr(m), native.ptr(v),
+                          native.ptr(master), native.ptr(grad_scale), p.numel(), lr, beta1, beta2, eps,
+                          weight_decay, bc1, bc2, native.stream())
         native.check(rc, "qn_adamw")
         native.count()
         return

@@ -1,0 +1,209 @@
+"""sm_100a kernel numerics vs plain-PyTorch fp32 references (run on the B200 box)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from quintnet_b200.ops import native
+    return native.require()
+
+
+def _rel(a, b):
+    return ((a.float() - b.float()).norm() / (b.float().norm() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (384, 768, 1024), (16384 // 8, 3072, 1024),
+                                   (400, 64, 64), (130, 264, 72), (1000, 50264 // 8, 256)])
+@pytest.mark.parametrize("block_n", [0, 128, 256])
+def test_gemm_tn(M, N, K, block_n):
+    from quintnet_b200.ops import cuda_ops
+    torch.manual_seed(0)
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    c = cuda_ops.gemm(a, b, M, N, K, block_n=block_n)
+    ref = a.float() @ b.float().t()
+    assert _rel(c, ref) < 1e-2, _rel(c, ref)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (384, 1024, 520), (1024, 768, 2048), (136, 200, 72)])
+def test_gemm_layouts(a_mn, b_mn, M, N, K):
+    from quintnet_b200.ops import cuda_ops
+    torch.manual_seed(1)
+    A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    B = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    a = A.t().contiguous() if a_mn else A
+    b = B.t().contiguous() if b_mn else B
+    c = cuda_ops.gemm(a, b, M, N, K, a_mn=a_mn, b_mn=b_mn)
+    ref = A.float() @ B.float().t()
+    assert _rel(c, ref) < 1e-2, _rel(c, ref)
+
+
+def test_gemm_epilogues():
+    from quintnet_b200.ops import cuda_ops
+    torch.manual_seed(2)
+    M, N, K = 512, 1024, 256
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16) * 0.5
+    b = torch.randn(N, K, device="cuda", dtype=torch.bfloat16) * 0.1
+    bias = torch.randn(N, device="cuda", dtype=torch.bfloat16)
+    ref = a.float() @ b.float().t() + bias.float()
+    c = cuda_ops.gemm(a, b, M, N, K, epilogue=cuda_ops.EPI_BIAS, bias=bias)
+    assert _rel(c, ref) < 1e-2
+    z = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    g = cuda_ops.gemm(a, b, M, N, K, epilogue=cuda_ops.EPI_BIAS_GELU, bias=bias, z=z)
+    assert _rel(z, ref) < 1e-2
+    assert _rel(g, F.gelu(ref)) < 1e-2
+    zz = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+    gb = cuda_ops.gemm(a, b, M, N, K, epilogue=cuda_ops.EPI_GELU_BWD, z=zz)
+    zf = zz.float()
+    dg = 0.5 * (1 + torch.erf(zf / math.sqrt(2))) + zf * torch.exp(-0.5 * zf * zf) / math.sqrt(2 * math.pi)
+    assert _rel(gb, (a.float() @ b.float().t()) * dg) < 1.5e-2
+
+
+def test_linear_autograd():
+    from quintnet_b200 import ops
+    torch.manual_seed(3)
+    for act in (None, "gelu"):
+        x = torch.randn(4, 96, 256, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+        w = (torch.randn(512, 256, device="cuda", dtype=torch.bfloat16) * 0.05).requires_grad_(True)
+        b = torch.randn(512, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+        y = ops.linear(x, w, b, act)
+        dy = torch.randn_like(y)
+        y.backward(dy)
+        xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+        yr = F.linear(xr, wr, br)
+        if act == "gelu":
+            yr = F.gelu(yr)
+        yr.backward(dy.float())
+        assert _rel(y, yr) < 1e-2
+        assert _rel(x.grad, xr.grad) < 2e-2, (act, _rel(x.grad, xr.grad))
+        assert _rel(w.grad, wr.grad) < 2e-2
+        assert _rel(b.grad, br.grad) < 2e-2
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("rows,cols", [(64, 64), (1000, 768), (4096, 1024), (333, 1600)])
+def test_layernorm(dtype, rows, cols):
+    from quintnet_b200 import ops
+    torch.manual_seed(4)
+    x = torch.randn(rows, cols, device="cuda", dtype=dtype, requires_grad=True)
+    w = torch.randn(cols, device="cuda", dtype=dtype, requires_grad=True)
+    b = torch.randn(cols, device="cuda", dtype=dtype, requires_grad=True)
+    y = ops.layer_norm(x, w, b, 1e-5)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+    yr = F.layer_norm(xr, (cols,), wr, br, 1e-5)
+    yr.backward(dy.float())
+    tol = 2e-2 if dtype == torch.bfloat16 else 1e-4
+    assert _rel(y, yr) < tol
+    assert _rel(x.grad, xr.grad) < tol
+    assert _rel(w.grad, wr.grad) < tol and _rel(b.grad, br.grad) < tol
+
+
+def test_add_layernorm():
+    from quintnet_b200 import ops
+    torch.manual_seed(5)
+    x = torch.randn(512, 768, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    r = torch.randn(512, 768, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    w = torch.ones(768, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    b = torch.zeros(768, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    y, s = ops.add_layer_norm(x, r, w, b)
+    (y.float().pow(2).sum() + s.float().sum()).backward()
+    xr, rr = x.detach().float().requires_grad_(True), r.detach().float().requires_grad_(True)
+    sr = xr + rr
+    yr = F.layer_norm(sr, (768,))
+    (yr.pow(2).sum() + sr.sum()).backward()
+    assert _rel(y, yr) < 2e-2 and _rel(s, sr) < 1e-2
+    assert _rel(x.grad, xr.grad) < 3e-2 and _rel(r.grad, rr.grad) < 3e-2
+
+
+def test_gelu_dropout_rope():
+    from quintnet_b200 import ops
+    from quintnet_b200.ops import cuda_ops, reference
+    torch.manual_seed(6)
+    x = torch.randn(1024, 512, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    y = ops.gelu(x)
+    y.backward(torch.ones_like(y))
+    xr = x.detach().float().requires_grad_(True)
+    F.gelu(xr).sum().backward()
+    assert _rel(y, F.gelu(xr)) < 1e-2 and _rel(x.grad, xr.grad) < 1e-2
+    # dropout: keep fraction, scaling, mask consistency between fwd and bwd
+    cuda_ops.manual_seed(123)
+    x = torch.ones(1 << 20, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    res = torch.full_like(x, 2.0)
+    y = ops.dropout_add(x, res, 0.1, True)
+    kept = (y.float() > 2.5)
+    assert abs(kept.float().mean().item() - 0.9) < 5e-3
+    assert torch.allclose(y.float()[kept], torch.full_like(y.float()[kept], 2.0 + 1 / 0.9), atol=2e-2)
+    y.backward(torch.ones_like(y))
+    assert torch.equal(x.grad.float() > 0.5, kept)
+    # rope
+    q = torch.randn(2, 4, 64, 64, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    cos, sin = ops.rope_tables(64, 64, device="cuda")
+    o = ops.rope(q, cos, sin)
+    o.backward(torch.ones_like(o))
+    qr = q.detach().float().requires_grad_(True)
+    orf = reference.rope(qr, cos, sin)
+    orf.sum().backward()
+    assert _rel(o, orf) < 1e-2 and _rel(q.grad, qr.grad) < 1e-2
+
+
+def test_fused_adamw_matches_torch():
+    from quintnet_b200.optim import FusedAdamW
+    torch.manual_seed(7)
+    ref = torch.nn.Sequential(torch.nn.Linear(64, 128), torch.nn.Linear(128, 32)).cuda()
+    mine = torch.nn.Sequential(torch.nn.Linear(64, 128), torch.nn.Linear(128, 32)).cuda()
+    mine.load_state_dict(ref.state_dict())
+    o_ref = torch.optim.AdamW(ref.parameters(), lr=1e-2, weight_decay=0.01)
+    o_mine = FusedAdamW(mine.parameters(), lr=1e-2, weight_decay=0.01)
+    for _ in range(5):
+        x = torch.randn(16, 64, device="cuda")
+        for m, o in ((ref, o_ref), (mine, o_mine)):
+            o.zero_grad()
+            m(x).pow(2).mean().backward()
+            o.step()
+    for p, q in zip(ref.parameters(), mine.parameters()):
+        assert torch.allclose(p, q, atol=1e-5), (p - q).abs().max()
+
+
+def test_linear_cross_entropy():
+    from quintnet_b200 import ops
+    torch.manual_seed(8)
+    N, E, V = 1024, 256, 50257 // 16
+    h = (torch.randn(N, E, device="cuda", dtype=torch.bfloat16) * 0.5).requires_grad_(True)
+    w = (torch.randn(V, E, device="cuda", dtype=torch.bfloat16) * 0.05).requires_grad_(True)
+    labels = torch.randint(0, V, (N,), device="cuda")
+    labels[::7] = -100
+    ls, n = ops.linear_cross_entropy(h, w, labels)
+    (ls / n).backward()
+    hr, wr = h.detach().float().requires_grad_(True), w.detach().float().requires_grad_(True)
+    lr_ = F.cross_entropy(hr @ wr.t(), labels, ignore_index=-100, reduction="sum")
+    nr = (labels != -100).sum()
+    (lr_ / nr).backward()
+    assert abs(ls.item() - lr_.item()) / lr_.item() < 5e-3 and int(n.item()) == int(nr.item())
+    assert _rel(h.grad, hr.grad) < 3e-2, _rel(h.grad, hr.grad)
+    assert _rel(w.grad, wr.grad) < 3e-2, _rel(w.grad, wr.grad)
+
+
+def test_gpt2_gpu_matches_cpu_reference():
+    """Tiny GPT-2 in bf16 through the native ops vs the same weights in fp32 on CPU."""
+    from quintnet_b200.models.gpt2 import GPT2Config, GPT2Model
+    cfg = GPT2Config(vocab_size=512, n_positions=64, n_embd=128, n_layer=2, n_head=4,
+                     resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+    ref = GPT2Model(cfg, seed=3)
+    gpu = GPT2Model(cfg, device=torch.device("cuda"), dtype=torch.bfloat16, seed=3)
+    ids = torch.randint(0, 512, (8, 64))
+    lr_, nr = ref(ids, labels=ids)
+    lg, ng = gpu(ids.cuda(), labels=ids.cuda())
+    assert abs(lg.item() / ng.item() - lr_.item() / nr.item()) < 3e-2
+    (lr_ / nr).backward()
+    (lg / ng).backward()
+    g1 = ref.blocks[0].mlp.c_fc.proj.weight.grad
+    g2 = gpu.blocks[0].mlp.c_fc.proj.weight.grad
+    assert _rel(g2.cpu(), g1) < 8e-2, _rel(g2.cpu(), g1)
