@@ -1,0 +1,270 @@
+// quintnet_b200 — in-kernel collectives over NVLink peer memory / NVLS multicast (sm_100a).
+//
+// Every buffer is "symmetric": the same allocation exists on every rank of the group and each rank has all
+// peers' device pointers mapped (ops/symm.py).  The kernels issue the communication themselves:
+//   K1  all_reduce      : two-shot — rank r reduces slice r from every peer (fp32 accumulation) and stores
+//                         the result straight into every peer's buffer; or, with an NVLS multicast mapping,
+//                         one multimem.ld_reduce + multimem.st per 16 bytes (reduction inside the NVSwitch).
+//   K2a reduce_scatter  : + 1/P scale + masked squared-norm partial (ZeRO-1 phase A)
+//   K2b adamw_allgather : AdamW on the local fp32 shard, updated bf16/fp32 parameters pushed into every
+//                         peer's parameter buffer (ZeRO-1 phase B)
+// Cross-rank ordering uses per-block release/acquire flags in a symmetric signal pad with a monotonically
+// increasing epoch (no host round-trips, no NCCL).  A watchdog turns a lost peer into a trap.
+#include "common.cuh"
+
+namespace qn {
+
+constexpr int COMM_MAX_RANKS = 8;
+constexpr int COMM_THREADS = 512;
+
+struct PeerPtrs {
+  void* buf[COMM_MAX_RANKS];        // peer r's mapping of the data buffer (same offset applied by caller)
+  uint32_t* sig[COMM_MAX_RANKS];    // peer r's signal pad: [num_blocks][COMM_MAX_RANKS] uint32
+  void* mc;                         // NVLS multicast address of the data buffer (or null)
+  int rank, world;
+};
+
+// All ranks' block `blockIdx.x` meet here.  slot layout: sig[dst][block][src].
+QN_DEVICE void block_barrier(const PeerPtrs& pp, uint32_t epoch) {
+  __syncthreads();
+  if (threadIdx.x < pp.world) {
+    const int peer = threadIdx.x;
+    __threadfence_system();
+    st_release_sys(pp.sig[peer] + blockIdx.x * COMM_MAX_RANKS + pp.rank, epoch);
+    wait_flag_ge(pp.sig[pp.rank] + blockIdx.x * COMM_MAX_RANKS + peer, epoch);
+  }
+  __syncthreads();
+}
+
+template <typename T> struct V16;
+template <> struct V16<float> {
+  static constexpr int N = 4;
+  static QN_DEVICE void unpack(const uint4& u, float (&f)[4]) {
+    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+  }
+  static QN_DEVICE uint4 pack(const float (&f)[4]) {
+    return make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+  }
+  static QN_DEVICE uint4 mc_reduce(const void* p) { return multimem_ld_reduce_f32x4(p); }
+};
+template <> struct V16<__nv_bfloat16> {
+  static constexpr int N = 8;
+  static QN_DEVICE void unpack(const uint4& u, float (&f)[8]) {
+    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), c = unpack_bf16(u.z), d = unpack_bf16(u.w);
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+  }
+  static QN_DEVICE uint4 pack(const float (&f)[8]) {
+    return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+  }
+  static QN_DEVICE uint4 mc_reduce(const void* p) { return multimem_ld_reduce_bf16x8(p); }
+};
+
+// ------------------------------------------------------------------------------------------------ K1
+// In-place all-reduce(+scale) of n elements (n % (world * VecN) == 0).
+template <typename T, bool USE_MC>
+__global__ void __launch_bounds__(COMM_THREADS)
+allreduce_kernel(PeerPtrs pp, long long n, float scale, uint32_t epoch) {
+  constexpr int VN = V16<T>::N;
+  block_barrier(pp, epoch);                                  // every rank's input is complete
+  const long long nvec = n / VN;
+  const long long per_rank = nvec / pp.world;
+  const long long lo = per_rank * pp.rank;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < per_rank; i += stride) {
+    const long long v = lo + i;
+    float acc[VN];
+    if constexpr (USE_MC) {
+      const uint4 r = V16<T>::mc_reduce(reinterpret_cast<const uint4*>(pp.mc) + v);
+      V16<T>::unpack(r, acc);
+    } else {
+#pragma unroll
+      for (int e = 0; e < VN; ++e) acc[e] = 0.f;
+#pragma unroll
+      for (int p = 0; p < COMM_MAX_RANKS; ++p) {
+        if (p < pp.world) {
+          const int src = (pp.rank + p) % pp.world;          // stagger peers across ranks
+          float f[VN];
+          V16<T>::unpack(ld_cv_v4(reinterpret_cast<const uint4*>(pp.buf[src]) + v), f);
+#pragma unroll
+          for (int e = 0; e < VN; ++e) acc[e] += f[e];
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < VN; ++e) acc[e] *= scale;
+    const uint4 out = V16<T>::pack(acc);
+    if constexpr (USE_MC) {
+      multimem_st_v4(reinterpret_cast<uint4*>(pp.mc) + v, out);
+    } else {
+#pragma unroll
+      for (int p = 0; p < COMM_MAX_RANKS; ++p)
+        if (p < pp.world) st_v4(reinterpret_cast<uint4*>(pp.buf[(pp.rank + p) % pp.world]) + v, out);
+    }
+  }
+  block_barrier(pp, epoch + 1);                              // every rank's writes have landed everywhere
+}
+
+// ----------------------------------------------------------------------------------------------- K2a
+// out[i] = scale * sum_p grad_p[lo + i]  (fp32), i in this rank's shard;  sq += sum (out*mask)^2
+template <typename T>
+__global__ void __launch_bounds__(COMM_THREADS)
+reduce_scatter_sqnorm_kernel(PeerPtrs pp, float* __restrict__ out, const float* __restrict__ mask,
+                             float* __restrict__ sq, long long n, float scale, uint32_t epoch) {
+  constexpr int VN = V16<T>::N;
+  __shared__ float red[COMM_THREADS / 32];
+  block_barrier(pp, epoch);
+  const long long per_rank = n / pp.world;                   // elements
+  const long long nvec = per_rank / VN;
+  const long long lo_vec = (per_rank * pp.rank) / VN;
+  float local = 0.f;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+    float acc[VN];
+#pragma unroll
+    for (int e = 0; e < VN; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int p = 0; p < COMM_MAX_RANKS; ++p) {
+      if (p < pp.world) {
+        const int src = (pp.rank + p) % pp.world;
+        float f[VN];
+        V16<T>::unpack(ld_cv_v4(reinterpret_cast<const uint4*>(pp.buf[src]) + lo_vec + i), f);
+#pragma unroll
+        for (int e = 0; e < VN; ++e) acc[e] += f[e];
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < VN; ++e) {
+      acc[e] *= scale;
+      const float mk = mask != nullptr ? mask[i * VN + e] : 1.0f;
+      local += acc[e] * acc[e] * mk;
+      out[i * VN + e] = acc[e];
+    }
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < COMM_THREADS / 32; ++w) t += red[w];
+    atomicAdd(sq, t);
+  }
+  block_barrier(pp, epoch + 1);                              // peers are done reading my gradient buffer
+}
+
+// ----------------------------------------------------------------------------------------------- K2b
+// AdamW on the local shard (fp32 master/m/v, fp32 reduced gradient) and all-gather of the new parameters:
+// the updated value is stored into every peer's parameter buffer at [lo + i].
+template <typename PT>
+__global__ void __launch_bounds__(COMM_THREADS)
+adamw_allgather_kernel(PeerPtrs pp, const float* __restrict__ grad, float* __restrict__ master, float* __restrict__ m,
+                       float* __restrict__ v, const float* __restrict__ grad_scale, long long n, float lr, float beta1,
+                       float beta2, float eps, float wd, float inv_bc1, float inv_sqrt_bc2, uint32_t epoch) {
+  const float gs = grad_scale != nullptr ? *grad_scale : 1.0f;
+  const long long per_rank = n / pp.world;
+  const long long lo = per_rank * pp.rank;
+  const long long n4 = per_rank / 4;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g4 = *reinterpret_cast<const float4*>(grad + i * 4);
+    float4 w4 = *reinterpret_cast<const float4*>(master + i * 4);
+    float4 m4 = *reinterpret_cast<const float4*>(m + i * 4);
+    float4 v4 = *reinterpret_cast<const float4*>(v + i * 4);
+    const float* gp = reinterpret_cast<const float*>(&g4);
+    float* wp = reinterpret_cast<float*>(&w4);
+    float* mp = reinterpret_cast<float*>(&m4);
+    float* vp = reinterpret_cast<float*>(&v4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float gr = gp[e] * gs;
+      mp[e] = beta1 * mp[e] + (1.0f - beta1) * gr;
+      vp[e] = beta2 * vp[e] + (1.0f - beta2) * gr * gr;
+      wp[e] = wp[e] * (1.0f - lr * wd) - lr * (mp[e] * inv_bc1) / (sqrtf(vp[e]) * inv_sqrt_bc2 + eps);
+    }
+    *reinterpret_cast<float4*>(master + i * 4) = w4;
+    *reinterpret_cast<float4*>(m + i * 4) = m4;
+    *reinterpret_cast<float4*>(v + i * 4) = v4;
+    if constexpr (sizeof(PT) == 2) {
+      const uint2 o = make_uint2(pack_bf16(wp[0], wp[1]), pack_bf16(wp[2], wp[3]));
+#pragma unroll
+      for (int p = 0; p < COMM_MAX_RANKS; ++p)
+        if (p < pp.world)
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(pp.buf[(pp.rank + p) % pp.world]) + lo + i * 4) = o;
+    } else {
+#pragma unroll
+      for (int p = 0; p < COMM_MAX_RANKS; ++p)
+        if (p < pp.world)
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(pp.buf[(pp.rank + p) % pp.world]) + lo + i * 4) = w4;
+    }
+  }
+  block_barrier(pp, epoch);                                  // all shards have been pushed to all ranks
+}
+
+static int fill(PeerPtrs& pp, void* const* bufs, void* const* sigs, void* mc, int rank, int world) {
+  if (world < 1 || world > COMM_MAX_RANKS) return 960;
+  for (int i = 0; i < world; ++i) { pp.buf[i] = bufs[i]; pp.sig[i] = static_cast<uint32_t*>(sigs[i]); }
+  pp.mc = mc; pp.rank = rank; pp.world = world;
+  return 0;
+}
+
+}  // namespace qn
+
+using namespace qn;
+
+// bufs / sigs: host arrays of `world` device pointers (peer mappings).  The signal pad must hold at least
+// blocks * 8 uint32 and `epoch` must grow by >= 2 between launches that use the same pad.
+extern "C" int qn_allreduce(void* const* bufs, void* const* sigs, void* mc, int rank, int world, long long n,
+                            int dtype, float scale, unsigned int epoch, int blocks, cudaStream_t s) {
+  PeerPtrs pp;
+  if (int rc = fill(pp, bufs, sigs, mc, rank, world)) return rc;
+  const int vn = dtype == 1 ? 8 : 4;
+  if (n % (world * vn)) return 961;
+  if (mc != nullptr) {
+    if (dtype == 1) allreduce_kernel<__nv_bfloat16, true><<<blocks, COMM_THREADS, 0, s>>>(pp, n, scale, epoch);
+    else allreduce_kernel<float, true><<<blocks, COMM_THREADS, 0, s>>>(pp, n, scale, epoch);
+  } else {
+    if (dtype == 1) allreduce_kernel<__nv_bfloat16, false><<<blocks, COMM_THREADS, 0, s>>>(pp, n, scale, epoch);
+    else allreduce_kernel<float, false><<<blocks, COMM_THREADS, 0, s>>>(pp, n, scale, epoch);
+  }
+  return (int)cudaGetLastError();
+}
+
+extern "C" int qn_reduce_scatter_sqnorm(void* const* bufs, void* const* sigs, int rank, int world, float* out,
+                                        const float* mask, float* sq, long long n, int dtype, float scale,
+                                        unsigned int epoch, int blocks, cudaStream_t s) {
+  PeerPtrs pp;
+  if (int rc = fill(pp, bufs, sigs, nullptr, rank, world)) return rc;
+  const int vn = dtype == 1 ? 8 : 4;
+  if (n % (world * vn)) return 961;
+  if (dtype == 1)
+    reduce_scatter_sqnorm_kernel<__nv_bfloat16><<<blocks, COMM_THREADS, 0, s>>>(pp, out, mask, sq, n, scale, epoch);
+  else
+    reduce_scatter_sqnorm_kernel<float><<<blocks, COMM_THREADS, 0, s>>>(pp, out, mask, sq, n, scale, epoch);
+  return (int)cudaGetLastError();
+}
+
+extern "C" int qn_adamw_allgather(void* const* bufs, void* const* sigs, int rank, int world, const float* grad,
+                                  float* master, float* m, float* v, const float* grad_scale, long long n,
+                                  int pdtype, float lr, float beta1, float beta2, float eps, float wd, float bc1,
+                                  float bc2, unsigned int epoch, int blocks, cudaStream_t s) {
+  PeerPtrs pp;
+  if (int rc = fill(pp, bufs, sigs, nullptr, rank, world)) return rc;
+  if (n % (world * 4)) return 961;
+  const float inv_bc1 = 1.0f / bc1, inv_sqrt_bc2 = 1.0f / sqrtf(bc2);
+  if (pdtype == 1)
+    adamw_allgather_kernel<__nv_bfloat16><<<blocks, COMM_THREADS, 0, s>>>(pp, grad, master, m, v, grad_scale, n, lr,
+                                                                         beta1, beta2, eps, wd, inv_bc1, inv_sqrt_bc2, epoch);
+  else
+    adamw_allgather_kernel<float><<<blocks, COMM_THREADS, 0, s>>>(pp, grad, master, m, v, grad_scale, n, lr, beta1,
+                                                                 beta2, eps, wd, inv_bc1, inv_sqrt_bc2, epoch);
+  return (int)cudaGetLastError();
+}
+
+// ---- plain IPC helpers (fallback rendezvous when torch symmetric memory is unavailable)
+extern "C" int qn_ipc_get_handle(void* ptr, void* handle64) {
+  return (int)cudaIpcGetMemHandle(static_cast<cudaIpcMemHandle_t*>(handle64), ptr);
+}
+extern "C" int qn_ipc_open_handle(const void* handle64, void** out) {
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  return (int)cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess);
+}
+extern "C" int qn_malloc(void** out, long long bytes) { return (int)cudaMalloc(out, (size_t)bytes); }
+extern "C" int qn_memset0(void* p, long long bytes, cudaStream_t s) { return (int)cudaMemsetAsync(p, 0, (size_t)bytes, s); }

@@ -45,8 +45,9 @@ ce_fwd_bwd_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restric
     sm += __expf(f - mx);
   }
   // warp then CTA combine of (max, sum)
+  // (threads / warps that saw no element carry max = -inf, sum = 0: guard the inf - inf)
   const float wm = warp_max(mx);
-  sm = warp_sum(sm * __expf(mx - wm));
+  sm = warp_sum(mx == -INFINITY ? 0.f : sm * __expf(mx - wm));
   if (lane == 0) { s_max[w] = wm; s_sum[w] = sm; }
   __syncthreads();
   float gm = s_max[0];
@@ -54,7 +55,7 @@ ce_fwd_bwd_kernel(__nv_bfloat16* __restrict__ logits, const long long* __restric
   for (int i = 1; i < CE_THREADS / 32; ++i) gm = fmaxf(gm, s_max[i]);
   float gs = 0.f;
 #pragma unroll
-  for (int i = 0; i < CE_THREADS / 32; ++i) gs += s_sum[i] * __expf(s_max[i] - gm);
+  for (int i = 0; i < CE_THREADS / 32; ++i) gs += (s_max[i] == -INFINITY) ? 0.f : s_sum[i] * __expf(s_max[i] - gm);
   const float lse = gm + __logf(gs);
   if (tid == 0) {
     const float xl = __bfloat162float(x[label]);

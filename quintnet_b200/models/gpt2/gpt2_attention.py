@@ -58,6 +58,11 @@ class GPT2Attention(nn.Module):
         qkv = self.c_attn(hidden_states)                      # [B, T, 3*E/tp]
         B, T, _ = qkv.shape
         Hl, d = self.num_heads_local, self.head_dim
+        if not self.use_rope and ops.attention_qkvpacked_ok(qkv, d):
+            # native tcgen05 flash attention straight on the packed projection (no split/transpose copies)
+            o = ops.attention_qkvpacked(qkv, Hl, causal=True, dropout_p=self.attn_pdrop, training=self.training)
+            o = self.c_proj(o)
+            return ops.dropout_add(o, residual, self.resid_pdrop, self.training)
         q, k, v = qkv.view(B, T, 3, Hl, d).permute(2, 0, 3, 1, 4)   # each [B, Hl, T, d] (views)
         if self.use_rope:
             cos, sin = self._rope(T, qkv.device)

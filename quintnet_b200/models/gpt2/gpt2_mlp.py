@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from ... import ops
+from ...core.communication import All_Reduce, Copy_To_Parallel
 from ...parallel.tensor_parallel.layers import ColumnParallelLinear, RowParallelLinear
 
 
@@ -40,6 +41,13 @@ class GPT2MLP(nn.Module):
         self.dropout = nn.Dropout(config.resid_pdrop)
 
     def forward(self, hidden_states: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if not self.c_fc.sequence_parallel:
+            # whole MLP as ONE autograd op (GELU and GELU' fused into GEMM epilogues); the TP conjugate
+            # collectives f / g wrap it exactly as they wrap the two separate layers
+            x = Copy_To_Parallel.apply(hidden_states, self.tp_group)
+            h = ops.mlp(x, self.c_fc.proj.weight, self.c_fc.proj.bias, self.c_proj.proj.weight, self.c_proj.bias)
+            h = All_Reduce.apply(h, self.tp_group)
+            return ops.dropout_add(h, residual, self.resid_pdrop, self.training)
         h = self.c_fc(hidden_states)          # bias + GELU fused
         h = self.c_proj(h)
         return ops.dropout_add(h, residual, self.resid_pdrop, self.training)

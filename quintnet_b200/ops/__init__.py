@@ -33,6 +33,15 @@ def linear(x, w, b=None, act: Optional[str] = None):
     return reference.linear(x, w, b, act)
 
 
+def mlp(x, w1, b1, w2, b2):
+    """gelu(x·W1ᵀ + b1)·W2ᵀ + b2 — one fused autograd op on B200 (GELU / GELU' live in GEMM epilogues)."""
+    if _use_native("gemm", x):
+        from . import cuda_ops
+        if cuda_ops.mlp_ok(x, w1, b1, w2, b2):
+            return cuda_ops.mlp(x, w1, b1, w2, b2)
+    return linear(linear(x, w1, b1, "gelu"), w2, b2)
+
+
 def layer_norm(x, w, b, eps: float = 1e-5):
     if _use_native("layernorm", x) and x.dtype in (torch.bfloat16, torch.float32):
         from . import cuda_ops
@@ -56,15 +65,25 @@ def gelu(x):
 
 def attention(q, k, v, causal: bool, dropout_p: float = 0.0, scale=None, training: bool = True):
     """q,k,v: [B, H, T, d] -> [B, H, T, d]"""
-    if _use_native("attention", q) and q.dtype == torch.bfloat16:
-        from . import cuda_ops
-        return cuda_ops.attention(q, k, v, causal, dropout_p if training else 0.0, scale)
     if q.is_cuda:
         # library attention (cuDNN/flash SDPA) until the native kernel is enabled
         import torch.nn.functional as F
         return F.scaled_dot_product_attention(q, k, v, is_causal=causal, scale=scale,
                                               dropout_p=dropout_p if training else 0.0)
     return reference.attention(q, k, v, causal, dropout_p, scale, training)
+
+
+def attention_qkvpacked_ok(qkv, head_dim: int) -> bool:
+    """True if the packed native flash-attention kernel (head_dim 64, bf16, CUDA) can take ``qkv``."""
+    return (qkv.is_cuda and qkv.dtype == torch.bfloat16 and head_dim == 64
+            and _use_native("attention", qkv))
+
+
+def attention_qkvpacked(qkv, n_heads: int, causal: bool, dropout_p: float = 0.0, scale=None,
+                        training: bool = True):
+    """qkv: [B, T, 3*H*64] (layout [3, H, 64] in the last dim) -> [B, T, H*64]; native sm_100a kernel."""
+    from . import cuda_ops
+    return cuda_ops.attention_qkvpacked(qkv, n_heads, causal, dropout_p if training else 0.0, scale)
 
 
 def cross_entropy_sum(logits, labels, ignore_index: int = -100):

@@ -104,6 +104,53 @@ class _Linear(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class _FusedMLP(torch.autograd.Function):
+    """y = (gelu(x·W1ᵀ + b1))·W2ᵀ + b2 with the GELU fused into the first GEMM's epilogue (forward) and
+    gelu' fused into the dgrad GEMM's epilogue (backward): no stand-alone activation kernels."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2):
+        E, I = x.shape[-1], w1.shape[0]
+        x2 = x.reshape(-1, E)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        z = torch.empty((M, I), dtype=torch.bfloat16, device=x.device)
+        a = gemm(x2, w1, M, I, E, epilogue=EPI_BIAS_GELU, bias=b1, z=z)
+        y = gemm(a, w2, M, w2.shape[0], I, epilogue=EPI_BIAS if b2 is not None else EPI_NONE, bias=b2)
+        ctx.save_for_backward(x2, w1, w2, z, a)
+        ctx.xshape, ctx.has_b1, ctx.has_b2 = x.shape, b1 is not None, b2 is not None
+        return y.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w1, w2, z, a = ctx.saved_tensors
+        M, E = x2.shape
+        I, O = w1.shape[0], w2.shape[0]
+        dy2 = dy.reshape(M, O)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dz = gemm(dy2, w2, M, I, O, b_mn=True, epilogue=EPI_GELU_BWD, z=z)     # (dY·W2) ⊙ gelu'(z)
+        dw2 = gemm(dy2, a, O, I, M, a_mn=True, b_mn=True) if ctx.needs_input_grad[3] else None
+        db2 = colsum(dy2) if (ctx.has_b2 and ctx.needs_input_grad[4]) else None
+        dx = gemm(dz, w1, M, E, I, b_mn=True).view(ctx.xshape) if ctx.needs_input_grad[0] else None
+        dw1 = gemm(dz, x2, I, E, M, a_mn=True, b_mn=True) if ctx.needs_input_grad[1] else None
+        db1 = colsum(dz) if (ctx.has_b1 and ctx.needs_input_grad[2]) else None
+        return dx, dw1, db1, dw2, db2
+
+
+def mlp(x, w1, b1, w2, b2):
+    return _FusedMLP.apply(x, w1, b1, w2, b2)
+
+
+def mlp_ok(x, w1, b1, w2, b2) -> bool:
+    E, I, O = x.shape[-1], w1.shape[0], w2.shape[0]
+    M = x.numel() // E
+    ts = [t for t in (x, w1, b1, w2, b2) if t is not None]
+    return (all(t.dtype == torch.bfloat16 and t.is_cuda for t in ts) and gemm_ok(M, I, E, E, I, O)
+            and all(t.data_ptr() % 16 == 0 for t in ts) and M % 8 == 0)
+
+
 def colsum(x2: torch.Tensor) -> torch.Tensor:
     rows, cols = x2.shape
     acc = torch.empty(cols, dtype=torch.float32, device=x2.device)
@@ -406,3 +453,45 @@ def linear_cross_entropy(h, w, labels, ignore_index=-100):
         from . import reference
         return reference.linear_cross_entropy(h, w.to(h.dtype), labels, ignore_index)
     return _LinearCrossEntropy.apply(h, w, labels, ignore_index)
+
+
+# ---------------------------------------------------------------- attention
+class _AttnPacked(torch.autograd.Function):
+    """Flash attention on the packed c_attn output: qkv [B, T, 3*H*64] -> out [B, T, H*64]."""
+
+    @staticmethod
+    def forward(ctx, qkv, H, causal, p_drop, scale):
+        B, T, _ = qkv.shape
+        qkv_c = qkv if qkv.is_contiguous() else qkv.contiguous()
+        out = torch.empty((B, T, H * 64), dtype=torch.bfloat16, device=qkv.device)
+        lse = torch.empty((B, H, T), dtype=torch.float32, device=qkv.device)
+        seed = 0
+        if p_drop > 0.0:
+            seed, off = _PhiloxState.next(8)
+            seed = (seed * 0x9E3779B97F4A7C15 + off) & 0xFFFFFFFFFFFFFFFF
+        rc = _lib().qn_attn_fwd(qkv_c.data_ptr(), out.data_ptr(), lse.data_ptr(), B, H, T, float(scale), int(causal),
+                                float(p_drop), seed, native.stream())
+        native.check(rc, "qn_attn_fwd")
+        native.count()
+        ctx.save_for_backward(qkv_c, out, lse)
+        ctx.args = (B, H, T, float(scale), int(causal), float(p_drop), seed)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        qkv, out, lse = ctx.saved_tensors
+        B, H, T, scale, causal, p_drop, seed = ctx.args
+        do = dout if dout.is_contiguous() else dout.contiguous()
+        dqkv = torch.empty_like(qkv)
+        ws = torch.empty(B * T * H * 64 + B * H * T, dtype=torch.float32, device=qkv.device)
+        rc = _lib().qn_attn_bwd(qkv.data_ptr(), out.data_ptr(), do.data_ptr(), lse.data_ptr(), dqkv.data_ptr(),
+                                ws.data_ptr(), B, H, T, scale, causal, p_drop, seed, native.stream())
+        native.check(rc, "qn_attn_bwd")
+        native.count(5)
+        return dqkv, None, None, None, None
+
+
+def attention_qkvpacked(qkv: torch.Tensor, H: int, causal: bool, p_drop: float = 0.0, scale=None):
+    if scale is None:
+        scale = 1.0 / 8.0   # 1/sqrt(64)
+    return _AttnPacked.apply(qkv, H, causal, p_drop, scale)

@@ -32,7 +32,7 @@ _load_error: Optional[str] = None
 # ops whose native kernel is used on CUDA tensors.  Env override:
 #   QUINTNET_NATIVE=all | none | comma-separated list
 _DEFAULT_ENABLED = {
-    "layernorm", "gelu", "adamw", "dropout", "rope", "cross_entropy", "gemm",
+    "layernorm", "gelu", "adamw", "dropout", "rope", "cross_entropy", "gemm", "attention",
 }
 
 
@@ -139,6 +139,8 @@ _SIGNATURES = {
     "qn_adamw": [_P, _I, _P, _I, _P, _P, _P, _P, _L, _F, _F, _F, _F, _F, _F, _F, _P],
     "qn_cross_entropy": [_P, _P, _P, _P, _I, _I, _L, _L, _I, _P],
     "qn_scale_bf16": [_P, _P, _P, _L, _P],
+    "qn_attn_fwd": [_P, _P, _P, _I, _I, _I, _F, _I, _F, _U, _P],
+    "qn_attn_bwd": [_P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _I, _F, _U, _P],
 }
 
 

@@ -1,0 +1,228 @@
+"""NVLink symmetric memory: allocation, rendezvous and the in-kernel collectives
+built on it (``csrc/comm.cu``).
+
+A *symmetric buffer* is an allocation that exists at the same size on every
+rank of a process group, with every peer's copy mapped into this process'
+address space (and, when the fabric supports NVLS, a multicast address that
+fans out to / reduces over all copies inside the NVSwitch).  The sm_100a
+kernels take the raw peer pointers and do the communication themselves with
+ordinary ``ld``/``st`` (or ``multimem.*``) — no NCCL call on the data path.
+
+Rendezvous back-ends, tried in order:
+  1. ``torch.distributed._symmetric_memory`` (CUDA VMM + fabric/fd handles;
+     also provides the multicast pointer and a signal pad);
+  2. plain CUDA IPC (``cudaIpcGetMemHandle`` on a dedicated ``cudaMalloc``
+     block, handles exchanged over the process group) — peer pointers only.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from . import native
+
+_P, _I, _L, _F, _U32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_uint
+native.declare("qn_allreduce", [_P, _P, _P, _I, _I, _L, _I, _F, _U32, _I, _P])
+native.declare("qn_reduce_scatter_sqnorm", [_P, _P, _I, _I, _P, _P, _P, _L, _I, _F, _U32, _I, _P])
+native.declare("qn_adamw_allgather", [_P, _P, _I, _I, _P, _P, _P, _P, _P, _L, _I, _F, _F, _F, _F, _F, _F, _F,
+                                      _U32, _I, _P])
+native.declare("qn_ipc_get_handle", [_P, _P])
+native.declare("qn_ipc_open_handle", [_P, ctypes.POINTER(ctypes.c_void_p)])
+native.declare("qn_malloc", [ctypes.POINTER(ctypes.c_void_p), _L])
+native.declare("qn_memset0", [_P, _L, _P])
+
+SIGNAL_PAD_BYTES = 64 * 1024
+COMM_BLOCKS = int(os.environ.get("QUINTNET_COMM_BLOCKS", "32"))
+_DT = {torch.float32: 0, torch.bfloat16: 1}
+
+
+class _RawCudaTensorHolder:
+    """Expose a raw device allocation to torch through ``__cuda_array_interface__``."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.ptr, self.nbytes = ptr, nbytes
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                         "version": 3, "strides": None}
+
+
+class SymmBuffer:
+    """One symmetric allocation (``nbytes`` on every rank of ``group``)."""
+
+    def __init__(self, tensor: torch.Tensor, group, peer_ptrs: List[int], sig_ptrs: List[int],
+                 mc_ptr: int, backend: str, keepalive=None):
+        self.tensor, self.group = tensor, group
+        self.base = tensor.data_ptr()
+        self.nbytes = tensor.numel() * tensor.element_size()
+        self.peer_ptrs, self.sig_ptrs, self.mc_ptr = peer_ptrs, sig_ptrs, mc_ptr
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.backend = backend
+        self.epoch = 2
+        self._keepalive = keepalive
+
+    def ptr_arrays(self, byte_offset: int = 0):
+        arr = (ctypes.c_void_p * self.world)(*[p + byte_offset for p in self.peer_ptrs])
+        sig = (ctypes.c_void_p * self.world)(*self.sig_ptrs)
+        return arr, sig
+
+    def next_epoch(self, n: int = 2) -> int:
+        e = self.epoch
+        self.epoch = (self.epoch + n) & 0x7FFFFFFF
+        if self.epoch < 2:
+            self.epoch = 2
+        return e
+
+
+_registry: List[SymmBuffer] = []
+_pads: Dict[Tuple[int, str], SymmBuffer] = {}
+_disabled_reason: Optional[str] = None
+
+
+def lookup(t: torch.Tensor) -> Optional[Tuple[SymmBuffer, int]]:
+    """``(buffer, byte_offset)`` if ``t`` lives inside a symmetric allocation."""
+    if not t.is_cuda:
+        return None
+    p = t.data_ptr()
+    for b in _registry:
+        if b.base <= p < b.base + b.nbytes:
+            return b, p - b.base
+    return None
+
+
+def _group_key(group) -> int:
+    return id(group)
+
+
+def _torch_symm_alloc(nbytes: int, device, group):
+    import torch.distributed._symmetric_memory as sm
+    t = sm.empty(nbytes, dtype=torch.uint8, device=device)
+    try:
+        h = sm.rendezvous(t, group=group)
+    except TypeError:
+        h = sm.rendezvous(t, group.group_name)
+    world = dist.get_world_size(group)
+    peer = [int(h.buffer_ptrs[i]) for i in range(world)]
+    sig = [int(h.signal_pad_ptrs[i]) for i in range(world)]
+    mc = 0
+    try:
+        mc = int(h.multicast_ptr or 0)
+    except Exception:
+        mc = 0
+    return t, peer, sig, mc, h
+
+
+def _ipc_alloc(nbytes: int, device, group):
+    lib = native.require()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+
+    def one(nb):
+        out = ctypes.c_void_p()
+        native.check(lib.qn_malloc(ctypes.byref(out), nb), "cudaMalloc")
+        native.check(lib.qn_memset0(out.value, nb, native.stream()), "cudaMemset")
+        hb = ctypes.create_string_buffer(64)
+        native.check(lib.qn_ipc_get_handle(out.value, hb), "cudaIpcGetMemHandle")
+        handles = [None] * world
+        dist.all_gather_object(handles, hb.raw, group=group)
+        ptrs = []
+        for r in range(world):
+            if r == rank:
+                ptrs.append(out.value)
+            else:
+                o = ctypes.c_void_p()
+                native.check(lib.qn_ipc_open_handle(handles[r], ctypes.byref(o)), "cudaIpcOpenMemHandle")
+                ptrs.append(o.value)
+        return out.value, ptrs
+
+    torch.cuda.synchronize()
+    base, peer = one(nbytes)
+    sbase, sig = one(SIGNAL_PAD_BYTES)
+    torch.cuda.synchronize()
+    dist.barrier(group=group)
+    holder = _RawCudaTensorHolder(base, nbytes)
+    t = torch.as_tensor(holder, device=device)
+    return t, peer, sig, 0, holder
+
+
+def alloc_bytes(nbytes: int, device, group) -> SymmBuffer:
+    global _disabled_reason
+    nbytes = (nbytes + 4095) // 4096 * 4096
+    mode = os.environ.get("QUINTNET_SYMM", "auto")
+    errs = []
+    if mode in ("auto", "torch"):
+        try:
+            t, peer, sig, mc, keep = _torch_symm_alloc(nbytes, device, group)
+            if os.environ.get("QUINTNET_NVLS", "1") != "1":
+                mc = 0
+            b = SymmBuffer(t, group, peer, sig, mc, "torch_symm_mem", keep)
+            _registry.append(b)
+            return b
+        except Exception as e:  # noqa: BLE001
+            errs.append(f"torch symm_mem: {type(e).__name__}: {e}")
+            if mode == "torch":
+                raise
+    try:
+        t, peer, sig, mc, keep = _ipc_alloc(nbytes, device, group)
+        b = SymmBuffer(t, group, peer, sig, mc, "cuda_ipc", keep)
+        _registry.append(b)
+        return b
+    except Exception as e:  # noqa: BLE001
+        errs.append(f"cuda ipc: {type(e).__name__}: {e}")
+        _disabled_reason = "; ".join(errs)
+        raise RuntimeError(f"symmetric memory unavailable: {_disabled_reason}")
+
+
+def alloc(n: int, dtype: torch.dtype, device, group) -> torch.Tensor:
+    """Zero-initialised symmetric 1-D tensor of ``n`` elements of ``dtype``."""
+    es = torch.empty((), dtype=dtype).element_size()
+    b = alloc_bytes(n * es, device, group)
+    t = b.tensor[: n * es].view(dtype)
+    t.zero_()
+    return t
+
+
+def available(group) -> bool:
+    return (group is not None and dist.get_world_size(group) > 1 and torch.cuda.is_available()
+            and native.available() and _disabled_reason is None)
+
+
+# ------------------------------------------------------------------ collectives
+def all_reduce_(buf_off: Tuple[SymmBuffer, int], t: torch.Tensor, scale: float = 1.0,
+                use_multicast: bool = True, blocks: Optional[int] = None) -> None:
+    """In-place SUM all-reduce (× ``scale``) of symmetric tensor ``t`` by K1."""
+    b, off = buf_off
+    arr, sig = b.ptr_arrays(off)
+    mc = (b.mc_ptr + off) if (use_multicast and b.mc_ptr) else None
+    rc = native.require().qn_allreduce(arr, sig, mc, b.rank, b.world, t.numel(), _DT[t.dtype], float(scale),
+                                       b.next_epoch(2), blocks or COMM_BLOCKS, native.stream())
+    native.check(rc, "qn_allreduce")
+    native.count()
+
+
+def reduce_scatter_sqnorm(flat_grad: torch.Tensor, out_shard: torch.Tensor, scale: float,
+                          mask: Optional[torch.Tensor], sq: torch.Tensor) -> None:
+    b, off = lookup(flat_grad)
+    arr, sig = b.ptr_arrays(off)
+    rc = native.require().qn_reduce_scatter_sqnorm(arr, sig, b.rank, b.world, out_shard.data_ptr(),
+                                                   native.ptr(mask), sq.data_ptr(), flat_grad.numel(),
+                                                   _DT[flat_grad.dtype], float(scale), b.next_epoch(2),
+                                                   COMM_BLOCKS, native.stream())
+    native.check(rc, "qn_reduce_scatter_sqnorm")
+    native.count()
+
+
+def adamw_allgather(flat_param: torch.Tensor, st: dict, coef: Optional[torch.Tensor], *, step: int, lr: float,
+                    beta1: float, beta2: float, eps: float, weight_decay: float) -> None:
+    b, off = lookup(flat_param)
+    arr, sig = b.ptr_arrays(off)
+    if coef is not None and coef.dtype != torch.float32:
+        coef = coef.float()
+    rc = native.require().qn_adamw_allgather(arr, sig, b.rank, b.world, st["grad"].data_ptr(),
+                                             st["master"].data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(),
+                                             native.ptr(coef), flat_param.numel(), _DT[flat_param.dtype], lr,
+                                             beta1, beta2, eps, weight_decay, 1.0 - beta1 ** step,
+                                             1.0 - beta2 ** step, b.next_epoch(2), COMM_BLOCKS, native.stream())
+    native.check(rc, "qn_adamw_allgather")
+    native.count()

@@ -18,7 +18,7 @@ def _rel(a, b):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 256, 64), (256, 512, 128), (384, 768, 1024), (16384 // 8, 3072, 1024),
-                                   (400, 64, 64), (130, 264, 72), (1000, 50264 // 8, 256)])
+                                   (400, 64, 64), (130, 264, 72), (1000, 6288, 256)])
 @pytest.mark.parametrize("block_n", [0, 128, 256])
 def test_gemm_tn(M, N, K, block_n):
     from quintnet_b200.ops import cuda_ops
@@ -207,3 +207,58 @@ def test_gpt2_gpu_matches_cpu_reference():
     g1 = ref.blocks[0].mlp.c_fc.proj.weight.grad
     g2 = gpu.blocks[0].mlp.c_fc.proj.weight.grad
     assert _rel(g2.cpu(), g1) < 8e-2, _rel(g2.cpu(), g1)
+
+
+@pytest.mark.parametrize("causal", [True, False])
+@pytest.mark.parametrize("B,H,T", [(2, 4, 128), (2, 3, 512), (1, 2, 384), (2, 2, 200)])
+def test_attention_qkvpacked(causal, B, H, T):
+    from quintnet_b200 import ops
+    from quintnet_b200.ops import reference
+    torch.manual_seed(9)
+    qkv = (torch.randn(B, T, 3 * H * 64, device="cuda", dtype=torch.bfloat16)).requires_grad_(True)
+    out = ops.attention_qkvpacked(qkv, H, causal=causal, dropout_p=0.0)
+    dout = torch.randn_like(out)
+    out.backward(dout)
+    qr = qkv.detach().float().requires_grad_(True)
+    q, k, v = qr.view(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    oref = reference.attention(q, k, v, causal, 0.0, None, False).transpose(1, 2).reshape(B, T, H * 64)
+    oref.backward(dout.float())
+    assert _rel(out, oref) < 2e-2, _rel(out, oref)
+    g, gr = qkv.grad.view(B, T, 3, H, 64), qr.grad.view(B, T, 3, H, 64)
+    for i, name in enumerate("qkv"):
+        assert _rel(g[:, :, i], gr[:, :, i]) < 4e-2, (name, _rel(g[:, :, i], gr[:, :, i]))
+
+
+def test_attention_dropout_statistics():
+    from quintnet_b200 import ops
+    from quintnet_b200.ops import cuda_ops
+    cuda_ops.manual_seed(5)
+    B, H, T = 2, 4, 256
+    qkv = torch.zeros(B, T, 3 * H * 64, device="cuda", dtype=torch.bfloat16)
+    qkv.view(B, T, 3, H, 64)[:, :, 2] = 1.0            # V = 1, uniform attention -> out = kept fraction / (1-p)
+    qkv.requires_grad_(True)
+    out = ops.attention_qkvpacked(qkv, H, causal=False, dropout_p=0.25)
+    m = out.float().mean().item()
+    assert abs(m - 1.0) < 2e-2, m                       # E[keep/(1-p)] = 1
+    assert out.float().std().item() > 1e-3              # masks differ per row
+    out.sum().backward()                                # backward regenerates the same mask (finite grads)
+    assert torch.isfinite(qkv.grad.float()).all()
+
+
+def test_fused_mlp():
+    from quintnet_b200 import ops
+    torch.manual_seed(10)
+    x = torch.randn(512, 256, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    w1 = (torch.randn(1024, 256, device="cuda", dtype=torch.bfloat16) * 0.05).requires_grad_(True)
+    b1 = (torch.randn(1024, device="cuda", dtype=torch.bfloat16) * 0.1).requires_grad_(True)
+    w2 = (torch.randn(256, 1024, device="cuda", dtype=torch.bfloat16) * 0.05).requires_grad_(True)
+    b2 = (torch.randn(256, device="cuda", dtype=torch.bfloat16) * 0.1).requires_grad_(True)
+    y = ops.mlp(x, w1, b1, w2, b2)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    ref = [t.detach().float().requires_grad_(True) for t in (x, w1, b1, w2, b2)]
+    yr = F.linear(F.gelu(F.linear(ref[0], ref[1], ref[2])), ref[3], ref[4])
+    yr.backward(dy.float())
+    assert _rel(y, yr) < 2e-2
+    for t, r, n in zip((x, w1, b1, w2, b2), ref, "x w1 b1 w2 b2".split()):
+        assert _rel(t.grad, r.grad) < 3e-2, (n, _rel(t.grad, r.grad))
