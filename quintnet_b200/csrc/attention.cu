@@ -63,8 +63,18 @@ QN_DEVICE uint32_t drop_key(uint64_t seed, uint32_t b, uint32_t h) {
   k ^= k >> 13; k *= 0x5bd1e995u; k ^= k >> 15;
   return k;
 }
-// keep flags for elements (q, k) and (q, k+1), k even
-QN_DEVICE uint32_t drop_pair(uint32_t key, uint32_t q, uint32_t k, uint32_t T) { return hash2(q * T + k, key); }
+// 2 x 16-bit uniforms for elements (q, k) and (q, k+1), k even (one multiply-xorshift round pair)
+QN_DEVICE uint32_t drop_pair(uint32_t key, uint32_t idx) {
+  uint32_t x = (idx ^ key) * 0x9E3779B1u;
+  x ^= x >> 15;
+  x *= 0x85EBCA77u;
+  x ^= x >> 13;
+  return x;
+}
+// AND-mask for a packed bf16 pair: keep element iff its 16-bit uniform >= thr
+QN_DEVICE uint32_t drop_mask_pair(uint32_t h, uint32_t thr) {
+  return (((h & 0xFFFFu) >= thr) ? 0x0000FFFFu : 0u) | (((h >> 16) >= thr) ? 0xFFFF0000u : 0u);
+}
 
 // write 8 packed bf16 (16 B) of row `r` at 16-byte chunk index `c16` (0..15 over 128 columns) into a
 // [2 atoms][128 rows][128 B] K-major SW128 tile
@@ -168,59 +178,69 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       const bool need_mask = (p.causal && j == qb) || (k0 + BKV > p.T);
       mbar_wait(s_full, j & 1);
       tcgen05_fence_after();
-      // pass 1: row max
-      float mx = m;
+      // pass 1: row max of the RAW scores (scale > 0 commutes with max); masked variant only on the
+      // diagonal / tail block (warp-uniform branch outside the element loops)
+      float mx_raw = -INFINITY;
+      if (!need_mask) {
 #pragma unroll 1
-      for (uint32_t c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_S + lane_base + c * 32, v);
-        tmem_ld_wait();
+        for (uint32_t c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_S + lane_base + c * 32, v);
+          tmem_ld_wait();
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float sv = __uint_as_float(v[e]) * p.scale_log2;
-          if (need_mask) {
-            const uint32_t kk = k0 + c * 32 + e;
-            if (kk >= p.T || (p.causal && kk > q)) sv = -INFINITY;
-          }
-          mx = fmaxf(mx, sv);
+          for (int e = 0; e < 32; ++e) mx_raw = fmaxf(mx_raw, __uint_as_float(v[e]));
+        }
+      } else {
+        const uint32_t klim = min(p.T, p.causal ? q + 1 : p.T);    // valid keys: kk < klim
+#pragma unroll 1
+        for (uint32_t c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_S + lane_base + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            if (k0 + c * 32 + e < klim) mx_raw = fmaxf(mx_raw, __uint_as_float(v[e]));
         }
       }
-      const float m_new = mx;
+      const float m_new = fmaxf(m, mx_raw * p.scale_log2);
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;      // fully-masked row guard
       const float alpha = exp2f(m - m_use);                        // m = -inf -> 0
       float lsum = 0.f;
-      // pass 2: P = exp2(s - m), rowsum, dropout, bf16 -> smem
+      // pass 2: P = exp2(s*scale - m), rowsum, (dropout as an AND-mask on the packed bf16), -> smem
+      const uint32_t klim2 = need_mask ? min(p.T, p.causal ? q + 1 : p.T) : 0xFFFFFFFFu;
+      const bool drop = p.p_drop > 0.f;
+      const uint32_t ridx = q * p.T + k0;
 #pragma unroll 1
       for (uint32_t c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_S + lane_base + c * 32, v);
         tmem_ld_wait();
-        float pf[32];
-#pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float sv = __uint_as_float(v[e]) * p.scale_log2;
-          if (need_mask) {
-            const uint32_t kk = k0 + c * 32 + e;
-            if (kk >= p.T || (p.causal && kk > q)) sv = -INFINITY;
-          }
-          pf[e] = exp2f(sv - m_use);
-          lsum += pf[e];
-        }
-        if (p.p_drop > 0.f) {
+        uint32_t pk[16];
+        if (!need_mask) {
 #pragma unroll
           for (int e = 0; e < 32; e += 2) {
-            const uint32_t hh = drop_pair(dkey, q, k0 + c * 32 + e, p.T);
-            pf[e] = ((hh & 0xFFFFu) >= p.drop_thr16) ? pf[e] * p.drop_scale : 0.f;
-            pf[e + 1] = ((hh >> 16) >= p.drop_thr16) ? pf[e + 1] * p.drop_scale : 0.f;
+            const float p0 = exp2f(fmaf(__uint_as_float(v[e]), p.scale_log2, -m_use));
+            const float p1 = exp2f(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -m_use));
+            lsum += p0 + p1;
+            pk[e >> 1] = pack_bf16(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            const uint32_t kk = k0 + c * 32 + e;
+            const float p0 = (kk < klim2) ? exp2f(fmaf(__uint_as_float(v[e]), p.scale_log2, -m_use)) : 0.f;
+            const float p1 = (kk + 1 < klim2) ? exp2f(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -m_use)) : 0.f;
+            lsum += p0 + p1;
+            pk[e >> 1] = pack_bf16(p0, p1);
           }
         }
+        if (drop) {
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 pk;
-          pk.x = pack_bf16(pf[g * 8 + 0], pf[g * 8 + 1]); pk.y = pack_bf16(pf[g * 8 + 2], pf[g * 8 + 3]);
-          pk.z = pack_bf16(pf[g * 8 + 4], pf[g * 8 + 5]); pk.w = pack_bf16(pf[g * 8 + 6], pf[g * 8 + 7]);
-          st_tile_chunk(sP, r, c * 4 + g, pk);
+          for (int e = 0; e < 16; ++e) pk[e] &= drop_mask_pair(drop_pair(dkey, ridx + c * 32 + 2 * e), p.drop_thr16);
         }
+#pragma unroll
+        for (int g = 0; g < 4; ++g)
+          st_tile_chunk(sP, r, c * 4 + g, make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
       }
       l = l * alpha + lsum;
       m = m_new;
@@ -242,7 +262,7 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
       tcgen05_fence_before();
     }
     if (q < p.T) {
-      const float inv = l > 0.f ? 1.0f / l : 0.f;
+      const float inv = l > 0.f ? p.drop_scale / l : 0.f;     // dropout 1/(1-p) folded here
       __nv_bfloat16* op = p.out + ((static_cast<size_t>(b) * p.T + q) * p.H + h) * D;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
@@ -398,48 +418,44 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       const bool need_mask = (p.causal && qb == kb) || (k0 + BKV > p.T);
       mbar_wait(sdp_full, it & 1);
       tcgen05_fence_after();
+      // dS = P ⊙ (mask·rs·dP − δ)·scale = (P·scale·rs) ⊙ (mask·dP − δ/rs); dV uses mask·P (rs applied at the end)
+      const float c_ds = p.scale * p.drop_scale;
+      const float dl2 = dl / p.drop_scale;
+      const bool drop = p.p_drop > 0.f;
+      const uint32_t klim = need_mask ? min(p.T, p.causal ? q + 1 : p.T) : 0xFFFFFFFFu;
+      const uint32_t ridx = q * p.T + k0;
 #pragma unroll 1
       for (uint32_t c = 0; c < 4; ++c) {
         uint32_t sv[32], dv[32];
         tmem_ld_32x32b_x32(tmem_S + lane_base + c * 32, sv);
         tmem_ld_32x32b_x32(tmem_dP + lane_base + c * 32, dv);
         tmem_ld_wait();
-        float pf[32], ds[32];
+        uint32_t pk[16], dk[16];
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          float pe = exp2f(__uint_as_float(sv[e]) * p.scale_log2 - lse);
+        for (int e = 0; e < 32; e += 2) {
+          float p0 = exp2f(fmaf(__uint_as_float(sv[e]), p.scale_log2, -lse));
+          float p1 = exp2f(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -lse));
           if (need_mask) {
             const uint32_t kk = k0 + c * 32 + e;
-            if (kk >= p.T || (p.causal && kk > q)) pe = 0.f;
+            p0 = (kk < klim) ? p0 : 0.f;
+            p1 = (kk + 1 < klim) ? p1 : 0.f;
           }
-          pf[e] = pe;
-          ds[e] = __uint_as_float(dv[e]);
-        }
-        if (p.p_drop > 0.f) {
-#pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const uint32_t hh = drop_pair(dkey, q, k0 + c * 32 + e, p.T);
-            const float k0f = ((hh & 0xFFFFu) >= p.drop_thr16) ? p.drop_scale : 0.f;
-            const float k1f = ((hh >> 16) >= p.drop_thr16) ? p.drop_scale : 0.f;
-            ds[e] *= k0f; ds[e + 1] *= k1f;                     // dP w.r.t. the un-dropped probabilities
-            const float p0 = pf[e], p1 = pf[e + 1];
-            pf[e] = p0 * k0f; pf[e + 1] = p1 * k1f;             // dropped P (for dV)
-            ds[e] = p0 * (ds[e] - dl) * p.scale;
-            ds[e + 1] = p1 * (ds[e + 1] - dl) * p.scale;
+          float d0 = __uint_as_float(dv[e]), d1 = __uint_as_float(dv[e + 1]);
+          uint32_t pw = pack_bf16(p0, p1);
+          if (drop) {
+            const uint32_t h2 = drop_pair(dkey, ridx + c * 32 + e);
+            const bool k0b = (h2 & 0xFFFFu) >= p.drop_thr16, k1b = (h2 >> 16) >= p.drop_thr16;
+            d0 = k0b ? d0 : 0.f;
+            d1 = k1b ? d1 : 0.f;
+            pw &= (k0b ? 0x0000FFFFu : 0u) | (k1b ? 0xFFFF0000u : 0u);
           }
-        } else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) ds[e] = pf[e] * (ds[e] - dl) * p.scale;
+          pk[e >> 1] = pw;
+          dk[e >> 1] = pack_bf16((p0 * c_ds) * (d0 - dl2), (p1 * c_ds) * (d1 - dl2));
         }
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          uint4 pk, dk;
-          pk.x = pack_bf16(pf[g * 8 + 0], pf[g * 8 + 1]); pk.y = pack_bf16(pf[g * 8 + 2], pf[g * 8 + 3]);
-          pk.z = pack_bf16(pf[g * 8 + 4], pf[g * 8 + 5]); pk.w = pack_bf16(pf[g * 8 + 6], pf[g * 8 + 7]);
-          dk.x = pack_bf16(ds[g * 8 + 0], ds[g * 8 + 1]); dk.y = pack_bf16(ds[g * 8 + 2], ds[g * 8 + 3]);
-          dk.z = pack_bf16(ds[g * 8 + 4], ds[g * 8 + 5]); dk.w = pack_bf16(ds[g * 8 + 6], ds[g * 8 + 7]);
-          st_tile_chunk(sP, r, c * 4 + g, pk);
-          st_tile_chunk(sDS, r, c * 4 + g, dk);
+          st_tile_chunk(sP, r, c * 4 + g, make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
+          st_tile_chunk(sDS, r, c * 4 + g, make_uint4(dk[g * 4 + 0], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]));
         }
       }
       tcgen05_fence_before();
@@ -477,12 +493,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         tmem_ld_wait();
         if (kk < p.T) {
 #pragma unroll
+          const float osc = (which == 1) ? p.drop_scale : 1.0f;      // dV carries the dropout 1/(1-p)
           for (int g = 0; g < 4; ++g) {
             uint4 pk;
-            pk.x = pack_bf16(__uint_as_float(v[g * 8 + 0]), __uint_as_float(v[g * 8 + 1]));
-            pk.y = pack_bf16(__uint_as_float(v[g * 8 + 2]), __uint_as_float(v[g * 8 + 3]));
-            pk.z = pack_bf16(__uint_as_float(v[g * 8 + 4]), __uint_as_float(v[g * 8 + 5]));
-            pk.w = pack_bf16(__uint_as_float(v[g * 8 + 6]), __uint_as_float(v[g * 8 + 7]));
+            pk.x = pack_bf16(__uint_as_float(v[g * 8 + 0]) * osc, __uint_as_float(v[g * 8 + 1]) * osc);
+            pk.y = pack_bf16(__uint_as_float(v[g * 8 + 2]) * osc, __uint_as_float(v[g * 8 + 3]) * osc);
+            pk.z = pack_bf16(__uint_as_float(v[g * 8 + 4]) * osc, __uint_as_float(v[g * 8 + 5]) * osc);
+            pk.w = pack_bf16(__uint_as_float(v[g * 8 + 6]) * osc, __uint_as_float(v[g * 8 + 7]) * osc);
             *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = pk;
           }
         }
@@ -544,6 +561,13 @@ static int make_tmap4(CUtensorMap* m, const void* ptr, uint64_t B, uint64_t T, u
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
+    // first CUDA call on this host thread (e.g. an autograd worker): bind the primary context and retry
+    cudaFree(nullptr);
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   return r == CUDA_SUCCESS ? 0 : 900 + static_cast<int>(r);
 }
 

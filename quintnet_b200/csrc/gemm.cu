@@ -7,11 +7,11 @@
 //   * MN-major  (row-major [rows=K,  cols=MN])  — e.g. dY as A of the wgrad, W as B of the dgrad
 // so forward (X·Wᵀ), dgrad (dY·W) and wgrad (dYᵀ·X) all run here without a transpose pass.
 //
-// Structure (one CTA per SM, 256 threads):
+// Structure (one CTA per SM, 384 threads):
 //   warp 0   : TMA producer  — cp.async.bulk.tensor 2-D tiles into a kStages-deep smem ring (128B swizzle)
 //   warp 1   : MMA issuer    — one thread issues tcgen05.mma (128 x BLOCK_N x 16), commits to mbarriers
 //   warp 2   : TMEM allocator
-//   warps 4-7: epilogue      — tcgen05.ld accumulators -> bias / GELU / GELU' -> bf16 -> swizzled smem -> TMA store
+//   warps 4-11: epilogue     — tcgen05.ld accumulators -> bias / GELU / GELU' -> bf16 -> swizzled smem -> TMA store
 // Accumulators are double-buffered in TMEM (2 x BLOCK_N columns) so the epilogue of tile i overlaps the
 // main loop of tile i+1.  Tiles are walked in a grouped order for L2 reuse.
 #include "common.cuh"
@@ -24,19 +24,17 @@ namespace qn {
 constexpr uint32_t BLOCK_M = 128;
 constexpr uint32_t BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle atom
 constexpr uint32_t UMMA_K = 16;
-constexpr uint32_t kNumThreads = 256;
+constexpr uint32_t kNumThreads = 384;   // 4 control warps + 8 epilogue warps
 constexpr uint32_t kEpiWarp0 = 4;
 constexpr uint32_t kGroupM = 8;
 
-enum Epilogue : int { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_GELU_BWD = 3 };
+enum Epilogue : int { EPI_NONE = 0, EPI_BIAS = 1, EPI_BIAS_GELU = 2, EPI_MUL_AUX = 3 };
 
 struct GemmParams {
   uint32_t M, N, K;
   const __nv_bfloat16* bias;   // [N] or null
-  const __nv_bfloat16* aux;    // EPI_GELU_BWD: pre-activation z [M, ldaux]
-  uint32_t ldaux;
   int epilogue;
-  int has_z;                   // EPI_BIAS_GELU: also store the pre-activation through tmap_z
+  int has_z;                   // EPI_BIAS_GELU: also store gelu'(z) through tmap_z (consumed by EPI_MUL_AUX)
 };
 
 template <uint32_t BLOCK_N>
@@ -44,7 +42,7 @@ struct Cfg {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
   static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;        // 16/32 KB
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t EPI_BYTES = 4 * 2 * 4096;               // 4 warps x 2 buffers x (32 rows x 128 B)
+  static constexpr uint32_t EPI_BYTES = 8 * 4096;                   // 8 epilogue warps x (32 rows x 128 B)
   static constexpr uint32_t kStages = (BLOCK_N == 256) ? 4 : 6;
   static constexpr uint32_t BAR_BYTES = 256;
   static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +align slack
@@ -76,7 +74,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* aux_bar = tmem_empty + 2;          // [8] one per epilogue warp (EPI_MUL_AUX tile loads)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux_bar + 8);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -89,7 +88,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     prefetch_tensormap(&tmap_a);
     prefetch_tensormap(&tmap_b);
     prefetch_tensormap(&tmap_c);
-    if (p.has_z) prefetch_tensormap(&tmap_z);
+    if (p.has_z || p.epilogue == EPI_MUL_AUX) prefetch_tensormap(&tmap_z);
   }
   if (warp == 1 && lane == 0) {
     for (uint32_t i = 0; i < kStages; ++i) {
@@ -98,8 +97,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (uint32_t i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 4);
+      mbar_init(&tmem_empty[i], 8);
     }
+    for (uint32_t i = 0; i < 8; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_ptr);
@@ -173,81 +173,121 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp >= kEpiWarp0) {
-    // ---------------------------------------------------------------- epilogue
-    const uint32_t q = warp - kEpiWarp0;             // TMEM lane quarter == warp % 4
-    uint8_t* my_stage = smem_epi + q * 8192;
-    uint32_t as = 0, aphase = 0, buf = 0;
+    // ---------------------------------------------------------------- epilogue (8 warps)
+    // warp -> TMEM lane quarter (warp % 4) and column half ((warp - 4) / 4): two warps share each 32-row
+    // slab and split its 64-column chunks, doubling the elementwise throughput behind the MMA pipe.
+    const uint32_t q = (warp - kEpiWarp0) & 3;
+    const uint32_t half = (warp - kEpiWarp0) >> 2;
+    constexpr uint32_t kChunks = BLOCK_N / 64;
+    uint8_t* sbuf = smem_epi + (warp - kEpiWarp0) * 4096;
+    uint8_t* srow = sbuf + lane * 128;
+    uint32_t as = 0, aphase = 0, aux_phase = 0;
     for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       uint32_t m_blk, n_blk;
       tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
       const uint32_t m0 = m_blk * BLOCK_M + q * 32, n0 = n_blk * BLOCK_N;
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
-      const uint32_t row = m0 + lane;
 #pragma unroll 1
-      for (uint32_t chunk = 0; chunk < BLOCK_N / 64; ++chunk) {
+      for (uint32_t ci = 0; ci < kChunks / 2; ++ci) {
+        const uint32_t chunk = half * (kChunks / 2) + ci;
         const uint32_t nc = n0 + chunk * 64;
         if (nc >= p.N) break;                          // warp-uniform
         const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N + chunk * 64;
-        uint32_t acc[64];
-        tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
-        tmem_ld_32x32b_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
-        tmem_ld_wait();
-        float* f = reinterpret_cast<float*>(acc);
-        if (p.epilogue == EPI_BIAS || p.epilogue == EPI_BIAS_GELU) {
-          if (p.bias != nullptr) {
+        // the TMA store that last read this staging buffer must have finished reading it
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+        if (p.epilogue == EPI_MUL_AUX) {
+          // out = acc ⊙ aux : the aux tile (e.g. gelu'(z)) is bulk-loaded by TMA into the staging buffer,
+          // multiplied in place and stored back by TMA — no strided per-thread global loads
+          uint64_t* ab = &aux_bar[warp - kEpiWarp0];
+          if (lane == 0) {
+            mbar_arrive_expect_tx(ab, 4096);
+            tma_load_2d(sbuf, &tmap_z, ab, static_cast<int32_t>(nc), static_cast<int32_t>(m0));
+          }
+          uint32_t acc[64];
+          tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
+          tmem_ld_32x32b_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
+          tmem_ld_wait();
+          mbar_wait(ab, aux_phase);
+          aux_phase ^= 1;
+          const float* f = reinterpret_cast<const float*>(acc);
 #pragma unroll
-            for (uint32_t v = 0; v < 8; ++v) {
-              if (nc + v * 8 < p.N) {
-                const uint4 b = ld_nc_v4(p.bias + nc + v * 8);
+          for (uint32_t v = 0; v < 8; ++v) {
+            uint4* sp = reinterpret_cast<uint4*>(srow + ((v ^ (lane & 7)) << 4));
+            const uint4 a4 = *sp;
+            const float2 a0 = unpack_bf16(a4.x), a1 = unpack_bf16(a4.y), a2 = unpack_bf16(a4.z), a3 = unpack_bf16(a4.w);
+            uint4 pk;
+            pk.x = pack_bf16(f[v * 8 + 0] * a0.x, f[v * 8 + 1] * a0.y); pk.y = pack_bf16(f[v * 8 + 2] * a1.x, f[v * 8 + 3] * a1.y);
+            pk.z = pack_bf16(f[v * 8 + 4] * a2.x, f[v * 8 + 5] * a2.y); pk.w = pack_bf16(f[v * 8 + 6] * a3.x, f[v * 8 + 7] * a3.y);
+            *sp = pk;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_c, sbuf, static_cast<int32_t>(nc), static_cast<int32_t>(m0));
+            tma_store_commit();
+          }
+          continue;
+        }
+        const bool dual = (p.epilogue == EPI_BIAS_GELU);
+        uint32_t gpk[32];                                 // gelu'(z) packed bf16 (second store), dual only
+#pragma unroll
+        for (uint32_t hcol = 0; hcol < 2; ++hcol) {        // two 32-column halves keep registers low
+          uint32_t acc[32];
+          tmem_ld_32x32b_x32(taddr + hcol * 32, acc);
+          tmem_ld_wait();
+          float* f = reinterpret_cast<float*>(acc);
+          const uint32_t nh = nc + hcol * 32;
+          if (p.epilogue != EPI_NONE && p.bias != nullptr) {
+#pragma unroll
+            for (uint32_t v = 0; v < 4; ++v) {
+              if (nh + v * 8 < p.N) {
+                const uint4 b = ld_nc_v4(p.bias + nh + v * 8);
                 const float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
                 f[v * 8 + 0] += b0.x; f[v * 8 + 1] += b0.y; f[v * 8 + 2] += b1.x; f[v * 8 + 3] += b1.y;
                 f[v * 8 + 4] += b2.x; f[v * 8 + 5] += b2.y; f[v * 8 + 6] += b3.x; f[v * 8 + 7] += b3.y;
               }
             }
           }
-        } else if (p.epilogue == EPI_GELU_BWD) {
-          if (row < p.M) {
-            const __nv_bfloat16* zrow = p.aux + static_cast<size_t>(row) * p.ldaux + nc;
 #pragma unroll
-            for (uint32_t v = 0; v < 8; ++v) {
-              if (nc + v * 8 < p.N) {
-                const uint4 z = ld_nc_v4(zrow + v * 8);
-                const float2 z0 = unpack_bf16(z.x), z1 = unpack_bf16(z.y), z2 = unpack_bf16(z.z), z3 = unpack_bf16(z.w);
-                f[v * 8 + 0] *= gelu_erf_grad(z0.x); f[v * 8 + 1] *= gelu_erf_grad(z0.y);
-                f[v * 8 + 2] *= gelu_erf_grad(z1.x); f[v * 8 + 3] *= gelu_erf_grad(z1.y);
-                f[v * 8 + 4] *= gelu_erf_grad(z2.x); f[v * 8 + 5] *= gelu_erf_grad(z2.y);
-                f[v * 8 + 6] *= gelu_erf_grad(z3.x); f[v * 8 + 7] *= gelu_erf_grad(z3.y);
-              }
-            }
-          }
-        }
-        const int npass = (p.epilogue == EPI_BIAS_GELU && p.has_z) ? 2 : 1;
-        for (int pass = 0; pass < npass; ++pass) {
-          const bool store_z = (npass == 2 && pass == 0);
-          const bool do_gelu = (p.epilogue == EPI_BIAS_GELU) && !store_z;
-          // the TMA store that last read this staging buffer must have finished reading it
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
-          uint8_t* sbuf = my_stage + buf * 4096;
-          uint8_t* srow = sbuf + lane * 128;
-#pragma unroll
-          for (uint32_t v = 0; v < 8; ++v) {
+          for (uint32_t v = 0; v < 4; ++v) {
             float x[8];
+            if (dual) {
+              float g[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) x[e] = do_gelu ? gelu_erf(f[v * 8 + e]) : f[v * 8 + e];
+              for (int e = 0; e < 8; ++e) gelu_both(f[v * 8 + e], x[e], g[e]);
+              gpk[(hcol * 4 + v) * 4 + 0] = pack_bf16(g[0], g[1]); gpk[(hcol * 4 + v) * 4 + 1] = pack_bf16(g[2], g[3]);
+              gpk[(hcol * 4 + v) * 4 + 2] = pack_bf16(g[4], g[5]); gpk[(hcol * 4 + v) * 4 + 3] = pack_bf16(g[6], g[7]);
+            } else {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) x[e] = f[v * 8 + e];
+            }
             uint4 pk;
             pk.x = pack_bf16(x[0], x[1]); pk.y = pack_bf16(x[2], x[3]);
             pk.z = pack_bf16(x[4], x[5]); pk.w = pack_bf16(x[6], x[7]);
-            *reinterpret_cast<uint4*>(srow + ((v ^ (lane & 7)) << 4)) = pk;   // 128B swizzle
+            *reinterpret_cast<uint4*>(srow + (((hcol * 4 + v) ^ (lane & 7)) << 4)) = pk;   // 128B swizzle
           }
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmap_c, sbuf, static_cast<int32_t>(nc), static_cast<int32_t>(m0));
+          tma_store_commit();
+        }
+        if (dual && p.has_z) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+#pragma unroll
+          for (uint32_t v = 0; v < 8; ++v)
+            *reinterpret_cast<uint4*>(srow + ((v ^ (lane & 7)) << 4)) =
+                make_uint4(gpk[v * 4 + 0], gpk[v * 4 + 1], gpk[v * 4 + 2], gpk[v * 4 + 3]);
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(store_z ? &tmap_z : &tmap_c, sbuf, static_cast<int32_t>(nc), static_cast<int32_t>(m0));
+            tma_store_2d(&tmap_z, sbuf, static_cast<int32_t>(nc), static_cast<int32_t>(m0));
             tma_store_commit();
           }
-          buf ^= 1;
         }
       }
       // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
@@ -297,6 +337,13 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r == CUDA_ERROR_INVALID_CONTEXT || r == CUDA_ERROR_NOT_INITIALIZED) {
+    // first CUDA call on this host thread (e.g. an autograd worker): bind the primary context and retry
+    cudaFree(nullptr);
+    r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
   return r == CUDA_SUCCESS ? 0 : 900 + static_cast<int>(r);
 }
 
@@ -349,9 +396,7 @@ extern "C" int qn_gemm_bf16(const void* a, const void* b, void* c, int M, int N,
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.epilogue = epilogue;
   p.has_z = (epilogue == EPI_BIAS_GELU && z_or_aux != nullptr) ? 1 : 0;
-  p.aux = (epilogue == EPI_GELU_BWD) ? static_cast<const __nv_bfloat16*>(z_or_aux) : nullptr;
-  p.ldaux = static_cast<uint32_t>(ldz);
-  if (epilogue == EPI_GELU_BWD && (z_or_aux == nullptr || (ldz % 8))) return 911;
+  if (epilogue == EPI_MUL_AUX && (z_or_aux == nullptr || (ldz % 8))) return 911;
   if ((epilogue == EPI_BIAS || epilogue == EPI_BIAS_GELU) && bias != nullptr && (N % 8)) return 912;
 
   CUtensorMap ta, tb, tc, tz;
@@ -362,7 +407,7 @@ extern "C" int qn_gemm_bf16(const void* a, const void* b, void* c, int M, int N,
   if (rc) return rc;
   rc = make_tmap(&tc, c, M, N, ldc, 64, 32);
   if (rc) return rc;
-  if (p.has_z) {
+  if (p.has_z || epilogue == EPI_MUL_AUX) {
     if ((ldz % 8) || (reinterpret_cast<uintptr_t>(z_or_aux) & 15)) return 913;
     rc = make_tmap(&tz, z_or_aux, M, N, ldz, 64, 32);
     if (rc) return rc;

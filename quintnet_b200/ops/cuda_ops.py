@@ -13,7 +13,7 @@ import torch.nn.functional as F
 
 from . import native
 
-EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_GELU_BWD = 0, 1, 2, 3
+EPI_NONE, EPI_BIAS, EPI_BIAS_GELU, EPI_MUL_AUX = 0, 1, 2, 3
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
 
@@ -85,11 +85,7 @@ class _Linear(torch.autograd.Function):
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
         if ctx.act == "gelu":
-            dz = torch.empty_like(dy2)
-            native.check(_lib().qn_gelu_bwd(dy2.data_ptr(), z.data_ptr(), dz.data_ptr(), dy2.numel(),
-                                            native.stream()), "qn_gelu_bwd")
-            native.count()
-            dy2 = dz
+            dy2 = dy2 * z            # z holds gelu'(pre-activation), written by the forward epilogue
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             # dX[M,K] = dY[M,N] · W[N,K]        (B stored [K_red=N, N_out=K] -> MN-major)
@@ -130,7 +126,7 @@ class _FusedMLP(torch.autograd.Function):
         dy2 = dy.reshape(M, O)
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
-        dz = gemm(dy2, w2, M, I, O, b_mn=True, epilogue=EPI_GELU_BWD, z=z)     # (dY·W2) ⊙ gelu'(z)
+        dz = gemm(dy2, w2, M, I, O, b_mn=True, epilogue=EPI_MUL_AUX, z=z)      # (dY·W2) ⊙ gelu'(z), z := gelu'
         dw2 = gemm(dy2, a, O, I, M, a_mn=True, b_mn=True) if ctx.needs_input_grad[3] else None
         db2 = colsum(dy2) if (ctx.has_b2 and ctx.needs_input_grad[4]) else None
         dx = gemm(dz, w1, M, E, I, b_mn=True).view(ctx.xshape) if ctx.needs_input_grad[0] else None

@@ -70,7 +70,20 @@ class DataParallel(nn.Module):
         if isinstance(self.backend, NVLinkBackend):
             from ....ops import symm
             group = self.distributed_config.process_group
-            return lambda n, dtype, device: symm.alloc(n, dtype, device, group)
+            state = {"ok": True}
+
+            def alloc(n, dtype, device):
+                if state["ok"]:
+                    try:
+                        return symm.alloc(n, dtype, device, group)
+                    except Exception as e:  # noqa: BLE001 — loud, not silent
+                        import sys
+                        state["ok"] = False
+                        print(f"[quintnet_b200] WARNING: symmetric memory unavailable ({e}); "
+                              f"DP buckets fall back to NCCL collectives", file=sys.stderr, flush=True)
+                return torch.zeros(n, dtype=dtype, device=device)
+
+            return alloc
         return None
 
     def _setup(self) -> None:

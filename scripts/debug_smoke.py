@@ -58,3 +58,14 @@ for name, p in model.named_parameters():
     if p.grad is not None and not torch.isfinite(p.grad.float()).all():
         print("NON-FINITE grad", name)
 print("done")
+
+# ---- tiny GPT-2 (head_dim 32 -> library attention) all-gradient comparison vs fp32 CPU
+cfg2 = GPT2Config(vocab_size=512, n_positions=64, n_embd=128, n_layer=2, n_head=4, resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
+ref = GPT2Model(cfg2, seed=3)
+gpu = GPT2Model(cfg2, device=dev, dtype=torch.bfloat16, seed=3)
+ids2 = torch.randint(0, 512, (8, 64))
+lr_, nr = ref(ids2, labels=ids2); (lr_ / nr).backward()
+lg, ng = gpu(ids2.cuda(), labels=ids2.cuda()); (lg / ng).backward()
+print("tiny loss", (lr_ / nr).item(), (lg / ng).item())
+for (n1, p1), (n2, p2) in zip(ref.named_parameters(), gpu.named_parameters()):
+    print(f"  grad rel {n1:45s} {rel(p2.grad.cpu(), p1.grad):.3e}")

@@ -56,13 +56,18 @@ def test_gemm_epilogues():
     assert _rel(c, ref) < 1e-2
     z = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     g = cuda_ops.gemm(a, b, M, N, K, epilogue=cuda_ops.EPI_BIAS_GELU, bias=bias, z=z)
-    assert _rel(z, ref) < 1e-2
+    dg = 0.5 * (1 + torch.erf(ref / math.sqrt(2))) + ref * torch.exp(-0.5 * ref * ref) / math.sqrt(2 * math.pi)
+    assert _rel(z, dg) < 1e-2, "second output = gelu'(pre-activation)"
     assert _rel(g, F.gelu(ref)) < 1e-2
-    zz = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
-    gb = cuda_ops.gemm(a, b, M, N, K, epilogue=cuda_ops.EPI_GELU_BWD, z=zz)
-    zf = zz.float()
-    dg = 0.5 * (1 + torch.erf(zf / math.sqrt(2))) + zf * torch.exp(-0.5 * zf * zf) / math.sqrt(2 * math.pi)
-    assert _rel(gb, (a.float() @ b.float().t()) * dg) < 1.5e-2
+    aux = torch.randn(M, N, device="cuda", dtype=torch.bfloat16)
+    gb = cuda_ops.gemm(a, b, M, N, K, epilogue=cuda_ops.EPI_MUL_AUX, z=aux)
+    assert _rel(gb, (a.float() @ b.float().t()) * aux.float()) < 1.5e-2
+    for (m2, n2) in [(130, 200), (1000, 328)]:          # ragged tiles through the TMA aux path
+        a2 = torch.randn(m2, K, device="cuda", dtype=torch.bfloat16)
+        b2 = torch.randn(n2, K, device="cuda", dtype=torch.bfloat16) * 0.1
+        x2 = torch.randn(m2, n2, device="cuda", dtype=torch.bfloat16)
+        o2 = cuda_ops.gemm(a2, b2, m2, n2, K, epilogue=cuda_ops.EPI_MUL_AUX, z=x2)
+        assert _rel(o2, (a2.float() @ b2.float().t()) * x2.float()) < 1.5e-2
 
 
 def test_linear_autograd():
