@@ -37,6 +37,31 @@ struct GemmParams {
   int has_z;                   // EPI_BIAS_GELU: also store gelu'(z) through tmap_z (consumed by EPI_MUL_AUX)
 };
 
+// Fused tensor-parallel collectives (FUSE template parameter of the kernel):
+//   FUSE_AG (K3): the A operand is the all-gather of every rank's row shard.  Local rows are read straight from
+//     x_local; warps 2-3 of every CTA PUSH this rank's shard into the peers' symmetric gather buffers over
+//     NVLink (plain 16-byte stores) and publish a per-32-row release flag; the TMA producer acquires the flags
+//     of a remote 128-row block before its first load.  Tiles are ordered local-rows-first, so the transfer
+//     hides behind the local half of the GEMM.
+//   FUSE_RS (K4): the output is reduce-scattered by rows.  Partial tiles whose rows belong to a peer are
+//     written from the epilogue into that peer's symmetric staging buffer (coalesced 16-byte NVLink stores) and
+//     flagged; tiles owned by this rank are processed LAST and their epilogue adds the peers' partials (TMA
+//     load from the local staging buffer after acquiring the flag) before the bias / store.
+enum Fuse : int { FUSE_NONE = 0, FUSE_AG = 1, FUSE_RS = 2 };
+constexpr int TP_MAX = 8;
+struct TpComm {
+  int rank, world;
+  uint32_t seq;                       // launch sequence number of this workspace (flags hold seq values)
+  uint32_t rows_per_rank, mb_per_rank;
+  const __nv_bfloat16* x_local;       // AG: [rows_per_rank, K] contiguous
+  __nv_bfloat16* gather[TP_MAX];      // AG: every rank's gather buffer [M, K] (peer mappings)
+  uint32_t* ag_flags[TP_MAX];         // AG: every rank's per-32-row flags [M / 32]
+  __nv_bfloat16* stage[TP_MAX];       // RS: every rank's staging buffer [world][rows_per_rank][N]
+  uint32_t* rs_flags[TP_MAX];         // RS: every rank's flags [mb_per_rank][4][N/64][world]
+};
+
+QN_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 template <uint32_t BLOCK_N>
 struct Cfg {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
@@ -59,11 +84,11 @@ QN_DEVICE void tile_coords(uint32_t tile, uint32_t tiles_m, uint32_t tiles_n, ui
   n_blk = in_group / gsize;
 }
 
-template <uint32_t BLOCK_N, bool A_MN, bool B_MN>
+template <uint32_t BLOCK_N, bool A_MN, bool B_MN, int FUSE>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_z,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmap_x, const GemmParams p, const TpComm tc) {
   using C = Cfg<BLOCK_N>;
   constexpr uint32_t kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -83,6 +108,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const uint32_t num_tiles = tiles_m * tiles_n;
   const uint32_t num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  // tile order: AG walks this rank's own row blocks first, RS walks them last
+  const uint32_t m_shift = FUSE == FUSE_AG ? tc.rank * tc.mb_per_rank
+                         : FUSE == FUSE_RS ? ((tc.rank + 1) % tc.world) * tc.mb_per_rank : 0u;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmap_a);
@@ -115,14 +143,26 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         uint32_t m_blk, n_blk;
         tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
+        m_blk = (m_blk + m_shift) % tiles_m;
         const int32_t m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+        bool a_remote = false;
+        if constexpr (FUSE == FUSE_AG) {
+          a_remote = (m_blk / tc.mb_per_rank) != static_cast<uint32_t>(tc.rank);
+          if (a_remote) {                 // the peer's pushes of these 128 rows must have landed
+            for (uint32_t u = 0; u < 4; ++u) wait_flag_ge(tc.ag_flags[tc.rank] + m_blk * 4 + u, tc.seq);
+            fence_proxy_async_all();      // generic-proxy (NVLink) writes -> async-proxy (TMA) reads
+          }
+        }
         for (uint32_t kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           const int32_t k0 = kb * BLOCK_K;
-          if constexpr (!A_MN) {
+          if constexpr (FUSE == FUSE_AG) {
+            if (a_remote) tma_load_2d(sa, &tmap_x, &full_bar[stage], k0, m0);
+            else tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0 - tc.rank * static_cast<int32_t>(tc.rows_per_rank));
+          } else if constexpr (!A_MN) {
             tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0);                 // box {64 K, 128 M}
           } else {
 #pragma unroll
@@ -172,6 +212,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
+  } else if (FUSE == FUSE_AG && (warp == 2 || warp == 3)) {
+    // ------------------------------------------------ all-gather push (this rank's shard -> every peer)
+    const uint32_t units = tc.rows_per_rank / 32;
+    const uint32_t vec_per_unit = 32 * p.K / 8;                 // 16-byte vectors per 32-row unit
+    for (uint32_t u = blockIdx.x * 2 + (warp - 2); u < units; u += gridDim.x * 2) {
+      const uint4* src = reinterpret_cast<const uint4*>(tc.x_local + static_cast<size_t>(u) * 32 * p.K);
+      const size_t dst_off = (static_cast<size_t>(tc.rank) * tc.rows_per_rank + u * 32) * p.K;
+      for (uint32_t i = lane; i < vec_per_unit; i += 32 * 8) {
+        uint4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) if (i + j * 32 < vec_per_unit) v[j] = ld_nc_v4(src + i + j * 32);
+        for (int pr = 1; pr < tc.world; ++pr) {
+          uint4* dst = reinterpret_cast<uint4*>(tc.gather[(tc.rank + pr) % tc.world] + dst_off);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (i + j * 32 < vec_per_unit) st_v4(dst + i + j * 32, v[j]);
+        }
+      }
+      __threadfence_system();
+      __syncwarp();
+      if (lane == 0)
+        for (int pr = 1; pr < tc.world; ++pr)
+          st_release_sys(tc.ag_flags[(tc.rank + pr) % tc.world] + tc.rank * units + u, tc.seq);
+    }
   } else if (warp >= kEpiWarp0) {
     // ---------------------------------------------------------------- epilogue (8 warps)
     // warp -> TMEM lane quarter (warp % 4) and column half ((warp - 4) / 4): two warps share each 32-row
@@ -185,6 +248,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       uint32_t m_blk, n_blk;
       tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
+      m_blk = (m_blk + m_shift) % tiles_m;
       const uint32_t m0 = m_blk * BLOCK_M + q * 32, n0 = n_blk * BLOCK_N;
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
@@ -197,6 +261,82 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // the TMA store that last read this staging buffer must have finished reading it
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
+        if constexpr (FUSE == FUSE_RS) {
+          const uint32_t owner = m_blk / tc.mb_per_rank;
+          const uint32_t m_loc = m0 - owner * tc.rows_per_rank;          // first row of this warp's slab in the owner's shard
+          const uint32_t n_chunks = (p.N + 63) / 64;
+          const uint32_t fidx = (((m_blk % tc.mb_per_rank) * 4 + q) * n_chunks + (nc >> 6)) * tc.world;
+          uint32_t acc[64];
+          tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
+          tmem_ld_32x32b_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
+          tmem_ld_wait();
+          float* f = reinterpret_cast<float*>(acc);
+          if (p.bias != nullptr) {                                     // bias rides on the partial of the rank that owns it
+#pragma unroll
+            for (uint32_t v = 0; v < 8; ++v) {
+              if (nc + v * 8 < p.N) {
+                const uint4 b = ld_nc_v4(p.bias + nc + v * 8);
+                const float2 b0 = unpack_bf16(b.x), b1 = unpack_bf16(b.y), b2 = unpack_bf16(b.z), b3 = unpack_bf16(b.w);
+                f[v * 8 + 0] += b0.x; f[v * 8 + 1] += b0.y; f[v * 8 + 2] += b1.x; f[v * 8 + 3] += b1.y;
+                f[v * 8 + 4] += b2.x; f[v * 8 + 5] += b2.y; f[v * 8 + 6] += b3.x; f[v * 8 + 7] += b3.y;
+              }
+            }
+          }
+          if (owner == static_cast<uint32_t>(tc.rank)) {
+            // reduce: add every peer's partial of this [32 x 64] slab (flag acquire -> TMA load -> smem)
+            uint64_t* ab = &aux_bar[warp - kEpiWarp0];
+            for (int pr = 1; pr < tc.world; ++pr) {
+              const uint32_t src = (tc.rank + pr) % tc.world;
+              if (lane == 0) {
+                wait_flag_ge(tc.rs_flags[tc.rank] + fidx + src, tc.seq);
+                fence_proxy_async_all();
+                mbar_arrive_expect_tx(ab, 4096);
+                tma_load_2d(sbuf, &tmap_x, ab, static_cast<int32_t>(nc), static_cast<int32_t>(src * tc.rows_per_rank + m_loc));
+              }
+              mbar_wait(ab, aux_phase);
+              aux_phase ^= 1;
+#pragma unroll
+              for (uint32_t v = 0; v < 8; ++v) {
+                const uint4 a4 = *reinterpret_cast<const uint4*>(srow + ((v ^ (lane & 7)) << 4));
+                const float2 a0 = unpack_bf16(a4.x), a1 = unpack_bf16(a4.y), a2 = unpack_bf16(a4.z), a3 = unpack_bf16(a4.w);
+                f[v * 8 + 0] += a0.x; f[v * 8 + 1] += a0.y; f[v * 8 + 2] += a1.x; f[v * 8 + 3] += a1.y;
+                f[v * 8 + 4] += a2.x; f[v * 8 + 5] += a2.y; f[v * 8 + 6] += a3.x; f[v * 8 + 7] += a3.y;
+              }
+              __syncwarp();
+            }
+          }
+#pragma unroll
+          for (uint32_t v = 0; v < 8; ++v) {
+            uint4 pk;
+            pk.x = pack_bf16(f[v * 8 + 0], f[v * 8 + 1]); pk.y = pack_bf16(f[v * 8 + 2], f[v * 8 + 3]);
+            pk.z = pack_bf16(f[v * 8 + 4], f[v * 8 + 5]); pk.w = pack_bf16(f[v * 8 + 6], f[v * 8 + 7]);
+            *reinterpret_cast<uint4*>(srow + ((v ^ (lane & 7)) << 4)) = pk;
+          }
+          if (owner == static_cast<uint32_t>(tc.rank)) {
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&tmap_c, sbuf, static_cast<int32_t>(nc), static_cast<int32_t>(m_loc));
+              tma_store_commit();
+            }
+          } else {
+            // scatter: coalesced 16-byte NVLink stores of the bf16 partial slab into the owner's staging buffer
+            __syncwarp();
+            __nv_bfloat16* dst = tc.stage[owner] + (static_cast<size_t>(tc.rank) * tc.rows_per_rank + m_loc) * p.N + nc;
+#pragma unroll
+            for (uint32_t i = 0; i < 8; ++i) {
+              const uint32_t r = i * 4 + (lane >> 3), c = lane & 7;
+              if (nc + c * 8 < p.N) {
+                const uint4 v = *reinterpret_cast<const uint4*>(sbuf + r * 128 + ((c ^ (r & 7)) << 4));
+                st_v4(dst + static_cast<size_t>(r) * p.N + c * 8, v);
+              }
+            }
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) st_release_sys(tc.rs_flags[owner] + fidx + tc.rank, tc.seq);
+          }
+          continue;
+        }
         if (p.epilogue == EPI_MUL_AUX) {
           // out = acc ⊙ aux : the aux tile (e.g. gelu'(z)) is bulk-loaded by TMA into the staging buffer,
           // multiplied in place and stored back by TMA — no strided per-thread global loads
@@ -349,11 +489,12 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
 
 static int g_num_sms = 0;
 
-template <uint32_t BLOCK_N, bool A_MN, bool B_MN>
+template <uint32_t BLOCK_N, bool A_MN, bool B_MN, int FUSE = FUSE_NONE>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tz,
-                  const GemmParams& p, int max_ctas, cudaStream_t stream) {
+                  const GemmParams& p, int max_ctas, cudaStream_t stream, const CUtensorMap* tx = nullptr,
+                  const TpComm* comm = nullptr) {
   using C = Cfg<BLOCK_N>;
-  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, FUSE>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -368,7 +509,9 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   const uint32_t tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
   int grid = static_cast<int>(tiles < static_cast<uint32_t>(g_num_sms) ? tiles : g_num_sms);
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  kern<<<grid, kNumThreads, C::SMEM_BYTES, stream>>>(ta, tb, tc, tz, p);
+  TpComm c0{};
+  if (FUSE != FUSE_NONE && comm == nullptr) return 914;
+  kern<<<grid, kNumThreads, C::SMEM_BYTES, stream>>>(ta, tb, tc, tz, tx ? *tx : tc, p, comm ? *comm : c0);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -424,4 +567,89 @@ extern "C" int qn_gemm_bf16(const void* a, const void* b, void* c, int M, int N,
   if (block_n == 256) QN_DISPATCH(256);
   QN_DISPATCH(128);
 #undef QN_DISPATCH
+}
+
+
+// ------------------------------------------------------------------------------- fused TP entry points
+namespace qn {
+static int fill_comm(TpComm& c, int rank, int world, unsigned seq, int M) {
+  if (world < 2 || world > TP_MAX || M % (128 * world)) return 915;
+  c.rank = rank; c.world = world; c.seq = seq;
+  c.rows_per_rank = M / world; c.mb_per_rank = c.rows_per_rank / 128;
+  return 0;
+}
+}  // namespace qn
+
+// K3  all-gather -> GEMM:  C[M, N] = epilogue( AG(x_local)[M, K] · B )
+//   x_local [M/world, K] contiguous; gather[r] / ag_flags[r]: rank r's symmetric gather buffer [M, K] and flags [M/32]
+//   (host arrays of `world` peer-mapped pointers); b as in qn_gemm_bf16; seq: per-workspace launch counter (>= 1).
+extern "C" int qn_gemm_ag_bf16(const void* x_local, void* const* gather, void* const* ag_flags, int rank, int world,
+                               unsigned seq, const void* b, void* c, int M, int N, int K, long long ldb,
+                               long long ldc, int b_mn, int epilogue, const void* bias, void* z, long long ldz,
+                               int block_n, int max_ctas, cudaStream_t stream) {
+  using namespace qn;
+  TpComm comm{};
+  if (int rc = fill_comm(comm, rank, world, seq, M)) return rc;
+  if ((K % 8) || (ldb % 8) || (ldc % 8)) return 910;
+  comm.x_local = static_cast<const __nv_bfloat16*>(x_local);
+  for (int r = 0; r < world; ++r) {
+    comm.gather[r] = static_cast<__nv_bfloat16*>(gather[r]);
+    comm.ag_flags[r] = static_cast<uint32_t*>(ag_flags[r]);
+  }
+  if (block_n == 0) block_n = (N > 128 && static_cast<long long>(M / 128) * ((N + 255) / 256) >= 96) ? 256 : 128;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.epilogue = epilogue;
+  p.has_z = (epilogue == EPI_BIAS_GELU && z != nullptr) ? 1 : 0;
+  if (epilogue == EPI_MUL_AUX) return 916;
+  CUtensorMap ta, tb, tcm, tz, tx;
+  int rc;
+  if ((rc = make_tmap(&ta, x_local, comm.rows_per_rank, K, K, 64, BLOCK_M))) return rc;
+  if ((rc = make_tmap(&tx, gather[rank], M, K, K, 64, BLOCK_M))) return rc;
+  if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
+  if (rc) return rc;
+  if ((rc = make_tmap(&tcm, c, M, N, ldc, 64, 32))) return rc;
+  if (p.has_z) { if ((rc = make_tmap(&tz, z, M, N, ldz, 64, 32))) return rc; } else tz = tcm;
+  if (block_n == 256) {
+    if (!b_mn) return launch<256, false, false, FUSE_AG>(ta, tb, tcm, tz, p, max_ctas, stream, &tx, &comm);
+    return launch<256, false, true, FUSE_AG>(ta, tb, tcm, tz, p, max_ctas, stream, &tx, &comm);
+  }
+  if (!b_mn) return launch<128, false, false, FUSE_AG>(ta, tb, tcm, tz, p, max_ctas, stream, &tx, &comm);
+  return launch<128, false, true, FUSE_AG>(ta, tb, tcm, tz, p, max_ctas, stream, &tx, &comm);
+}
+
+// K4  GEMM -> reduce-scatter:  C_local[M/world, N] = sum_ranks( A[M, K] · B ) rows of this rank (+ bias)
+//   stage[r] / rs_flags[r]: rank r's symmetric staging buffer [world][M/world][N] and flags
+//   [(M/world/128) * 4 * ceil(N/64) * world] (host arrays of peer-mapped pointers).
+extern "C" int qn_gemm_rs_bf16(const void* a, const void* b, void* c_local, void* const* stage, void* const* rs_flags,
+                               int rank, int world, unsigned seq, int M, int N, int K, long long lda, long long ldb,
+                               long long ldc, int b_mn, const void* bias, int block_n, int max_ctas,
+                               cudaStream_t stream) {
+  using namespace qn;
+  TpComm comm{};
+  if (int rc = fill_comm(comm, rank, world, seq, M)) return rc;
+  if ((lda % 8) || (ldb % 8) || (ldc % 8) || (N % 8)) return 910;
+  for (int r = 0; r < world; ++r) {
+    comm.stage[r] = static_cast<__nv_bfloat16*>(stage[r]);
+    comm.rs_flags[r] = static_cast<uint32_t*>(rs_flags[r]);
+  }
+  if (block_n == 0) block_n = (N > 128 && static_cast<long long>(M / 128) * ((N + 255) / 256) >= 96) ? 256 : 128;
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.epilogue = bias ? EPI_BIAS : EPI_NONE;
+  CUtensorMap ta, tb, tcm, tx;
+  int rc;
+  if ((rc = make_tmap(&ta, a, M, K, lda, 64, BLOCK_M))) return rc;
+  if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
+  if (rc) return rc;
+  if ((rc = make_tmap(&tcm, c_local, comm.rows_per_rank, N, ldc, 64, 32))) return rc;
+  if ((rc = make_tmap(&tx, stage[rank], static_cast<uint64_t>(world) * comm.rows_per_rank, N, N, 64, 32))) return rc;
+  if (block_n == 256) {
+    if (!b_mn) return launch<256, false, false, FUSE_RS>(ta, tb, tcm, tcm, p, max_ctas, stream, &tx, &comm);
+    return launch<256, false, true, FUSE_RS>(ta, tb, tcm, tcm, p, max_ctas, stream, &tx, &comm);
+  }
+  if (!b_mn) return launch<128, false, false, FUSE_RS>(ta, tb, tcm, tcm, p, max_ctas, stream, &tx, &comm);
+  return launch<128, false, true, FUSE_RS>(ta, tb, tcm, tcm, p, max_ctas, stream, &tx, &comm);
 }

@@ -41,7 +41,8 @@ def _enabled_set():
     v = os.environ.get("QUINTNET_NATIVE", "").strip()
     if not v or v == "all":
         dis = {s for s in os.environ.get("QUINTNET_NATIVE_DISABLE", "").split(",") if s}
-        return _DEFAULT_ENABLED - dis
+        extra = {s for s in os.environ.get("QUINTNET_NATIVE_ENABLE", "").split(",") if s}
+        return (_DEFAULT_ENABLED | extra) - dis
     if v == "none":
         return set()
     return {s.strip() for s in v.split(",") if s.strip()}

@@ -1,0 +1,198 @@
+"""Fused tensor-parallel GEMM + collective ops (K3 / K4) over NVLink symmetric memory.
+
+``allgather_linear``      Y[M, N/tp]   = act( AG(X_local)[M, K] · W_localᵀ + b )        (ColumnParallel forward)
+``linear_reduce_scatter`` Y_local[M/tp, N] = RS( X[M, K/tp] · W_localᵀ (+ b on its owner) )  (RowParallel forward)
+
+Each is ONE launch of the tcgen05 GEMM kernel (``csrc/gemm.cu``, ``FUSE_AG`` / ``FUSE_RS``) that moves the
+activations itself: pushes of the local shard into the peers' gather buffers, or epilogue stores of partial
+tiles into the owner's staging buffer, synchronised by release/acquire flags — no NCCL call.  The backward of
+one op is the other op (plus local wgrad GEMMs), so a Megatron sequence-parallel block issues exactly four
+fused GEMM+collective launches per direction.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from . import native, symm
+from .cuda_ops import EPI_BIAS, EPI_BIAS_GELU, EPI_NONE, colsum, gemm
+
+_P, _I, _L, _U32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_uint
+native.declare("qn_gemm_ag_bf16", [_P, _P, _P, _I, _I, _U32, _P, _P, _I, _I, _I, _L, _L, _I, _I, _P, _P, _L, _I, _I, _P])
+native.declare("qn_gemm_rs_bf16", [_P, _P, _P, _P, _P, _I, _I, _U32, _I, _I, _I, _L, _L, _L, _I, _P, _I, _I, _P])
+
+_FLAG_BYTES = 1 << 20
+
+
+class _Workspace:
+    """Per-TP-group symmetric scratch: double-buffered gather / staging areas + monotonically increasing flags."""
+
+    def __init__(self, group, device):
+        self.group, self.device = group, device
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.gather = [None, None]
+        self.stage = [None, None]
+        self.cap = 0
+        self.ag_flags = symm.alloc_bytes(_FLAG_BYTES, device, group)
+        self.rs_flags = symm.alloc_bytes(_FLAG_BYTES, device, group)
+        self.ag_flags.tensor.zero_()
+        self.rs_flags.tensor.zero_()
+        self.seq_ag = 0
+        self.seq_rs = 0
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+    def ensure(self, nbytes: int) -> None:
+        if nbytes <= self.cap:
+            return
+        cap = max(nbytes, 32 << 20)
+        for i in range(2):
+            self.gather[i] = symm.alloc_bytes(cap, self.device, self.group)
+            self.stage[i] = symm.alloc_bytes(cap, self.device, self.group)
+        self.cap = cap
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+
+    @staticmethod
+    def ptrs(buf: symm.SymmBuffer):
+        return (ctypes.c_void_p * buf.world)(*buf.peer_ptrs)
+
+
+_workspaces: Dict[int, _Workspace] = {}
+_unavailable: Optional[str] = None
+
+
+def _ws(group, device) -> _Workspace:
+    key = id(group)
+    if key not in _workspaces:
+        _workspaces[key] = _Workspace(group, device)
+    return _workspaces[key]
+
+
+def available(group) -> bool:
+    return symm.available(group) and _unavailable is None
+
+
+def can_fuse(rows_total: int, group, *dims) -> bool:
+    """``rows_total`` = M of the (gathered) token matrix; dims = the K / N sizes involved."""
+    P = dist.get_world_size(group)
+    flags_needed = max(rows_total // 32, (rows_total // P // 128) * 4 * ((max(dims) + 63) // 64) * P) * 4
+    return (rows_total % (128 * P) == 0 and all(int(d) % 8 == 0 for d in dims) and P <= 8
+            and flags_needed <= _FLAG_BYTES)
+
+
+def _ag_gemm(ws: _Workspace, x_local: torch.Tensor, b: torch.Tensor, b_mn: bool, N: int, K: int, epilogue: int,
+             bias, z, out_full_x: bool):
+    """returns (Y [M, N], X_full [M, K] or None)"""
+    rows = x_local.shape[0]
+    M = rows * ws.world
+    ws.ensure(M * K * 2)
+    ws.seq_ag += 1
+    par = ws.seq_ag & 1
+    y = torch.empty((M, N), dtype=torch.bfloat16, device=x_local.device)
+    rc = native.require().qn_gemm_ag_bf16(
+        x_local.data_ptr(), ws.ptrs(ws.gather[par]), ws.ptrs(ws.ag_flags), ws.rank, ws.world, ws.seq_ag,
+        b.data_ptr(), y.data_ptr(), M, N, K, b.stride(0), N, int(b_mn), epilogue, native.ptr(bias), native.ptr(z),
+        z.stride(0) if z is not None else 0, 0, 0, native.stream())
+    native.check(rc, f"qn_gemm_ag_bf16(M={M},N={N},K={K})")
+    native.count()
+    x_full = None
+    if out_full_x:
+        g = ws.gather[par].tensor[: M * K * 2].view(torch.bfloat16).view(M, K)
+        x_full = g.clone()                                   # peers' rows arrived by NVLink push
+        x_full[ws.rank * rows:(ws.rank + 1) * rows].copy_(x_local)
+    return y, x_full
+
+
+def _gemm_rs(ws: _Workspace, a: torch.Tensor, b: torch.Tensor, b_mn: bool, N: int, K: int, bias):
+    """returns Y_local [M/world, N]"""
+    M = a.shape[0]
+    ws.ensure(M * N * 2)
+    ws.seq_rs += 1
+    par = ws.seq_rs & 1
+    y = torch.empty((M // ws.world, N), dtype=torch.bfloat16, device=a.device)
+    rc = native.require().qn_gemm_rs_bf16(
+        a.data_ptr(), b.data_ptr(), y.data_ptr(), ws.ptrs(ws.stage[par]), ws.ptrs(ws.rs_flags), ws.rank, ws.world,
+        ws.seq_rs, M, N, K, a.stride(0), b.stride(0), N, int(b_mn), native.ptr(bias), 0, 0, native.stream())
+    native.check(rc, f"qn_gemm_rs_bf16(M={M},N={N},K={K})")
+    native.count()
+    return y
+
+
+class _AllGatherLinear(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, group, act):
+        K, N = x.shape[-1], w.shape[0]
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        ws = _ws(group, x.device)
+        M = x2.shape[0] * ws.world
+        z = torch.empty((M, N), dtype=torch.bfloat16, device=x.device) if act == "gelu" else None
+        epi = EPI_BIAS_GELU if act == "gelu" else (EPI_BIAS if b is not None else EPI_NONE)
+        need_x = ctx.needs_input_grad[1]
+        y, x_full = _ag_gemm(ws, x2, w, False, N, K, epi, b, z, need_x)
+        ctx.save_for_backward(x_full, w, z)
+        ctx.group, ctx.has_bias, ctx.xshape = group, b is not None, x.shape
+        return y.view(x.shape[0] * ws.world, *x.shape[1:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_full, w, z = ctx.saved_tensors
+        N, K = w.shape
+        dy2 = dy.reshape(-1, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        if z is not None:
+            dy2 = dy2 * z                                  # z = gelu'(pre-activation)
+        M = dy2.shape[0]
+        ws = _ws(ctx.group, dy.device)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:                        # dX_local = RS(dY · W)
+            dx = _gemm_rs(ws, dy2, w, True, K, N, None).view(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            dw = gemm(dy2, x_full, N, K, M, a_mn=True, b_mn=True)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2)
+        return dx, dw, db, None, None
+
+
+class _LinearReduceScatter(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, b, group):
+        K, N = x.shape[-1], w.shape[0]
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        ws = _ws(group, x.device)
+        y = _gemm_rs(ws, x2, w, False, N, K, b)
+        ctx.save_for_backward(x2, w)
+        ctx.group, ctx.has_bias, ctx.xshape = group, b is not None, x.shape
+        return y.view(x.shape[0] // ws.world, *x.shape[1:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        N, K = w.shape
+        dy2 = dy.reshape(-1, N)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        ws = _ws(ctx.group, dy.device)
+        M = x2.shape[0]
+        need_full = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        # dX = AG(dY_local) · W   (W [N, K] stored [K_red = N, N_out = K] -> MN-major B)
+        dx, dy_full = _ag_gemm(ws, dy2, w, True, K, N, EPI_NONE, None, None, need_full)
+        dw = gemm(dy_full, x2, N, K, M, a_mn=True, b_mn=True) if ctx.needs_input_grad[1] else None
+        db = colsum(dy_full) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx.view(ctx.xshape), dw, db, None
+
+
+def allgather_linear(x, w, b, group, act: Optional[str] = None):
+    return _AllGatherLinear.apply(x, w, b, group, act)
+
+
+def linear_reduce_scatter(x, w, b, group):
+    return _LinearReduceScatter.apply(x, w, b, group)

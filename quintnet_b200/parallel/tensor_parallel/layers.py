@@ -29,14 +29,15 @@ from ...core.communication import (All_Gather, All_Reduce, Copy_To_Parallel, Red
                                    Scatter_To_Parallel, group_rank, group_size)
 
 
-def _fused_tp_ok(x: torch.Tensor, group) -> bool:
+def _fused_tp_ok(x: torch.Tensor, group, rows_total: int, *dims) -> bool:
+    """True when the fused sm_100a GEMM+collective kernel can serve this call."""
     if not x.is_cuda or x.dtype != torch.bfloat16 or group_size(group) == 1:
         return False
     from ...ops import native
-    if "tp_fused" not in native._enabled_set():
+    if "tp_fused" not in native._enabled_set() or not native.available():
         return False
     from ...ops import tp_fused
-    return tp_fused.available(group)
+    return tp_fused.available(group) and tp_fused.can_fuse(rows_total, group, *dims)
 
 
 class ColumnParallelLinear(nn.Module):
@@ -70,7 +71,9 @@ class ColumnParallelLinear(nn.Module):
         w, b = self.proj.weight, self.proj.bias
         if self.sequence_parallel and group_size(self.tp_group) > 1:
             # x is token-sharded along dim 0: all-gather -> GEMM
-            if _fused_tp_ok(x, self.tp_group):
+            rows_total = (x.numel() // x.shape[-1]) * group_size(self.tp_group)
+            if _fused_tp_ok(x, self.tp_group, rows_total, w.shape[0], w.shape[1]) and \
+                    (b is None or b.dtype == torch.bfloat16):
                 from ...ops import tp_fused
                 return tp_fused.allgather_linear(x, w, b, self.tp_group, self.activation)
             xg = All_Gather.apply(x, self.tp_group, "reduce_scatter", 0)
@@ -119,7 +122,9 @@ class RowParallelLinear(nn.Module):
             x = Scatter_To_Parallel.apply(x, self.tp_group, -1)
         w = self.proj.weight
         if self.sequence_parallel and n > 1:
-            if _fused_tp_ok(x, self.tp_group):
+            rows_total = x.numel() // x.shape[-1]
+            if _fused_tp_ok(x, self.tp_group, rows_total, w.shape[0], w.shape[1]) and \
+                    (self.bias is None or self.bias.dtype == torch.bfloat16):
                 from ...ops import tp_fused
                 return tp_fused.linear_reduce_scatter(x, w, self.bias, self.tp_group)
             y = ops.linear(x, w, self.bias)          # bias joins rank 0's partial sum

@@ -100,3 +100,55 @@ def test_ddp_nvlink_backend():
 
 def test_zero1_fused_kernels():
     run_distributed(_zero1_native, 2, backend="nccl")
+
+
+def _tp_fused(rank, world):
+    """Fused AG->GEMM / GEMM->RS kernels == unfused collectives + dense GEMM, forward and backward."""
+    import torch.nn.functional as F
+    from quintnet_b200.ops import tp_fused
+    dev = torch.device("cuda", rank)
+    g = dist.group.WORLD
+    torch.manual_seed(0)
+    for (M, K, N) in [(512, 256, 384), (2048, 1024, 1536), (4096, 512, 256)]:
+        rows = M // world
+        X = (torch.randn(M, K, device=dev) * 0.5).to(torch.bfloat16)             # same on every rank (same seed)
+        W = (torch.randn(N, K, device=dev) * 0.05).to(torch.bfloat16)
+        b = torch.randn(N, device=dev).to(torch.bfloat16)
+        dY = torch.randn(M, N, device=dev).to(torch.bfloat16)
+        # ---- all-gather -> GEMM (+ gelu)
+        for act in (None, "gelu"):
+            xl = X[rank * rows:(rank + 1) * rows].clone().requires_grad_(True)
+            w = W.clone().requires_grad_(True)
+            bb = b.clone().requires_grad_(True)
+            y = tp_fused.allgather_linear(xl, w, bb, g, act)
+            y.backward(dY)
+            Xr, Wr, br = X.float().requires_grad_(True), W.float().requires_grad_(True), b.float().requires_grad_(True)
+            yr = F.linear(Xr, Wr, br)
+            if act == "gelu":
+                yr = F.gelu(yr)
+            yr.backward(dY.float())
+            rel = lambda a, c: ((a.float() - c.float()).norm() / (c.float().norm() + 1e-9)).item()
+            assert rel(y, yr) < 2e-2, ("ag fwd", M, K, N, act, rel(y, yr))
+            # dX_local = reduce-scatter over ranks of dY·W; every rank used the same dY -> world x the dense grad rows
+            assert rel(xl.grad, Xr.grad[rank * rows:(rank + 1) * rows] * world) < 3e-2, ("ag dx", rel(xl.grad, Xr.grad[rank * rows:(rank + 1) * rows] * world))
+            assert rel(w.grad, Wr.grad) < 3e-2, ("ag dw", rel(w.grad, Wr.grad))
+            assert rel(bb.grad, br.grad) < 3e-2
+        # ---- GEMM -> reduce-scatter (K sharded over ranks)
+        kl = K // world
+        xk = X[:, rank * kl:(rank + 1) * kl].contiguous().requires_grad_(True)
+        wk = W[:, rank * kl:(rank + 1) * kl].contiguous().requires_grad_(True)
+        bias = b.clone().requires_grad_(True) if rank == 0 else None
+        yl = tp_fused.linear_reduce_scatter(xk, wk, bias, g)
+        dYl = dY[rank * rows:(rank + 1) * rows]
+        yl.backward(dYl)
+        Xr, Wr = X.float().requires_grad_(True), W.float().requires_grad_(True)
+        yr = F.linear(Xr, Wr, b.float())
+        yr.backward(dY.float())
+        assert rel(yl, yr[rank * rows:(rank + 1) * rows]) < 2e-2, ("rs fwd", M, K, N, rel(yl, yr[rank * rows:(rank + 1) * rows]))
+        assert rel(xk.grad, Xr.grad[:, rank * kl:(rank + 1) * kl]) < 3e-2, ("rs dx",)
+        assert rel(wk.grad, Wr.grad[:, rank * kl:(rank + 1) * kl]) < 3e-2, ("rs dw",)
+    torch.cuda.synchronize()
+
+
+def test_tp_fused_gemm_collectives():
+    run_distributed(_tp_fused, 2, backend="nccl")
