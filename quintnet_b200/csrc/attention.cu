@@ -314,7 +314,9 @@ struct BwdSmem {
   static constexpr uint32_t BYTES = 10 * TILE + 256;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+constexpr uint32_t kBwdThreads = 320;   // 8 compute warps + TMA warp + MMA warp
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                 const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -323,34 +325,37 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   uint64_t* q_full = bars + 1;      // [2]
   uint64_t* q_empty = bars + 3;     // [2]
   uint64_t* sdp_full = bars + 5;
-  uint64_t* pds_full = bars + 6;    // count 4
-  uint64_t* dq_full = bars + 7;
-  uint64_t* done = bars + 8;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* pds_full = bars + 6;    // count 8 (one per compute warp)
+  uint64_t* dq_full = bars + 7;     // [2]  (dQ accumulator is double-buffered in TMEM)
+  uint64_t* done = bars + 9;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
 
+  if ((smem_u32(smem) & 1023u) != 0 && threadIdx.x == 0) { printf("[quintnet_b200] attention smem misaligned\n"); __trap(); }
   const uint32_t warp = warp_id(), lane = lane_id();
   const uint32_t kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const uint32_t k0 = kb * BKV;
   const uint32_t nq_total = (p.T + BQ - 1) / BQ;
   const uint32_t qb_first = p.causal ? kb : 0;
   const uint32_t niter = nq_total - qb_first;
+  constexpr uint32_t kTmaWarp = 8, kMmaWarp = 9;
 
-  if (warp == 4 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     prefetch_tensormap(&tmap_qkv);
     prefetch_tensormap(&tmap_do);
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-    mbar_init(sdp_full, 1); mbar_init(pds_full, 4); mbar_init(dq_full, 1); mbar_init(done, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&dq_full[i], 1); }
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 8); mbar_init(done, 1);
     fence_barrier_init();
   }
-  if (warp == 5) tmem_alloc<512>(tmem_ptr);
+  if (warp == kMmaWarp) tmem_alloc<512>(tmem_ptr);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem = *tmem_ptr;
+  // TMEM columns: S 0-127 | dP 128-255 | dV 256-319 | dK 320-383 | dQ[0] 384-447 | dQ[1] 448-511
   const uint32_t tmem_S = tmem, tmem_dP = tmem + 128, tmem_dV = tmem + 256, tmem_dK = tmem + 320, tmem_dQ = tmem + 384;
 
-  if (warp == 4) {
+  if (warp == kTmaWarp) {
     if (lane == 0) {
       mbar_arrive_expect_tx(kv_full, 2 * TILE);
       tma_load_4d(smem + BwdSmem::K, &tmap_qkv, kv_full, 0, p.H + h, k0, b);
@@ -364,27 +369,35 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         tma_load_4d(smem + BwdSmem::DO + s * TILE, &tmap_do, &q_full[s], 0, h, q0, b);
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == kMmaWarp) {
     if (lane == 0) {
       const uint32_t sK = smem_u32(smem + BwdSmem::K), sV = smem_u32(smem + BwdSmem::V);
       const uint32_t sP = smem_u32(smem + BwdSmem::P), sDS = smem_u32(smem + BwdSmem::DS);
-      mbar_wait(kv_full, 0);
-      for (uint32_t it = 0; it < niter; ++it) {
+      auto issue_s_dp = [&](uint32_t it) {            // S = Q·Kᵀ, dP = dO·Vᵀ of query block `it`
         const uint32_t s = it & 1, ph = (it >> 1) & 1;
         const uint32_t sQ = smem_u32(smem + BwdSmem::Q + s * TILE), sDO = smem_u32(smem + BwdSmem::DO + s * TILE);
         mbar_wait(&q_full[s], ph);
         tcgen05_fence_after();
 #pragma unroll
-        for (uint32_t k = 0; k < D / 16; ++k)      // S = Q · Kᵀ
+        for (uint32_t k = 0; k < D / 16; ++k)
           umma_bf16_ss(tmem_S, make_smem_desc_sw128(sQ + k * 32, 1024, 0), make_smem_desc_sw128(sK + k * 32, 1024, 0),
                        IDESC_S, k != 0);
 #pragma unroll
-        for (uint32_t k = 0; k < D / 16; ++k)      // dP = dO · Vᵀ
+        for (uint32_t k = 0; k < D / 16; ++k)
           umma_bf16_ss(tmem_dP, make_smem_desc_sw128(sDO + k * 32, 1024, 0), make_smem_desc_sw128(sV + k * 32, 1024, 0),
                        IDESC_S, k != 0);
         umma_commit(sdp_full);
-        mbar_wait(pds_full, it & 1);
+      };
+      mbar_wait(kv_full, 0);
+      issue_s_dp(0);
+      for (uint32_t it = 0; it < niter; ++it) {
+        const uint32_t s = it & 1;
+        const uint32_t sQ = smem_u32(smem + BwdSmem::Q + s * TILE), sDO = smem_u32(smem + BwdSmem::DO + s * TILE);
+        mbar_wait(pds_full, it & 1);                 // P / dS of block `it` are in smem, S / dP TMEM consumed
         tcgen05_fence_after();
+        // the next block's S / dP go FIRST so the compute warps can start on them while the tensor pipe
+        // is busy with this block's dV / dK / dQ
+        if (it + 1 < niter) issue_s_dp(it + 1);
 #pragma unroll
         for (uint32_t k = 0; k < BQ / 16; ++k)     // dV += Pᵀ · dO   (A = P as MN-major, B = dO as MN-major)
           umma_bf16_ss(tmem_dV, make_smem_desc_sw128(sP + k * 2048, 1024, TILE), make_smem_desc_sw128(sDO + k * 2048, 1024, TILE),
@@ -395,37 +408,56 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
                        IDESC_TT, (it | k) != 0);
 #pragma unroll
         for (uint32_t k = 0; k < BKV / 16; ++k)    // dQ = dS · K     (A = dS K-major, B = K as MN-major)
-          umma_bf16_ss(tmem_dQ, make_smem_desc_sw128(sDS + (k >> 2) * TILE + (k & 3) * 32, 1024, 0),
+          umma_bf16_ss(tmem_dQ + s * 64, make_smem_desc_sw128(sDS + (k >> 2) * TILE + (k & 3) * 32, 1024, 0),
                        make_smem_desc_sw128(sK + k * 2048, 1024, TILE), IDESC_PV, k != 0);
         umma_commit(&q_empty[s]);
-        umma_commit(dq_full);
+        umma_commit(&dq_full[s]);
       }
       umma_commit(done);
     }
   } else {
-    const uint32_t r = warp * 32 + lane;
-    const uint32_t lane_base = (warp * 32u) << 16;
+    // ------------------------------------------------------------------ 8 compute warps
+    const uint32_t qtr = warp & 3, half = warp >> 2;          // TMEM lane quarter, column half
+    const uint32_t r = qtr * 32 + lane;
+    const uint32_t lane_base = (qtr * 32u) << 16;
     uint8_t* sP = smem + BwdSmem::P;
     uint8_t* sDS = smem + BwdSmem::DS;
     const uint32_t dkey = drop_key(p.seed, b, h);
+    const float c_ds = p.scale * p.drop_scale;
+    const bool drop = p.p_drop > 0.f;
+    auto drain_dq = [&](uint32_t it) {                         // dQ block `it` -> fp32 atomics (32 columns per thread)
+      const uint32_t q = (qb_first + it) * BQ + r;
+      mbar_wait(&dq_full[it & 1], (it >> 1) & 1);
+      tcgen05_fence_after();
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(tmem_dQ + (it & 1) * 64 + lane_base + half * 32, v);
+      tmem_ld_wait();
+      if (q < p.T) {
+        float* dq = p.dq_acc + ((static_cast<size_t>(b) * p.T + q) * p.H + h) * D + half * 32;
+#pragma unroll
+        for (int e = 0; e < 32; e += 4)
+          asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dq + e), "f"(__uint_as_float(v[e])),
+                       "f"(__uint_as_float(v[e + 1])), "f"(__uint_as_float(v[e + 2])), "f"(__uint_as_float(v[e + 3]))
+                       : "memory");
+      }
+      tcgen05_fence_before();
+    };
     for (uint32_t it = 0; it < niter; ++it) {
       const uint32_t qb = qb_first + it;
       const uint32_t q = qb * BQ + r;
       const bool q_ok = q < p.T;
       const size_t stat = (static_cast<size_t>(b) * p.H + h) * p.T + (q_ok ? q : 0);
       const float lse = q_ok ? p.lse[stat] : INFINITY;        // rows beyond T -> p = 0
-      const float dl = q_ok ? p.delta[stat] : 0.f;
+      const float dl2 = (q_ok ? p.delta[stat] : 0.f) / p.drop_scale;
       const bool need_mask = (p.causal && qb == kb) || (k0 + BKV > p.T);
-      mbar_wait(sdp_full, it & 1);
-      tcgen05_fence_after();
-      // dS = P ⊙ (mask·rs·dP − δ)·scale = (P·scale·rs) ⊙ (mask·dP − δ/rs); dV uses mask·P (rs applied at the end)
-      const float c_ds = p.scale * p.drop_scale;
-      const float dl2 = dl / p.drop_scale;
-      const bool drop = p.p_drop > 0.f;
       const uint32_t klim = need_mask ? min(p.T, p.causal ? q + 1 : p.T) : 0xFFFFFFFFu;
       const uint32_t ridx = q * p.T + k0;
+      mbar_wait(sdp_full, it & 1);
+      tcgen05_fence_after();
+      // dS = (P·scale·rs) ⊙ (mask·dP − δ/rs);  dV uses mask·P (rs applied when dV is written)
 #pragma unroll 1
-      for (uint32_t c = 0; c < 4; ++c) {
+      for (uint32_t cc = 0; cc < 2; ++cc) {
+        const uint32_t c = half * 2 + cc;                      // this warp's 32-column chunk
         uint32_t sv[32], dv[32];
         tmem_ld_32x32b_x32(tmem_S + lane_base + c * 32, sv);
         tmem_ld_32x32b_x32(tmem_dP + lane_base + c * 32, dv);
@@ -452,6 +484,9 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           pk[e >> 1] = pw;
           dk[e >> 1] = pack_bf16((p0 * c_ds) * (d0 - dl2), (p1 * c_ds) * (d1 - dl2));
         }
+        // the P / dS smem tiles are still being read by the dV / dK / dQ MMAs of the previous query block:
+        // the register math above overlapped with them, the stores must wait for their completion
+        if (cc == 0 && it > 0) mbar_wait(&dq_full[(it - 1) & 1], ((it - 1) >> 1) & 1);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           st_tile_chunk(sP, r, c * 4 + g, make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
@@ -462,29 +497,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
       fence_proxy_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pds_full);
-      // dQ block -> fp32 atomics
-      mbar_wait(dq_full, it & 1);
-      tcgen05_fence_after();
-      float* dq = p.dq_acc + ((static_cast<size_t>(b) * p.T + (q_ok ? q : 0)) * p.H + h) * D;
-#pragma unroll
-      for (uint32_t c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_dQ + lane_base + c * 32, v);
-        tmem_ld_wait();
-        if (q_ok) {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) atomicAdd(dq + c * 32 + e, __uint_as_float(v[e]));
-        }
-      }
-      tcgen05_fence_before();
+      if (it > 0) drain_dq(it - 1);                // dQ of the previous block: TMEM -> fp32 atomics
     }
-    // dK / dV of this key block (thread == key row)
+    drain_dq(niter - 1);
+    // dK / dV of this key block (thread == key row): half 0 writes dK, half 1 writes dV
     mbar_wait(done, 0);
     tcgen05_fence_after();
     const uint32_t kk = k0 + r;
-#pragma unroll
-    for (uint32_t which = 0; which < 2; ++which) {          // 0 -> dK (slot 1), 1 -> dV (slot 2)
+    {
+      const uint32_t which = half;                           // 0 -> dK (slot 1), 1 -> dV (slot 2)
       const uint32_t taddr = (which == 0 ? tmem_dK : tmem_dV) + lane_base;
+      const float osc = (which == 1) ? p.drop_scale : 1.0f;  // dV carries the dropout 1/(1-p)
       __nv_bfloat16* dst = p.dqkv + (((static_cast<size_t>(b) * p.T + (kk < p.T ? kk : 0)) * 3 + (which + 1)) * p.H + h) * D;
 #pragma unroll
       for (uint32_t c = 0; c < 2; ++c) {
@@ -493,7 +516,6 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         tmem_ld_wait();
         if (kk < p.T) {
 #pragma unroll
-          const float osc = (which == 1) ? p.drop_scale : 1.0f;      // dV carries the dropout 1/(1-p)
           for (int g = 0; g < 4; ++g) {
             uint4 pk;
             pk.x = pack_bf16(__uint_as_float(v[g * 8 + 0]) * osc, __uint_as_float(v[g * 8 + 1]) * osc);
@@ -509,7 +531,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   }
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     tcgen05_fence_after();
     tmem_dealloc<512>(tmem);
   }
@@ -634,7 +656,7 @@ extern "C" int qn_attn_bwd(const void* qkv, const void* out, const void* dout, c
     configured = true;
   }
   dim3 grid((T + BKV - 1) / BKV, H, B);
-  attn_bwd_kernel<<<grid, kThreads, BwdSmem::BYTES, s>>>(tq, tdo, p);
+  attn_bwd_kernel<<<grid, kBwdThreads, BwdSmem::BYTES, s>>>(tq, tdo, p);
   const size_t groups = rows * (D / 8);
   attn_dq_convert_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, s>>>(dq_acc, p.dqkv, B, H, T);
   return (int)cudaGetLastError();

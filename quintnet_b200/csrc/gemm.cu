@@ -35,6 +35,9 @@ struct GemmParams {
   const __nv_bfloat16* bias;   // [N] or null
   int epilogue;
   int has_z;                   // EPI_BIAS_GELU: also store gelu'(z) through tmap_z (consumed by EPI_MUL_AUX)
+  uint32_t splits;             // split-K factor (>1: fp32 partials are atomically added into acc32)
+  float* acc32;                // [M, ld32] fp32, zero-initialised by the caller
+  uint32_t ld32;
 };
 
 // Fused tensor-parallel collectives (FUSE template parameter of the kernel):
@@ -107,7 +110,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
   const uint32_t tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const uint32_t num_tiles = tiles_m * tiles_n;
-  const uint32_t num_kb = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const uint32_t num_kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const uint32_t splits = p.splits > 1 ? p.splits : 1;
+  const uint32_t kb_per_split = (num_kb_total + splits - 1) / splits;
+  const uint32_t num_work = num_tiles * splits;
   // tile order: AG walks this rank's own row blocks first, RS walks them last
   const uint32_t m_shift = FUSE == FUSE_AG ? tc.rank * tc.mb_per_rank
                          : FUSE == FUSE_RS ? ((tc.rank + 1) % tc.world) * tc.mb_per_rank : 0u;
@@ -140,7 +146,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
-      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (uint32_t work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const uint32_t tile = work / splits, split = work - tile * splits;
+        const uint32_t kb_begin = split * kb_per_split, kb_end = min(num_kb_total, kb_begin + kb_per_split);
         uint32_t m_blk, n_blk;
         tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
         m_blk = (m_blk + m_shift) % tiles_m;
@@ -153,7 +161,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             fence_proxy_async_all();      // generic-proxy (NVLink) writes -> async-proxy (TMA) reads
           }
         }
-        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+        for (uint32_t kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
@@ -190,11 +198,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       constexpr uint32_t A_KSTEP = A_MN ? UMMA_K * 128 : UMMA_K * 2;
       constexpr uint32_t B_KSTEP = B_MN ? UMMA_K * 128 : UMMA_K * 2;
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (uint32_t work = blockIdx.x; work < num_work; work += gridDim.x) {
+        const uint32_t split = work % splits;
+        const uint32_t kb_begin = split * kb_per_split, kb_end = min(num_kb_total, kb_begin + kb_per_split);
         mbar_wait(&tmem_empty[as], aphase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-        for (uint32_t kb = 0; kb < num_kb; ++kb) {
+        for (uint32_t kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
@@ -203,7 +213,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (uint32_t k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(sa + k * A_KSTEP, 1024, A_LBO);
             const uint64_t bdesc = make_smem_desc_sw128(sb + k * B_KSTEP, 1024, B_LBO);
-            umma_bf16_ss(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss(tmem_d, adesc, bdesc, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -245,7 +255,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* sbuf = smem_epi + (warp - kEpiWarp0) * 4096;
     uint8_t* srow = sbuf + lane * 128;
     uint32_t as = 0, aphase = 0, aux_phase = 0;
-    for (uint32_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (uint32_t work = blockIdx.x; work < num_work; work += gridDim.x) {
+      const uint32_t tile = work / splits;
       uint32_t m_blk, n_blk;
       tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
       m_blk = (m_blk + m_shift) % tiles_m;
@@ -261,6 +272,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         // the TMA store that last read this staging buffer must have finished reading it
         if (lane == 0) tma_store_wait_read<0>();
         __syncwarp();
+        if (p.splits > 1) {
+          // split-K: fp32 partial of this K-slice -> vectorised atomics into the fp32 accumulator
+          const uint32_t row = m0 + lane;
+#pragma unroll
+          for (uint32_t hcol = 0; hcol < 2; ++hcol) {
+            uint32_t acc[32];
+            tmem_ld_32x32b_x32(taddr + hcol * 32, acc);
+            tmem_ld_wait();
+            if (row < p.M) {
+              float* dst = p.acc32 + static_cast<size_t>(row) * p.ld32 + nc + hcol * 32;
+#pragma unroll
+              for (uint32_t v = 0; v < 8; ++v) {
+                if (nc + hcol * 32 + v * 4 < p.N)
+                  asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dst + v * 4),
+                               "f"(__uint_as_float(acc[v * 4 + 0])), "f"(__uint_as_float(acc[v * 4 + 1])),
+                               "f"(__uint_as_float(acc[v * 4 + 2])), "f"(__uint_as_float(acc[v * 4 + 3]))
+                               : "memory");
+              }
+            }
+          }
+          continue;
+        }
         if constexpr (FUSE == FUSE_RS) {
           const uint32_t owner = m_blk / tc.mb_per_rank;
           const uint32_t m_loc = m0 - owner * tc.rows_per_rank;          // first row of this warp's slab in the owner's shard
@@ -506,7 +539,7 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
-  const uint32_t tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N);
+  const uint32_t tiles = ((p.M + BLOCK_M - 1) / BLOCK_M) * ((p.N + BLOCK_N - 1) / BLOCK_N) * (p.splits > 1 ? p.splits : 1);
   int grid = static_cast<int>(tiles < static_cast<uint32_t>(g_num_sms) ? tiles : g_num_sms);
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   TpComm c0{};
@@ -569,6 +602,67 @@ extern "C" int qn_gemm_bf16(const void* a, const void* b, void* c, int M, int N,
 #undef QN_DISPATCH
 }
 
+
+// ------------------------------------------------------------------------------------------- split-K
+namespace qn {
+__global__ void __launch_bounds__(256)
+f32_to_bf16_2d_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int rows, int cols, long long ld_in,
+                      long long ld_out) {
+  const long long n4 = static_cast<long long>(rows) * (cols / 4);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / (cols / 4)), c = static_cast<int>(i % (cols / 4)) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(in + r * ld_in + c);
+    *reinterpret_cast<uint2*>(out + r * ld_out + c) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+}  // namespace qn
+
+// C = A·B with the K loop split `splits` ways over CTAs (for few-tile / long-K shapes such as weight
+// gradients).  acc32: fp32 workspace [M, N] that the caller has ZEROED; the bf16 result is written to c.
+extern "C" int qn_gemm_bf16_splitk(const void* a, const void* b, void* c, float* acc32, int M, int N, int K,
+                                   long long lda, long long ldb, long long ldc, int a_mn, int b_mn, int splits,
+                                   int block_n, cudaStream_t stream) {
+  using namespace qn;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda % 8) || (ldb % 8) || (ldc % 8) || (N % 4)) return 910;
+  if (block_n == 0) block_n = N > 128 ? 256 : 128;
+  const int num_kb = (K + 63) / 64;
+  if (splits > num_kb) splits = num_kb;
+  if (splits < 1) splits = 1;
+  {  // no empty K-slices: every work unit must issue at least one MMA before its accumulator is read
+    const int per = (num_kb + splits - 1) / splits;
+    splits = (num_kb + per - 1) / per;
+  }
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.epilogue = EPI_NONE;
+  p.splits = splits; p.acc32 = acc32; p.ld32 = N;
+  CUtensorMap ta, tb, tcm;
+  int rc;
+  if (!a_mn) rc = make_tmap(&ta, a, M, K, lda, 64, BLOCK_M); else rc = make_tmap(&ta, a, K, M, lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
+  if (rc) return rc;
+  if ((rc = make_tmap(&tcm, c, M, N, ldc, 64, 32))) return rc;
+#define QN_DISPATCH_SK(BN)                                                                               \
+  do {                                                                                                    \
+    if (!a_mn && !b_mn) rc = launch<BN, false, false>(ta, tb, tcm, tcm, p, 0, stream);                    \
+    else if (!a_mn && b_mn) rc = launch<BN, false, true>(ta, tb, tcm, tcm, p, 0, stream);                 \
+    else if (a_mn && !b_mn) rc = launch<BN, true, false>(ta, tb, tcm, tcm, p, 0, stream);                 \
+    else rc = launch<BN, true, true>(ta, tb, tcm, tcm, p, 0, stream);                                     \
+  } while (0)
+  if (block_n == 256) QN_DISPATCH_SK(256); else QN_DISPATCH_SK(128);
+#undef QN_DISPATCH_SK
+  if (rc) return rc;
+  if (splits > 1) {
+    long long n4 = static_cast<long long>(M) * (N / 4);
+    int grid = static_cast<int>((n4 + 255) / 256 > 148 * 8 ? 148 * 8 : (n4 + 255) / 256);
+    f32_to_bf16_2d_kernel<<<grid, 256, 0, stream>>>(acc32, static_cast<__nv_bfloat16*>(c), M, N, N, ldc);
+    return static_cast<int>(cudaGetLastError());
+  }
+  return 0;
+}
 
 // ------------------------------------------------------------------------------- fused TP entry points
 namespace qn {

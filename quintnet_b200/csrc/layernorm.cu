@@ -177,15 +177,29 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
   }
 }
 
+// fold the per-CTA partials: block = 32 columns x 8 partial-lanes
 template <typename T>
-__global__ void ln_reduce_partials_kernel(const float* __restrict__ pg, const float* __restrict__ pb,
-                                          T* __restrict__ dgamma, T* __restrict__ dbeta, int nparts, int cols) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= cols) return;
+__global__ void __launch_bounds__(256)
+ln_reduce_partials_kernel(const float* __restrict__ pg, const float* __restrict__ pb,
+                          T* __restrict__ dgamma, T* __restrict__ dbeta, int nparts, int cols) {
+  __shared__ float sg[8][33], sb[8][33];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cx;
   float a = 0.f, b = 0.f;
-  for (int i = 0; i < nparts; ++i) { a += pg[static_cast<size_t>(i) * cols + c]; b += pb[static_cast<size_t>(i) * cols + c]; }
-  dgamma[c] = static_cast<T>(a);
-  dbeta[c] = static_cast<T>(b);
+  if (c < cols) {
+    for (int i = py; i < nparts; i += 8) {
+      a += pg[static_cast<size_t>(i) * cols + c];
+      b += pb[static_cast<size_t>(i) * cols + c];
+    }
+  }
+  sg[py][cx] = a; sb[py][cx] = b;
+  __syncthreads();
+  if (py == 0 && c < cols) {
+#pragma unroll
+    for (int i = 1; i < 8; ++i) { a += sg[i][cx]; b += sb[i][cx]; }
+    dgamma[c] = static_cast<T>(a);
+    dbeta[c] = static_cast<T>(b);
+  }
 }
 
 template <typename T>
@@ -239,7 +253,7 @@ static int ln_bwd(const void* dy, const void* x, const void* g, const float* mea
 #undef QN_LN_BWD
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
-  ln_reduce_partials_kernel<T><<<(cols + 127) / 128, 128, 0, s>>>(pg, pb, (T*)dgamma, (T*)dbeta, nparts, cols);
+  ln_reduce_partials_kernel<T><<<(cols + 31) / 32, 256, 0, s>>>(pg, pb, (T*)dgamma, (T*)dbeta, nparts, cols);
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -29,7 +29,8 @@ def gemm_ok(M: int, N: int, K: int, *lds) -> bool:
 def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool = False,
          b_mn: bool = False, out: Optional[torch.Tensor] = None, ldc: Optional[int] = None,
          epilogue: int = EPI_NONE, bias: Optional[torch.Tensor] = None,
-         z: Optional[torch.Tensor] = None, block_n: int = 0, max_ctas: int = 0) -> torch.Tensor:
+         z: Optional[torch.Tensor] = None, block_n: int = 0, max_ctas: int = 0,
+         split_k: int = 0) -> torch.Tensor:
     """C[M,N] = epilogue(A·B) on tcgen05.  ``a``/``b`` are 2-D row-major bf16 tensors
     (possibly with a row stride); ``a_mn`` / ``b_mn`` say the tensor is stored
     ``[K, M]`` / ``[K, N]`` instead of ``[M, K]`` / ``[N, K]``."""
@@ -44,12 +45,33 @@ def gemm(a: torch.Tensor, b: torch.Tensor, M: int, N: int, K: int, *, a_mn: bool
         ldc = out.stride(0)
         out_view = out
     ldz = z.stride(0) if z is not None else 0
+    splits = _auto_splits(M, N, K) if (epilogue == EPI_NONE and split_k != 1) else 1
+    if split_k > 1 and epilogue == EPI_NONE:
+        splits = split_k
+    if splits > 1 and N % 4 == 0:
+        acc32 = torch.zeros((M, N), dtype=torch.float32, device=a.device)
+        rc = _lib().qn_gemm_bf16_splitk(a.data_ptr(), b.data_ptr(), out.data_ptr(), acc32.data_ptr(), M, N, K,
+                                        lda, ldb, ldc, int(a_mn), int(b_mn), splits, block_n, native.stream())
+        native.check(rc, f"qn_gemm_bf16_splitk(M={M},N={N},K={K},splits={splits})")
+        native.count(3)
+        return out_view
     rc = _lib().qn_gemm_bf16(a.data_ptr(), b.data_ptr(), out.data_ptr(), M, N, K, lda, ldb, ldc,
                              int(a_mn), int(b_mn), epilogue, native.ptr(bias), native.ptr(z), ldz,
                              block_n, max_ctas, native.stream())
     native.check(rc, f"qn_gemm_bf16(M={M},N={N},K={K},a_mn={a_mn},b_mn={b_mn})")
     native.count()
     return out_view
+
+
+def _auto_splits(M: int, N: int, K: int) -> int:
+    """Split-K factor for few-tile / long-K problems (weight gradients): fill ~148 SMs."""
+    bn = 256 if N > 128 else 128
+    tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+    num_kb = (K + 63) // 64
+    if tiles >= 100 or num_kb < 32:
+        return 1
+    s = min(148 // tiles, num_kb // 8, 16)
+    return s if s >= 2 else 1
 
 
 class _Linear(torch.autograd.Function):
@@ -170,7 +192,7 @@ def linear(x, w, b=None, act: Optional[str] = None):
 
 
 # ---------------------------------------------------------------- LayerNorm
-_LN_PARTS = 148 * 2
+_LN_PARTS = 148 * 4
 
 
 class _LayerNorm(torch.autograd.Function):

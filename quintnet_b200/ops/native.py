@@ -130,6 +130,7 @@ _I, _L, _F, _P = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_
 _U = ctypes.c_ulonglong
 _SIGNATURES = {
     "qn_gemm_bf16": [_P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _P, _P, _L, _I, _I, _P],
+    "qn_gemm_bf16_splitk": [_P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _P],
     "qn_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
     "qn_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "qn_dropout_add_fwd": [_P, _P, _P, _L, _F, _U, _U, _P],

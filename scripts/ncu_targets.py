@@ -31,7 +31,7 @@ def timeit(name, fn, flops, iters=20):
 
 if what in ("gemm", "all"):
     M = 16384
-    for (N, K, tag) in [(4096, 1024, "c_fc fwd"), (1024, 4096, "mlp c_proj fwd"), (3072, 1024, "c_attn fwd"), (1024, 1024, "attn c_proj fwd")]:
+    for (N, K, tag) in [(4096, 1024, "c_fc fwd"), (1024, 4096, "mlp c_proj fwd"), (3072, 1024, "c_attn fwd"), (1024, 1024, "attn c_proj fwd"), (1536, 1024, "tp2 c_attn"), (1024, 512, "tp2 attn c_proj")]:
         a = torch.randn(M, K, device=dev, dtype=torch.bfloat16)
         w = torch.randn(N, K, device=dev, dtype=torch.bfloat16)
         dy = torch.randn(M, N, device=dev, dtype=torch.bfloat16)
@@ -40,6 +40,7 @@ if what in ("gemm", "all"):
             timeit(f"gemm TN {M}x{N}x{K} ({tag})", lambda: cuda_ops.gemm(a, w, M, N, K), fl)
             timeit(f"gemm dgrad {M}x{K}x{N}", lambda: cuda_ops.gemm(dy, w, M, K, N, b_mn=True), fl)
             timeit(f"gemm wgrad {N}x{K}x{M}", lambda: cuda_ops.gemm(dy, a, N, K, M, a_mn=True, b_mn=True), fl)
+            timeit(f"gemm wgrad {N}x{K}x{M} no-splitK", lambda: cuda_ops.gemm(dy, a, N, K, M, a_mn=True, b_mn=True, split_k=1), fl)
             timeit(f"cuBLAS TN {M}x{N}x{K}", lambda: torch.matmul(a, w.t()), fl)
         else:
             cuda_ops.gemm(a, w, M, N, K); cuda_ops.gemm(dy, w, M, K, N, b_mn=True); cuda_ops.gemm(dy, a, N, K, M, a_mn=True, b_mn=True)

@@ -267,3 +267,17 @@ def test_fused_mlp():
     assert _rel(y, yr) < 2e-2
     for t, r, n in zip((x, w1, b1, w2, b2), ref, "x w1 b1 w2 b2".split()):
         assert _rel(t.grad, r.grad) < 3e-2, (n, _rel(t.grad, r.grad))
+
+
+@pytest.mark.parametrize("M,N,K,splits", [(1024, 1024, 16384, 0), (1024, 512, 16384, 4), (256, 256, 1000, 3),
+                                          (1536, 1024, 8192, 0)])
+def test_gemm_split_k(M, N, K, splits):
+    from quintnet_b200.ops import cuda_ops
+    torch.manual_seed(11)
+    A = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    B = torch.randn(N, K, device="cuda", dtype=torch.bfloat16)
+    ref = A.float() @ B.float().t()
+    c = cuda_ops.gemm(A.t().contiguous(), B.t().contiguous(), M, N, K, a_mn=True, b_mn=True, split_k=splits)
+    assert _rel(c, ref) < 1e-2, _rel(c, ref)
+    c2 = cuda_ops.gemm(A, B, M, N, K, split_k=splits if splits else 0)
+    assert _rel(c2, ref) < 1e-2
