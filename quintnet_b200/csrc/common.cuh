@@ -201,16 +201,25 @@ QN_DEVICE float gelu_erf_grad(float x) {
 
 // GELU(z) = z·Φ(z) and GELU'(z) = Φ(z) + z·φ(z) from ONE exponential: erf via Abramowitz–Stegun 7.1.26
 // (|err| < 1.5e-7, far below bf16 resolution), sharing u = exp(-z²/2) between Φ and φ.
+QN_DEVICE float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+QN_DEVICE float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
 QN_DEVICE void gelu_both(float z, float& act, float& grad) {
-  const float az = fabsf(z);
-  const float t = __frcp_rn(fmaf(az, 0.3275911f * 0.70710678118654752f, 1.0f));
-  const float u = exp2f(z * z * (-0.5f * 1.4426950408889634f));
+  const float t = rcp_approx(fmaf(fabsf(z), 0.3275911f * 0.70710678118654752f, 1.0f));
+  const float u = ex2_approx(z * z * (-0.5f * 1.4426950408889634f));        // exp(-z^2/2)
   float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
   poly = fmaf(poly, t, 0.5f * 1.421413741f);
   poly = fmaf(poly, t, 0.5f * -0.284496736f);
   poly = fmaf(poly, t, 0.5f * 0.254829592f);
-  const float h = poly * t * u;                       // 0.5 * erfc(|z|/sqrt2)
-  const float cdf = z >= 0.f ? 1.0f - h : h;
+  const float h = poly * t * u;                                            // 0.5 * erfc(|z| / sqrt 2)
+  const float cdf = 0.5f + copysignf(0.5f - h, z);                         // branch-free Φ(z)
   act = z * cdf;
   grad = fmaf(z * 0.39894228040143267f, u, cdf);
 }

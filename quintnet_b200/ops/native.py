@@ -33,7 +33,7 @@ _load_error: Optional[str] = None
 #   QUINTNET_NATIVE=all | none | comma-separated list
 _DEFAULT_ENABLED = {
     "layernorm", "gelu", "adamw", "dropout", "rope", "cross_entropy", "gemm", "attention",
-    "allreduce", "zero1",
+    "allreduce", "zero1", "tp_fused",
 }
 
 

@@ -203,10 +203,11 @@ def test_gpt2_gpu_matches_cpu_reference():
                      resid_pdrop=0.0, embd_pdrop=0.0, attn_pdrop=0.0)
     ref = GPT2Model(cfg, seed=3)
     gpu = GPT2Model(cfg, device=torch.device("cuda"), dtype=torch.bfloat16, seed=3)
+    gpu.load_state_dict(ref.state_dict())      # CPU and CUDA generators differ: copy the weights
     ids = torch.randint(0, 512, (8, 64))
     lr_, nr = ref(ids, labels=ids)
     lg, ng = gpu(ids.cuda(), labels=ids.cuda())
-    assert abs(lg.item() / ng.item() - lr_.item() / nr.item()) < 3e-2
+    assert abs(lg.item() / ng.item() - lr_.item() / nr.item()) < 1e-2
     (lr_ / nr).backward()
     (lg / ng).backward()
     g1 = ref.blocks[0].mlp.c_fc.proj.weight.grad
