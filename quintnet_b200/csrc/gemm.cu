@@ -255,6 +255,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* sbuf = smem_epi + (warp - kEpiWarp0) * 4096;
     uint8_t* srow = sbuf + lane * 128;
     uint32_t as = 0, aphase = 0, aux_phase = 0;
+    // FUSE_RS: flags of slabs already stored to a peer but not yet published (one system fence per 4 slabs)
+    uint32_t* pend0 = nullptr; uint32_t* pend1 = nullptr; uint32_t* pend2 = nullptr; uint32_t* pend3 = nullptr;
+    uint32_t npend = 0;
+    auto flush_pending = [&]() {
+      if (npend == 0) return;
+      __threadfence_system();
+      __syncwarp();
+      if (lane == 0) {
+        st_release_sys(pend0, tc.seq);
+        if (npend > 1) st_release_sys(pend1, tc.seq);
+        if (npend > 2) st_release_sys(pend2, tc.seq);
+        if (npend > 3) st_release_sys(pend3, tc.seq);
+      }
+      npend = 0;
+    };
     for (uint32_t work = blockIdx.x; work < num_work; work += gridDim.x) {
       const uint32_t tile = work / splits;
       uint32_t m_blk, n_blk;
@@ -316,6 +331,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             }
           }
           if (owner == static_cast<uint32_t>(tc.rank)) {
+            flush_pending();     // everything this warp sent must be visible before it starts waiting
             // reduce: add every peer's partial of this [32 x 64] slab (flag acquire -> TMA load -> smem)
             uint64_t* ab = &aux_bar[warp - kEpiWarp0];
             for (int pr = 1; pr < tc.world; ++pr) {
@@ -364,9 +380,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 st_v4(dst + static_cast<size_t>(r) * p.N + c * 8, v);
               }
             }
-            __threadfence_system();
-            __syncwarp();
-            if (lane == 0) st_release_sys(tc.rs_flags[owner] + fidx + tc.rank, tc.seq);
+            uint32_t* fl = tc.rs_flags[owner] + fidx + tc.rank;
+            if (npend == 0) pend0 = fl; else if (npend == 1) pend1 = fl; else if (npend == 2) pend2 = fl; else pend3 = fl;
+            if (++npend == 4) flush_pending();
           }
           continue;
         }
@@ -469,6 +485,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (lane == 0) mbar_arrive(&tmem_empty[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if constexpr (FUSE == FUSE_RS) flush_pending();
     if (lane == 0) tma_store_wait_all<0>();
   }
 
@@ -696,7 +713,7 @@ extern "C" int qn_gemm_ag_bf16(const void* x_local, void* const* gather, void* c
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.epilogue = epilogue;
   p.has_z = (epilogue == EPI_BIAS_GELU && z != nullptr) ? 1 : 0;
-  if (epilogue == EPI_MUL_AUX) return 916;
+  if (epilogue == EPI_MUL_AUX && (z == nullptr || (ldz % 8))) return 916;
   CUtensorMap ta, tb, tcm, tz, tx;
   int rc;
   if ((rc = make_tmap(&ta, x_local, comm.rows_per_rank, K, K, 64, BLOCK_M))) return rc;
@@ -704,7 +721,7 @@ extern "C" int qn_gemm_ag_bf16(const void* x_local, void* const* gather, void* c
   if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
   if (rc) return rc;
   if ((rc = make_tmap(&tcm, c, M, N, ldc, 64, 32))) return rc;
-  if (p.has_z) { if ((rc = make_tmap(&tz, z, M, N, ldz, 64, 32))) return rc; } else tz = tcm;
+  if (p.has_z || epilogue == EPI_MUL_AUX) { if ((rc = make_tmap(&tz, z, M, N, ldz, 64, 32))) return rc; } else tz = tcm;
   if (block_n == 256) {
     if (!b_mn) return launch<256, false, false, FUSE_AG>(ta, tb, tcm, tz, p, max_ctas, stream, &tx, &comm);
     return launch<256, false, true, FUSE_AG>(ta, tb, tcm, tz, p, max_ctas, stream, &tx, &comm);

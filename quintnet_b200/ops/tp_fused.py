@@ -18,7 +18,7 @@ import torch
 import torch.distributed as dist
 
 from . import native, symm
-from .cuda_ops import EPI_BIAS, EPI_BIAS_GELU, EPI_NONE, colsum, gemm
+from .cuda_ops import EPI_BIAS, EPI_BIAS_GELU, EPI_MUL_AUX, EPI_NONE, colsum, gemm
 
 _P, _I, _L, _U32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_uint
 native.declare("qn_gemm_ag_bf16", [_P, _P, _P, _I, _I, _U32, _P, _P, _I, _I, _I, _L, _L, _I, _I, _P, _P, _L, _I, _I, _P])
@@ -101,9 +101,16 @@ def _ag_gemm(ws: _Workspace, x_local: torch.Tensor, b: torch.Tensor, b_mn: bool,
     native.count()
     x_full = None
     if out_full_x:
+        # keep the gathered operand for the weight-gradient GEMM (the symmetric buffer is recycled two
+        # launches later): peers' rows arrived by NVLink push, own rows come from x_local — M*K*2 bytes moved
         g = ws.gather[par].tensor[: M * K * 2].view(torch.bfloat16).view(M, K)
-        x_full = g.clone()                                   # peers' rows arrived by NVLink push
-        x_full[ws.rank * rows:(ws.rank + 1) * rows].copy_(x_local)
+        x_full = torch.empty((M, K), dtype=torch.bfloat16, device=x_local.device)
+        lo, hi = ws.rank * rows, (ws.rank + 1) * rows
+        if lo > 0:
+            x_full[:lo].copy_(g[:lo])
+        if hi < M:
+            x_full[hi:].copy_(g[hi:])
+        x_full[lo:hi].copy_(x_local)
     return y, x_full
 
 
@@ -188,6 +195,49 @@ class _LinearReduceScatter(torch.autograd.Function):
         dw = gemm(dy_full, x2, N, K, M, a_mn=True, b_mn=True) if ctx.needs_input_grad[1] else None
         db = colsum(dy_full) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx.view(ctx.xshape), dw, db, None
+
+
+class _SequenceParallelMLP(torch.autograd.Function):
+    """Whole tensor-parallel MLP on token-sharded activations: 2 fused launches forward
+    (AG->GEMM+bias+GELU, GEMM->RS+bias) and 2 backward (AG->GEMM ⊙ gelu', GEMM->RS) plus local wgrads."""
+
+    @staticmethod
+    def forward(ctx, x, w1, b1, w2, b2, group):
+        E, I = x.shape[-1], w1.shape[0]
+        x2 = x.reshape(-1, E)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        ws = _ws(group, x.device)
+        M = x2.shape[0] * ws.world
+        g = torch.empty((M, I), dtype=torch.bfloat16, device=x.device)           # gelu'(pre-activation)
+        a, x_full = _ag_gemm(ws, x2, w1, False, I, E, EPI_BIAS_GELU, b1, g, True)
+        y = _gemm_rs(ws, a, w2, False, w2.shape[0], I, b2)
+        ctx.save_for_backward(x_full, w1, w2, g, a)
+        ctx.group, ctx.has_b1, ctx.has_b2, ctx.xshape = group, b1 is not None, b2 is not None, x.shape
+        return y.view(*x.shape[:-1], w2.shape[0])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_full, w1, w2, g, a = ctx.saved_tensors
+        I, E = w1.shape
+        O = w2.shape[0]
+        dy2 = dy.reshape(-1, O)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        ws = _ws(ctx.group, dy.device)
+        M = x_full.shape[0]
+        # dZ = (AG(dY_local) · W2) ⊙ gelu'(z)   — gelu' applied in the fused kernel's epilogue
+        dz, dy_full = _ag_gemm(ws, dy2, w2, True, I, O, EPI_MUL_AUX, None, g, True)
+        dw2 = gemm(dy_full, a, O, I, M, a_mn=True, b_mn=True)
+        db2 = colsum(dy_full) if ctx.has_b2 else None
+        dx = _gemm_rs(ws, dz, w1, True, E, I, None).view(ctx.xshape)             # dX_local = RS(dZ · W1)
+        dw1 = gemm(dz, x_full, I, E, M, a_mn=True, b_mn=True)
+        db1 = colsum(dz) if ctx.has_b1 else None
+        return dx, dw1, db1, dw2, db2, None
+
+
+def sequence_parallel_mlp(x, w1, b1, w2, b2, group):
+    return _SequenceParallelMLP.apply(x, w1, b1, w2, b2, group)
 
 
 def allgather_linear(x, w, b, group, act: Optional[str] = None):

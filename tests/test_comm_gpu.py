@@ -152,3 +152,41 @@ def _tp_fused(rank, world):
 
 def test_tp_fused_gemm_collectives():
     run_distributed(_tp_fused, 2, backend="nccl")
+
+
+def _sp_mlp(rank, world):
+    import torch.nn.functional as F
+    from quintnet_b200.ops import tp_fused
+    dev = torch.device("cuda", rank)
+    g = dist.group.WORLD
+    torch.manual_seed(0)
+    M, E, I = 2048, 512, 2048
+    rows, il = M // world, I // world
+    X = (torch.randn(M, E, device=dev) * 0.5).to(torch.bfloat16)
+    W1 = (torch.randn(I, E, device=dev) * 0.05).to(torch.bfloat16)
+    b1 = (torch.randn(I, device=dev) * 0.1).to(torch.bfloat16)
+    W2 = (torch.randn(E, I, device=dev) * 0.05).to(torch.bfloat16)
+    b2 = (torch.randn(E, device=dev) * 0.1).to(torch.bfloat16)
+    dY = torch.randn(M, E, device=dev).to(torch.bfloat16)
+    xl = X[rank * rows:(rank + 1) * rows].clone().requires_grad_(True)
+    w1 = W1[rank * il:(rank + 1) * il].clone().requires_grad_(True)
+    bb1 = b1[rank * il:(rank + 1) * il].clone().requires_grad_(True)
+    w2 = W2[:, rank * il:(rank + 1) * il].contiguous().requires_grad_(True)
+    bb2 = b2.clone().requires_grad_(True) if rank == 0 else None
+    y = tp_fused.sequence_parallel_mlp(xl, w1, bb1, w2, bb2, g)
+    y.backward(dY[rank * rows:(rank + 1) * rows])
+    Xr, W1r, b1r, W2r, b2r = (t.float().requires_grad_(True) for t in (X, W1, b1, W2, b2))
+    yr = F.linear(F.gelu(F.linear(Xr, W1r, b1r)), W2r, b2r)
+    yr.backward(dY.float())
+    rel = lambda a, c: ((a.float() - c.float()).norm() / (c.float().norm() + 1e-9)).item()
+    assert rel(y, yr[rank * rows:(rank + 1) * rows]) < 2e-2
+    assert rel(xl.grad, Xr.grad[rank * rows:(rank + 1) * rows]) < 3e-2
+    assert rel(w1.grad, W1r.grad[rank * il:(rank + 1) * il]) < 3e-2
+    assert rel(bb1.grad, b1r.grad[rank * il:(rank + 1) * il]) < 3e-2
+    assert rel(w2.grad, W2r.grad[:, rank * il:(rank + 1) * il]) < 3e-2
+    if rank == 0:
+        assert rel(bb2.grad, b2r.grad) < 3e-2
+
+
+def test_sequence_parallel_mlp_fused():
+    run_distributed(_sp_mlp, 2, backend="nccl")
