@@ -202,7 +202,7 @@ def build_config(args, mesh, impl):
         sp = args.sequence_parallel if args.sequence_parallel is not None else (1 if tp > 1 else 0)
         cfg.update({"dtype": "float32" if args.cpu else "bfloat16", "zero_stage": zero,
                     "sequence_parallel": bool(sp) and tp > 1, "seed": 0, "weight_decay": 0.01,
-                    "bucket_cap_mb": 128})
+                    "bucket_cap_mb": 128, "pp_balance": "auto"})
     return cfg, M
 
 

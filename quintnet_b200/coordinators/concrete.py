@@ -61,6 +61,11 @@ class Hybrid3DCoordinator(BaseCoordinator):
         model_config = mc if isinstance(mc, GPT2Config) else GPT2Config.from_dict(dict(mc))
         if cfg.get("sequence_parallel") is not None:
             model_config.sequence_parallel = bool(cfg["sequence_parallel"])
+        bal = cfg.get("pp_balance")
+        if bal is not None and pg.axis_size("pp") > 1:
+            from ..parallel.pipeline_parallel.utils import balanced_gpt2_split
+            model_config.pp_layer_counts = (balanced_gpt2_split(model_config.n_layer, pg.axis_size("pp"))
+                                            if bal == "auto" else [int(c) for c in bal])
         ckpt = getattr(self, "checkpoint_path", None)
         if ckpt in (None, "", "random"):
             sd = random_gpt2_state_dict(model_config, pg, device=device, seed=int(cfg.get("seed", 0)),

@@ -56,7 +56,7 @@ def shard_hf_tensors(get, config, tp_rank: int, tp_size: int, pp_rank: int, pp_s
     E = config.n_embd
     inner = config.n_inner
     is_first, is_last = pp_rank == 0, pp_rank == pp_size - 1
-    layers = distribute_layers(config.n_layer, pp_size)[pp_rank]
+    layers = distribute_layers(config.n_layer, pp_size, getattr(config, 'pp_layer_counts', None))[pp_rank]
     out: Dict[str, torch.Tensor] = {}
 
     def put(name, t):

@@ -23,6 +23,7 @@ class GPT2Config:
     use_rope: bool = False            # RoPE instead of learned wpe (K7)
     rope_base: float = 10000.0
     sequence_parallel: bool = False   # token-sharded TP (fused AG->GEMM / GEMM->RS)
+    pp_layer_counts: Optional[list] = None   # explicit layers per pipeline stage (default: even split)
 
     def __post_init__(self):
         if self.n_inner is None:

@@ -153,7 +153,7 @@ class GPT2Stage(nn.Module):
         ``ln_f.*``)."""
         from ...parallel.pipeline_parallel.utils import distribute_layers
         is_first, is_last = pp_rank == 0, pp_rank == pp_size - 1
-        layer_ids = distribute_layers(config.n_layer, pp_size)[pp_rank]
+        layer_ids = distribute_layers(config.n_layer, pp_size, getattr(config, 'pp_layer_counts', None))[pp_rank]
         sd = state_dict
         embedding = None
         if is_first:

@@ -65,9 +65,9 @@ def merge_tp_shards(tp_states: Dict[int, dict], legacy_qkv: bool = False) -> dic
     return out
 
 
-def merge_pp_stages(stage_states: Dict[int, dict], n_layer: int) -> dict:
+def merge_pp_stages(stage_states: Dict[int, dict], n_layer: int, counts=None) -> dict:
     pp = len(stage_states)
-    layer_map = distribute_layers(n_layer, pp)
+    layer_map = distribute_layers(n_layer, pp, counts)
     out = {}
     for p in range(pp):
         for key, v in stage_states[p].items():
@@ -112,7 +112,8 @@ def merge_checkpoints(input_dir: str, output: str, prefix: str = "final_model",
         stage_states[p] = merge_tp_shards({t: shards[(p, t)]["model_state_dict"] for t in tps}, legacy_qkv)
     n_layer = int(mc.get("n_layer", 0)) or sum(
         len({k.split(".")[1] for k in s if k.startswith("blocks.")}) for s in stage_states.values())
-    merged = merge_pp_stages(stage_states, n_layer)
+    counts = (any_shard.get("parallelism_info") or {}).get("pp_layer_counts")
+    merged = merge_pp_stages(stage_states, n_layer, counts)
     hf = convert_to_hf_format(merged)
     os.makedirs(os.path.dirname(os.path.abspath(output)), exist_ok=True)
     torch.save({"model_state_dict": hf, "config": mc}, output)

@@ -48,7 +48,8 @@ def save_shard(out_dir: str, filename: str, stage_module, optimizer, config, pg_
     sharded_opt = getattr(optimizer, "handles_grad_clipping", False) and hasattr(optimizer, "shards")
     info = {"pp_rank": pg_manager.axis_rank("pp"), "tp_rank": pg_manager.axis_rank("tp"),
             "pp_size": pg_manager.axis_size("pp"), "tp_size": pg_manager.axis_size("tp"),
-            "dp_size": pg_manager.axis_size("dp"), "zero_stage": 1 if sharded_opt else 0}
+            "dp_size": pg_manager.axis_size("dp"), "zero_stage": 1 if sharded_opt else 0,
+            "pp_layer_counts": getattr(getattr(stage_module, "config", None), "pp_layer_counts", None)}
     if pg_manager.axis_rank("dp") == 0:
         payload = {
             "model_state_dict": {k: v.detach().cpu() for k, v in stage_module.state_dict().items()},
