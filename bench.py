@@ -68,15 +68,19 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, enabled: bool):
+    def __init__(self, enabled: bool, n_gpus: int = 1):
         self.proc, self.lines, self.enabled = None, [], enabled
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+        ids = [v for v in vis.split(",") if v.strip()][:n_gpus] if vis else [str(i) for i in range(n_gpus)]
+        self.ids = ",".join(ids)          # only the GPUs this job runs on (idle neighbours would skew the median)
 
     def start(self):
         if not self.enabled:
             return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.ids}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -292,7 +296,7 @@ def run_ours(args):
 
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(rank == 0 and not args.cpu)
+    sampler = ClockSampler(rank == 0 and not args.cpu, args.gpus)
     sampler.start()
     l0 = native.launch_count
     ms = timed_region(step, args.steps, device, args.cpu)
@@ -402,7 +406,7 @@ def _run_reference(args, ref_root):
 
     for _ in range(args.warmup):
         step()
-    sampler = ClockSampler(rank == 0)
+    sampler = ClockSampler(rank == 0, args.gpus)
     sampler.start()
     ms = timed_region(step, args.steps, device, False)
     clocks = sampler.stop() if rank == 0 else None
