@@ -33,6 +33,20 @@ template <> struct Vec<float> {
   }
 };
 
+// keep-mask for the 8 consecutive elements of 16-byte vector `i8` (identical in forward and backward)
+QN_DEVICE uint32_t ln_keep_mask8(const Philox& rng, uint64_t offset, uint64_t i8, uint32_t threshold) {
+  const uint4 a = rng(offset + 2 * i8), b = rng(offset + 2 * i8 + 1);
+  uint32_t m = 0;
+  m |= (a.x >= threshold) << 0; m |= (a.y >= threshold) << 1; m |= (a.z >= threshold) << 2; m |= (a.w >= threshold) << 3;
+  m |= (b.x >= threshold) << 4; m |= (b.y >= threshold) << 5; m |= (b.z >= threshold) << 6; m |= (b.w >= threshold) << 7;
+  return m;
+}
+struct LnDropout {
+  uint32_t threshold;   // 0 = no dropout
+  float scale;          // 1 / (1 - p)
+  uint64_t seed, offset;
+};
+
 constexpr int LN_WARPS = 4;
 constexpr int LN_MAXV = 8;   // max vectors per lane kept in registers: cols <= 32*8*VecN (2048 bf16 / 1024 fp32)
 
@@ -41,12 +55,14 @@ template <typename T, int MAXV, bool HAS_RES>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const T* __restrict__ gamma,
                      const T* __restrict__ beta, T* __restrict__ y, T* __restrict__ sum_out,
-                     float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int cols, float eps) {
+                     float* __restrict__ mean_out, float* __restrict__ rstd_out, int rows, int cols, float eps,
+                     const LnDropout dr) {
   constexpr int VN = Vec<T>::N;
   const int lane = threadIdx.x & 31;
   const int warp_global = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * LN_WARPS;
   const int nvec = cols / VN;
+  const Philox rng(dr.seed);
   for (int row = warp_global; row < rows; row += nwarps) {
     const T* xr = x + static_cast<size_t>(row) * cols;
     float v[MAXV][VN];
@@ -56,6 +72,11 @@ layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const T
       const int vi = lane + i * 32;
       if (vi < nvec) {
         Vec<T>::load(xr + vi * VN, v[i]);
+        if (HAS_RES && VN == 8 && dr.threshold != 0) {       // y = LN(dropout(x)·s + residual)
+          const uint32_t m = ln_keep_mask8(rng, dr.offset, static_cast<uint64_t>(row) * nvec + vi, dr.threshold);
+#pragma unroll
+          for (int e = 0; e < VN; ++e) v[i][e] = ((m >> e) & 1) ? v[i][e] * dr.scale : 0.f;
+        }
         if (HAS_RES) {
           float r[VN];
           Vec<T>::load(res + static_cast<size_t>(row) * cols + vi * VN, r);
@@ -99,8 +120,9 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ gamma,
                      const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                      const T* __restrict__ dadd, T* __restrict__ dx, float* __restrict__ dgamma_part,
-                     float* __restrict__ dbeta_part, int rows, int cols) {
+                     float* __restrict__ dbeta_part, int rows, int cols, T* __restrict__ dx_drop, const LnDropout dr) {
   constexpr int VN = Vec<T>::N;
+  const Philox rng(dr.seed);
   extern __shared__ float red[];  // [LN_WARPS][cols] x 2
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int warp_global = blockIdx.x * LN_WARPS + w;
@@ -151,6 +173,14 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
           for (int e = 0; e < VN; ++e) o[e] += a[e];
         }
         Vec<T>::store(dx + static_cast<size_t>(row) * cols + vi * VN, o);
+        if (dx_drop != nullptr) {                            // gradient of the dropped branch input
+          if (VN == 8 && dr.threshold != 0) {
+            const uint32_t m = ln_keep_mask8(rng, dr.offset, static_cast<uint64_t>(row) * nvec + vi, dr.threshold);
+#pragma unroll
+            for (int e = 0; e < VN; ++e) o[e] = ((m >> e) & 1) ? o[e] * dr.scale : 0.f;
+          }
+          Vec<T>::store(dx_drop + static_cast<size_t>(row) * cols + vi * VN, o);
+        }
       }
     }
   }
@@ -204,7 +234,7 @@ ln_reduce_partials_kernel(const float* __restrict__ pg, const float* __restrict_
 
 template <typename T>
 static int ln_fwd(const void* x, const void* res, const void* g, const void* b, void* y, void* sum_out, float* mean,
-                  float* rstd, int rows, int cols, float eps, cudaStream_t s) {
+                  float* rstd, int rows, int cols, float eps, const LnDropout dr, cudaStream_t s) {
   constexpr int VN = Vec<T>::N;
   if (cols % VN || cols > 32 * LN_MAXV * VN) return 920;
   int grid = (rows + LN_WARPS - 1) / LN_WARPS;
@@ -215,11 +245,11 @@ static int ln_fwd(const void* x, const void* res, const void* g, const void* b, 
     if (res != nullptr)                                                                                                \
       layernorm_fwd_kernel<T, MV, true><<<grid, LN_WARPS * 32, 0, s>>>((const T*)x, (const T*)res, (const T*)g,        \
                                                                        (const T*)b, (T*)y, (T*)sum_out, mean, rstd,   \
-                                                                       rows, cols, eps);                              \
+                                                                       rows, cols, eps, dr);                          \
     else                                                                                                               \
       layernorm_fwd_kernel<T, MV, false><<<grid, LN_WARPS * 32, 0, s>>>((const T*)x, nullptr, (const T*)g,             \
                                                                         (const T*)b, (T*)y, nullptr, mean, rstd, rows, \
-                                                                        cols, eps);                                    \
+                                                                        cols, eps, dr);                                \
   } while (0)
   if (mv <= 1) QN_LN_FWD(1); else if (mv <= 2) QN_LN_FWD(2); else if (mv <= 4) QN_LN_FWD(4); else QN_LN_FWD(8);
 #undef QN_LN_FWD
@@ -229,7 +259,7 @@ static int ln_fwd(const void* x, const void* res, const void* g, const void* b, 
 template <typename T>
 static int ln_bwd(const void* dy, const void* x, const void* g, const float* mean, const float* rstd,
                   const void* dadd, void* dx, void* dgamma, void* dbeta, float* workspace, int nparts, int rows,
-                  int cols, cudaStream_t s) {
+                  int cols, void* dx_drop, const LnDropout dr, cudaStream_t s) {
   constexpr int VN = Vec<T>::N;
   if (cols % VN || cols > 32 * LN_MAXV * VN) return 920;
   const size_t smem = 2ull * LN_WARPS * cols * sizeof(float);
@@ -241,7 +271,7 @@ static int ln_bwd(const void* dy, const void* x, const void* g, const float* mea
     auto k = layernorm_bwd_kernel<T, MV, ADD>;                                                                        \
     if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
     k<<<nparts, LN_WARPS * 32, smem, s>>>((const T*)dy, (const T*)x, (const T*)g, mean, rstd, (const T*)dadd, (T*)dx, \
-                                          pg, pb, rows, cols);                                                        \
+                                          pg, pb, rows, cols, (T*)dx_drop, dr);                                       \
   } while (0)
 #define QN_LN_BWD2(ADD)                                                                                               \
   do {                                                                                                                 \
@@ -263,15 +293,39 @@ static int ln_bwd(const void* dy, const void* x, const void* g, const float* mea
 extern "C" int qn_layernorm_fwd(const void* x, const void* res, const void* gamma, const void* beta, void* y,
                                 void* sum_out, float* mean, float* rstd, int rows, int cols, float eps, int dtype,
                                 cudaStream_t s) {
-  if (dtype == 1) return qn::ln_fwd<__nv_bfloat16>(x, res, gamma, beta, y, sum_out, mean, rstd, rows, cols, eps, s);
-  return qn::ln_fwd<float>(x, res, gamma, beta, y, sum_out, mean, rstd, rows, cols, eps, s);
+  const qn::LnDropout nd{0u, 1.0f, 0ull, 0ull};
+  if (dtype == 1) return qn::ln_fwd<__nv_bfloat16>(x, res, gamma, beta, y, sum_out, mean, rstd, rows, cols, eps, nd, s);
+  return qn::ln_fwd<float>(x, res, gamma, beta, y, sum_out, mean, rstd, rows, cols, eps, nd, s);
+}
+
+// y = LN(h),  h = dropout(x, p)·1/(1-p) + res  (h written to sum_out); bf16 only
+extern "C" int qn_dropout_add_layernorm_fwd(const void* x, const void* res, const void* gamma, const void* beta,
+                                            void* y, void* sum_out, float* mean, float* rstd, int rows, int cols,
+                                            float eps, float p, unsigned long long seed, unsigned long long offset,
+                                            cudaStream_t s) {
+  qn::LnDropout dr{0u, 1.0f, seed, offset};
+  if (p > 0.f) { dr.threshold = (uint32_t)fminf(4294967295.0f, p * 4294967296.0f); dr.scale = 1.0f / (1.0f - p); }
+  return qn::ln_fwd<__nv_bfloat16>(x, res, gamma, beta, y, sum_out, mean, rstd, rows, cols, eps, dr, s);
 }
 
 // workspace: fp32 [2 * nparts * cols]; nparts = number of CTAs (<= 148*4 is plenty)
 extern "C" int qn_layernorm_bwd(const void* dy, const void* x, const void* gamma, const float* mean,
                                 const float* rstd, const void* dadd, void* dx, void* dgamma, void* dbeta,
                                 float* workspace, int nparts, int rows, int cols, int dtype, cudaStream_t s) {
+  const qn::LnDropout nd{0u, 1.0f, 0ull, 0ull};
   if (dtype == 1)
-    return qn::ln_bwd<__nv_bfloat16>(dy, x, gamma, mean, rstd, dadd, dx, dgamma, dbeta, workspace, nparts, rows, cols, s);
-  return qn::ln_bwd<float>(dy, x, gamma, mean, rstd, dadd, dx, dgamma, dbeta, workspace, nparts, rows, cols, s);
+    return qn::ln_bwd<__nv_bfloat16>(dy, x, gamma, mean, rstd, dadd, dx, dgamma, dbeta, workspace, nparts, rows, cols,
+                                     nullptr, nd, s);
+  return qn::ln_bwd<float>(dy, x, gamma, mean, rstd, dadd, dx, dgamma, dbeta, workspace, nparts, rows, cols, nullptr, nd, s);
+}
+
+// backward of qn_dropout_add_layernorm_fwd:  dres = LN'(dy) + dsum ;  dx = dropout'(dres)
+extern "C" int qn_dropout_add_layernorm_bwd(const void* dy, const void* h, const void* gamma, const float* mean,
+                                            const float* rstd, const void* dsum, void* dres, void* dx, void* dgamma,
+                                            void* dbeta, float* workspace, int nparts, int rows, int cols, float p,
+                                            unsigned long long seed, unsigned long long offset, cudaStream_t s) {
+  qn::LnDropout dr{0u, 1.0f, seed, offset};
+  if (p > 0.f) { dr.threshold = (uint32_t)fminf(4294967295.0f, p * 4294967296.0f); dr.scale = 1.0f / (1.0f - p); }
+  return qn::ln_bwd<__nv_bfloat16>(dy, h, gamma, mean, rstd, dsum, dres, dgamma, dbeta, workspace, nparts, rows, cols,
+                                   dx, dr, s);
 }

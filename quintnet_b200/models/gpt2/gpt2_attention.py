@@ -54,7 +54,10 @@ class GPT2Attention(nn.Module):
             c = self._rope_cache
         return c[0][:T], c[1][:T]
 
-    def forward(self, hidden_states: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, hidden_states: torch.Tensor, residual: Optional[torch.Tensor] = None,
+                raw: bool = False) -> torch.Tensor:
+        """``raw=True`` returns the c_proj output WITHOUT dropout/residual (the block fuses those into
+        the following LayerNorm)."""
         qkv = self.c_attn(hidden_states)                      # [B, T, 3*E/tp]
         B, T, _ = qkv.shape
         Hl, d = self.num_heads_local, self.head_dim
@@ -62,7 +65,7 @@ class GPT2Attention(nn.Module):
             # native tcgen05 flash attention straight on the packed projection (no split/transpose copies)
             o = ops.attention_qkvpacked(qkv, Hl, causal=True, dropout_p=self.attn_pdrop, training=self.training)
             o = self.c_proj(o)
-            return ops.dropout_add(o, residual, self.resid_pdrop, self.training)
+            return o if raw else ops.dropout_add(o, residual, self.resid_pdrop, self.training)
         q, k, v = qkv.view(B, T, 3, Hl, d).permute(2, 0, 3, 1, 4)   # each [B, Hl, T, d] (views)
         if self.use_rope:
             cos, sin = self._rope(T, qkv.device)
@@ -70,4 +73,4 @@ class GPT2Attention(nn.Module):
         o = ops.attention(q, k, v, causal=True, dropout_p=self.attn_pdrop, training=self.training)
         o = o.transpose(1, 2).reshape(B, T, Hl * d)
         o = self.c_proj(o)
-        return ops.dropout_add(o, residual, self.resid_pdrop, self.training)
+        return o if raw else ops.dropout_add(o, residual, self.resid_pdrop, self.training)

@@ -34,6 +34,20 @@ class GPT2Block(nn.Module):
                 if b is not None:
                     ln.bias.copy_(b)
 
+    def forward_fused(self, pending: Optional[torch.Tensor], residual: torch.Tensor):
+        """Fused residual chain: takes the previous branch output ``pending`` (not yet dropped / added) and
+        the residual stream, returns this block's (pending, residual).  Each dropout + residual-add is fused
+        into the LayerNorm that consumes it (one kernel forward, one backward)."""
+        p = self.attn.resid_pdrop
+        if pending is None:
+            a, h = ops.layer_norm(residual, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps), residual
+        else:
+            a, h = ops.dropout_add_layer_norm(pending, residual, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps,
+                                              p, self.training)
+        o = self.attn(a, raw=True)
+        m, h = ops.dropout_add_layer_norm(o, h, self.ln_2.weight, self.ln_2.bias, self.ln_2.eps, p, self.training)
+        return self.mlp(m, raw=True), h
+
     def forward(self, hidden_states: torch.Tensor) -> torch.Tensor:
         h = hidden_states
         a = ops.layer_norm(h, self.ln_1.weight, self.ln_1.bias, self.ln_1.eps)

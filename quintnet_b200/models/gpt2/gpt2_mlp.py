@@ -40,21 +40,22 @@ class GPT2MLP(nn.Module):
         self.resid_pdrop = config.resid_pdrop
         self.dropout = nn.Dropout(config.resid_pdrop)
 
-    def forward(self, hidden_states: torch.Tensor, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def forward(self, hidden_states: torch.Tensor, residual: Optional[torch.Tensor] = None,
+                raw: bool = False) -> torch.Tensor:
         if not self.c_fc.sequence_parallel:
             # whole MLP as ONE autograd op (GELU and GELU' fused into GEMM epilogues); the TP conjugate
             # collectives f / g wrap it exactly as they wrap the two separate layers
             x = Copy_To_Parallel.apply(hidden_states, self.tp_group)
             h = ops.mlp(x, self.c_fc.proj.weight, self.c_fc.proj.bias, self.c_proj.proj.weight, self.c_proj.bias)
             h = All_Reduce.apply(h, self.tp_group)
-            return ops.dropout_add(h, residual, self.resid_pdrop, self.training)
+            return h if raw else ops.dropout_add(h, residual, self.resid_pdrop, self.training)
         from ...parallel.tensor_parallel.layers import _fused_tp_ok
         rows_total = (hidden_states.numel() // hidden_states.shape[-1]) * self.tp_size
         if _fused_tp_ok(hidden_states, self.tp_group, rows_total, self.embed_dim, self.inner_dim_local):
             from ...ops import tp_fused
             h = tp_fused.sequence_parallel_mlp(hidden_states, self.c_fc.proj.weight, self.c_fc.proj.bias,
                                                self.c_proj.proj.weight, self.c_proj.bias, self.tp_group)
-            return ops.dropout_add(h, residual, self.resid_pdrop, self.training)
+            return h if raw else ops.dropout_add(h, residual, self.resid_pdrop, self.training)
         h = self.c_fc(hidden_states)          # bias + GELU fused
         h = self.c_proj(h)
-        return ops.dropout_add(h, residual, self.resid_pdrop, self.training)
+        return h if raw else ops.dropout_add(h, residual, self.resid_pdrop, self.training)

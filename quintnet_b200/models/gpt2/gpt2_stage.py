@@ -78,11 +78,17 @@ class GPT2Stage(nn.Module):
                 if position_ids is not None:
                     position_ids = self._local_rows(position_ids)
             x = self.embedding(x, position_ids)
+        pending = None                       # branch output whose dropout + residual add is still owed
         for blk in self.blocks:
-            x = blk(x)
+            pending, x = blk.forward_fused(pending, x)
+        p_res = self.blocks[-1].mlp.resid_pdrop if len(self.blocks) else 0.0
         if not self.is_last_stage:
-            return x
-        x = ops.layer_norm(x, self.ln_f.weight, self.ln_f.bias, self.ln_f.eps)
+            return x if pending is None else ops.dropout_add(pending, x, p_res, self.training)
+        if pending is None:
+            x = ops.layer_norm(x, self.ln_f.weight, self.ln_f.bias, self.ln_f.eps)
+        else:
+            x, _ = ops.dropout_add_layer_norm(pending, x, self.ln_f.weight, self.ln_f.bias, self.ln_f.eps,
+                                              p_res, self.training)
         if labels is None:
             if self.sequence_parallel:
                 x = All_Gather.apply(x, self.tp_group, "reduce_scatter", 0)

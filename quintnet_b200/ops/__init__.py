@@ -56,6 +56,15 @@ def add_layer_norm(x, residual, w, b, eps: float = 1e-5):
     return reference.add_layer_norm(x, residual, w, b, eps)
 
 
+def dropout_add_layer_norm(x, residual, w, b, eps: float, p: float, training: bool):
+    """(LN(h), h), h = dropout(x, p) + residual — fused into one kernel per direction on B200."""
+    if _use_native("layernorm", x) and _use_native("dropout", x):
+        from . import cuda_ops
+        if cuda_ops.dropout_add_layer_norm_ok(x):
+            return cuda_ops.dropout_add_layer_norm(x, residual, w, b, eps, p if training else 0.0)
+    return reference.dropout_add_layer_norm(x, residual, w.to(x.dtype), b.to(x.dtype), eps, p, training)
+
+
 def gelu(x):
     if _use_native("gelu", x) and x.dtype == torch.bfloat16:
         from . import cuda_ops

@@ -346,6 +346,74 @@ def dropout_add(x, residual, p: float):
     return _DropoutAdd.apply(x, residual, p)
 
 
+class _DropoutAddLayerNorm(torch.autograd.Function):
+    """(LN(h), h) with h = dropout(x)·1/(1-p) + residual — ONE kernel forward, ONE backward
+    (LN', residual-gradient add and dropout' fused; the mask is regenerated from the Philox counter)."""
+
+    @staticmethod
+    def forward(ctx, x, residual, w, b, eps, p):
+        cols = x.shape[-1]
+        x2 = x.reshape(-1, cols)
+        r2 = residual.reshape(-1, cols)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        if not r2.is_contiguous():
+            r2 = r2.contiguous()
+        rows = x2.shape[0]
+        y = torch.empty_like(x2)
+        h = torch.empty_like(x2)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        wq, bq = w.to(x.dtype), b.to(x.dtype)
+        seed, off = _PhiloxState.next(x2.numel()) if p > 0.0 else (0, 0)
+        rc = _lib().qn_dropout_add_layernorm_fwd(x2.data_ptr(), r2.data_ptr(), wq.data_ptr(), bq.data_ptr(),
+                                                 y.data_ptr(), h.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                 rows, cols, float(eps), float(p), seed, off, native.stream())
+        native.check(rc, "qn_dropout_add_layernorm_fwd")
+        native.count()
+        ctx.save_for_backward(h, wq, mean, rstd)
+        ctx.args = (float(p), seed, off, x.shape, w.dtype)
+        return y.view(x.shape), h.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy, dh):
+        h, w, mean, rstd = ctx.saved_tensors
+        p, seed, off, shape, wdtype = ctx.args
+        rows, cols = h.shape
+        dy2 = dy.reshape(rows, cols)
+        if not dy2.is_contiguous():
+            dy2 = dy2.contiguous()
+        dh2 = None
+        if dh is not None:
+            dh2 = dh.reshape(rows, cols)
+            if not dh2.is_contiguous():
+                dh2 = dh2.contiguous()
+        dres = torch.empty_like(h)
+        dx = torch.empty_like(h) if p > 0.0 else None
+        dg = torch.empty(cols, dtype=h.dtype, device=h.device)
+        db = torch.empty(cols, dtype=h.dtype, device=h.device)
+        nparts = min(_LN_PARTS, (rows + 3) // 4)
+        ws = torch.empty(2 * nparts * cols, dtype=torch.float32, device=h.device)
+        rc = _lib().qn_dropout_add_layernorm_bwd(dy2.data_ptr(), h.data_ptr(), w.data_ptr(), mean.data_ptr(),
+                                                 rstd.data_ptr(), native.ptr(dh2), dres.data_ptr(), native.ptr(dx),
+                                                 dg.data_ptr(), db.data_ptr(), ws.data_ptr(), nparts, rows, cols,
+                                                 p, seed, off, native.stream())
+        native.check(rc, "qn_dropout_add_layernorm_bwd")
+        native.count(2)
+        dres_v = dres.view(shape)
+        dx_v = dx.view(shape) if dx is not None else dres_v
+        return dx_v, dres_v, dg.to(wdtype), db.to(wdtype), None, None
+
+
+def dropout_add_layer_norm(x, residual, w, b, eps, p):
+    return _DropoutAddLayerNorm.apply(x, residual, w, b, eps, p)
+
+
+def dropout_add_layer_norm_ok(x) -> bool:
+    cols = x.shape[-1]
+    return x.dtype == torch.bfloat16 and cols % 8 == 0 and cols <= 2048
+
+
 # --------------------------------------------------------------------- RoPE
 class _Rope(torch.autograd.Function):
     @staticmethod

@@ -33,6 +33,12 @@ def add_layer_norm(x, residual, w, b, eps: float = 1e-5):
     return F.layer_norm(s, (s.shape[-1],), w, b, eps), s
 
 
+def dropout_add_layer_norm(x, residual, w, b, eps: float, p: float, training: bool):
+    """returns (LN(h), h) with h = dropout(x) + residual"""
+    h = dropout_add(x, residual, p, training)
+    return F.layer_norm(h, (h.shape[-1],), w, b, eps), h
+
+
 def gelu(x):
     return F.gelu(x)
 

@@ -282,3 +282,30 @@ def test_gemm_split_k(M, N, K, splits):
     assert _rel(c, ref) < 1e-2, _rel(c, ref)
     c2 = cuda_ops.gemm(A, B, M, N, K, split_k=splits if splits else 0)
     assert _rel(c2, ref) < 1e-2
+
+
+def test_dropout_add_layernorm_fused():
+    from quintnet_b200 import ops
+    from quintnet_b200.ops import cuda_ops
+    torch.manual_seed(12)
+    for p in (0.0, 0.1):
+        x = torch.randn(1024, 1024, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+        r = torch.randn(1024, 1024, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+        w = torch.randn(1024, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+        b = torch.randn(1024, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+        cuda_ops.manual_seed(77)
+        y, h = ops.dropout_add_layer_norm(x, r, w, b, 1e-5, p, True)
+        gy, gh = torch.randn_like(y), torch.randn_like(h)
+        torch.autograd.backward([y, h], [gy, gh])
+        # reference with the SAME mask: recover it from h - r  (kept elements have |h - r| > 0 almost surely)
+        keep = ((h.detach().float() - r.detach().float()).abs() > 1e-6) if p > 0 else torch.ones_like(h, dtype=torch.bool)
+        if p > 0:
+            assert abs(keep.float().mean().item() - (1 - p)) < 1e-2
+        xr, rr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, r, w, b))
+        hr = xr * keep.float() / (1 - p) + rr
+        yr = F.layer_norm(hr, (1024,), wr, br, 1e-5)
+        torch.autograd.backward([yr, hr], [gy.float(), gh.float()])
+        assert _rel(h, hr) < 1e-2 and _rel(y, yr) < 2e-2
+        assert _rel(x.grad, xr.grad) < 3e-2, (p, _rel(x.grad, xr.grad))
+        assert _rel(r.grad, rr.grad) < 3e-2
+        assert _rel(w.grad, wr.grad) < 3e-2 and _rel(b.grad, br.grad) < 3e-2
