@@ -255,6 +255,35 @@ struct Philox {
   }
 };
 
+// Cheap counter-based dropout RNG: one multiply-xorshift hash yields two 16-bit uniforms (one per element).
+// ~4 integer ops per element (Philox4x32-10 costs ~15) — dropout kernels stay memory-bound.  The mask is a
+// pure function of (seed, offset, element index), so backward regenerates it instead of storing it.
+QN_DEVICE uint32_t drop_key32(uint64_t seed, uint64_t offset) {
+  uint32_t k = static_cast<uint32_t>(seed) ^ (static_cast<uint32_t>(seed >> 32) * 0x9E3779B9u);
+  k ^= static_cast<uint32_t>(offset) * 0x85EBCA6Bu ^ static_cast<uint32_t>(offset >> 32) * 0xC2B2AE35u;
+  k ^= k >> 13; k *= 0x5BD1E995u; k ^= k >> 15;
+  return k;
+}
+QN_DEVICE uint32_t drop_hash32(uint32_t idx, uint32_t key) {
+  uint32_t x = (idx ^ key) * 0x9E3779B1u;
+  x ^= x >> 15;
+  x *= 0x85EBCA77u;
+  x ^= x >> 13;
+  return x;
+}
+// keep-mask (bit e = keep element e) of the 8 consecutive elements of 16-byte vector i8; thr16 = p * 65536
+QN_DEVICE uint32_t keep_mask8_fast(uint32_t key, uint64_t i8, uint32_t thr16) {
+  const uint32_t base = static_cast<uint32_t>(i8) * 4u + static_cast<uint32_t>(i8 >> 30) * 0x68E31DA4u;
+  uint32_t m = 0;
+#pragma unroll
+  for (uint32_t j = 0; j < 4; ++j) {
+    const uint32_t h = drop_hash32(base + j, key);
+    m |= ((h & 0xFFFFu) >= thr16 ? 1u : 0u) << (2 * j);
+    m |= ((h >> 16) >= thr16 ? 1u : 0u) << (2 * j + 1);
+  }
+  return m;
+}
+
 // ----------------------------------------------------------------------------
 // peer-memory / NVLink helpers (system-scope release/acquire flags, multimem)
 // ----------------------------------------------------------------------------

