@@ -59,6 +59,8 @@ def parse_args():
     ap.add_argument("--sequence-parallel", type=int, default=None)
     ap.add_argument("--cpu", action="store_true", help="gloo/CPU plumbing run (tiny model)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="gpt2", choices=["gpt2", "vit"],
+                    help="gpt2 = headline metric; vit = the reference's ViT-MNIST 3-D example config (secondary)")
     return ap.parse_args()
 
 
@@ -424,8 +426,94 @@ def _run_reference(args, ref_root):
     dist.destroy_process_group()
 
 
+# --------------------------------------------------------------------------------- ViT-MNIST (secondary)
+VIT_CFG = {"batch_size": 32, "num_workers": 0, "num_epochs": 1, "learning_rate": 1e-4, "grad_acc_steps": 2,
+           "max_grad_norm": 1.0, "img_size": 28, "patch_size": 4, "hidden_dim": 64, "in_channels": 1, "n_heads": 4,
+           "depth": 8, "schedule": "1f1b", "strategy_name": "3d"}
+
+
+def run_vit(args):
+    """ViT hidden 64 / depth 8 on MNIST-shaped synthetic images, the reference's examples/config.yaml
+    (global batch 32, grad_acc 2, Adam, 1F1B).  images/s x 50 tokens; both arms through Trainer's step loop."""
+    import torch
+    import torch.distributed as dist
+    rank, world, device = dist_env(args)
+    mesh = mesh_for(args)
+    dp, tp, pp = mesh
+    cfg = dict(VIT_CFG, device_type="cpu" if args.cpu else "cuda", mesh_dim=list(mesh), mesh_name=["dp", "tp", "pp"],
+               output_dir=tempfile.gettempdir())
+    M = cfg["grad_acc_steps"]
+    mb = max(cfg["batch_size"] // (M * dp), 1)
+    if args.impl == "reference":
+        ref_root = os.path.join(ROOT, "baseline", "_ref")
+        pkg = types.ModuleType("QuintNet")
+        pkg.__path__ = [ref_root]
+        sys.modules["QuintNet"] = pkg
+        from QuintNet.core import init_process_groups
+        from QuintNet.strategy import get_strategy
+        from QuintNet.trainer import Trainer
+        from QuintNet.utils.model import Model
+        dtype_name = "fp32"
+    else:
+        from quintnet_b200 import Trainer, get_strategy, init_process_groups
+        from quintnet_b200.models import Model
+        cfg.update(dtype="float32" if args.cpu else "bfloat16", tp_method="paired")
+        dtype_name = "fp32" if args.cpu else "bf16"
+    pg = init_process_groups(cfg["device_type"], cfg["mesh_dim"], cfg["mesh_name"])
+    g = torch.Generator().manual_seed(100 + pg.get_coordinates_tensor_search(rank)[0])
+    n_mb = M * 4
+    batches = [{"image": torch.randn(mb, 1, 28, 28, generator=g), "label": torch.randint(0, 10, (mb,), generator=g)}
+               for _ in range(n_mb)]
+    if not args.cpu:
+        batches = [{k: v.pin_memory() for k, v in b.items()} for b in batches]
+    loader = ListLoader(batches, mb)
+    model = Model(28, 4, 64, 1, 4, 8)
+    if args.impl == "ours" and tp > 1:
+        for blk in model.blocks:
+            blk.attention.tp_group = pg.get_group("tp")
+    model = get_strategy("3d", pg, cfg).apply(model)
+    trainer = Trainer(model, loader, loader, cfg, pg)
+    model.train()
+    if pp > 1:
+        dt = torch.float32 if args.impl == "reference" else trainer.dtype
+
+        def step():
+            trainer.pipeline_trainer.train_step(trainer.train_loader, trainer.tensor_shapes, trainer.device, dt)
+    else:
+        one = ListLoader(batches[:M], mb)
+
+        def step():
+            if args.impl == "reference":
+                trainer.train_loader = one
+                trainer._train_epoch(0)
+            else:
+                trainer.train_loader = one
+                trainer._train_epoch_standard(0)
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(rank == 0 and not args.cpu, args.gpus)
+    sampler.start()
+    ms = timed_region(step, args.steps, device, args.cpu)
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms, device)
+    if rank == 0:
+        imgs = cfg["batch_size"]
+        out = {"metric": "tokens/sec (device-timed, max over ranks) ViT-MNIST 3D training step (50 tokens/image)",
+               "value": imgs * 50 / (ms / args.steps / 1e3), "unit": "tokens/s", "images_per_s": imgs / (ms / args.steps / 1e3),
+               "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+               "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": dtype_name,
+               "data": "synthetic MNIST-shaped images", "impl": args.impl,
+               "config": {"model": "ViT hidden64 depth8 heads4", "global_batch": imgs, "seq_len": 50,
+                          "parallelism": f"dp{dp}tp{tp}pp{pp}", "grad_acc_steps": M}, "clocks": clocks}
+        print(json.dumps(out), flush=True)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def main():
     args = parse_args()
+    if args.workload == "vit":
+        return run_vit(args)
     if args.cpu and args.model != "gpt2-tiny":
         args.model, args.vocab, args.seq_len, args.micro_batch, args.global_batch = "gpt2-tiny", 1024, 64, 4, 32
     if args.impl == "reference":
