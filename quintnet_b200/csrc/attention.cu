@@ -93,6 +93,16 @@ struct FwdSmem {
   static constexpr uint32_t BYTES = 7 * TILE + 256;   // 2 CTAs/SM: 2 x (BYTES + 1 KB reserved) <= 228 KB
 };
 
+// work item -> (query block, head, batch).  Items are ordered longest-first (large causal query blocks first)
+// so the persistent CTAs finish together.
+QN_DEVICE void fwd_item(uint32_t item, const Params& p, uint32_t nq, uint32_t& qb, uint32_t& h, uint32_t& b) {
+  const uint32_t per_q = p.B * p.H;
+  qb = nq - 1 - item / per_q;
+  const uint32_t r = item % per_q;
+  h = r % p.H;
+  b = r / p.H;
+}
+
 __global__ void __launch_bounds__(kThreads, 2)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];      // SW128 tiles need 1024-byte alignment
@@ -103,18 +113,18 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   uint64_t* s_full = bars + 5;
   uint64_t* p_full = bars + 6;      // count 4 (one per softmax warp)
   uint64_t* o_full = bars + 7;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* q_empty = bars + 8;     // Q tile consumed by the last S MMA of a work item
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 9);
 
   if ((smem_u32(smem) & 1023u) != 0 && threadIdx.x == 0) { printf("[quintnet_b200] attention smem misaligned\n"); __trap(); }
   const uint32_t warp = warp_id(), lane = lane_id();
-  const uint32_t qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const uint32_t q0 = qb * BQ;
+  const uint32_t nq = (p.T + BQ - 1) / BQ;
   const uint32_t nkv_total = (p.T + BKV - 1) / BKV;
-  const uint32_t nkv = p.causal ? min(qb + 1, nkv_total) : nkv_total;
+  const uint32_t num_items = nq * p.H * p.B;
 
   if (warp == 4 && lane == 0) {
     prefetch_tensormap(&tmap);
-    mbar_init(q_full, 1);
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
     mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_full, 1);
     fence_barrier_init();
@@ -127,151 +137,173 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
   const uint32_t tmem_S = tmem, tmem_O = tmem + 128;
 
   if (warp == 4) {
+    // ------------------------------------------------ TMA producer (persistent: prefetches across work items)
     if (lane == 0) {
-      mbar_arrive_expect_tx(q_full, TILE);
-      tma_load_4d(smem + FwdSmem::Q, &tmap, q_full, 0, h, q0, b);                         // slot 0*H + h
-      for (uint32_t j = 0; j < nkv; ++j) {
-        const uint32_t s = j & 1, ph = (j >> 1) & 1;
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[s], 2 * TILE);
-        tma_load_4d(smem + FwdSmem::K + s * TILE, &tmap, &kv_full[s], 0, p.H + h, j * BKV, b);
-        tma_load_4d(smem + FwdSmem::V + s * TILE, &tmap, &kv_full[s], 0, 2 * p.H + h, j * BKV, b);
+      uint32_t kvc = 0, nitem = 0;                       // running K/V stage counter, items done
+      for (uint32_t item = blockIdx.x; item < num_items; item += gridDim.x, ++nitem) {
+        uint32_t qb, h, b;
+        fwd_item(item, p, nq, qb, h, b);
+        const uint32_t nkv = p.causal ? min(qb + 1, nkv_total) : nkv_total;
+        mbar_wait(q_empty, (nitem & 1) ^ 1);             // previous item's S MMAs are done with the Q tile
+        mbar_arrive_expect_tx(q_full, TILE);
+        tma_load_4d(smem + FwdSmem::Q, &tmap, q_full, 0, h, qb * BQ, b);                   // slot 0*H + h
+        for (uint32_t j = 0; j < nkv; ++j, ++kvc) {
+          const uint32_t s = kvc & 1, ph = (kvc >> 1) & 1;
+          mbar_wait(&kv_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&kv_full[s], 2 * TILE);
+          tma_load_4d(smem + FwdSmem::K + s * TILE, &tmap, &kv_full[s], 0, p.H + h, j * BKV, b);
+          tma_load_4d(smem + FwdSmem::V + s * TILE, &tmap, &kv_full[s], 0, 2 * p.H + h, j * BKV, b);
+        }
       }
     }
   } else if (warp == 5) {
+    // ---------------------------------------------------------------------------------------- MMA issuer
     if (lane == 0) {
       const uint32_t sQ = smem_u32(smem + FwdSmem::Q), sP = smem_u32(smem + FwdSmem::P);
-      mbar_wait(q_full, 0);
-      for (uint32_t j = 0; j < nkv; ++j) {
-        const uint32_t s = j & 1, ph = (j >> 1) & 1;
-        const uint32_t sK = smem_u32(smem + FwdSmem::K + s * TILE), sV = smem_u32(smem + FwdSmem::V + s * TILE);
-        mbar_wait(&kv_full[s], ph);
-        tcgen05_fence_after();
+      uint32_t kvc = 0, itc = 0, nitem = 0;
+      for (uint32_t item = blockIdx.x; item < num_items; item += gridDim.x, ++nitem) {
+        uint32_t qb, h, b;
+        fwd_item(item, p, nq, qb, h, b);
+        const uint32_t nkv = p.causal ? min(qb + 1, nkv_total) : nkv_total;
+        mbar_wait(q_full, nitem & 1);
+        for (uint32_t j = 0; j < nkv; ++j, ++kvc, ++itc) {
+          const uint32_t s = kvc & 1, ph = (kvc >> 1) & 1;
+          const uint32_t sK = smem_u32(smem + FwdSmem::K + s * TILE), sV = smem_u32(smem + FwdSmem::V + s * TILE);
+          mbar_wait(&kv_full[s], ph);
+          tcgen05_fence_after();
 #pragma unroll
-        for (uint32_t k = 0; k < D / 16; ++k)
-          umma_bf16_ss(tmem_S, make_smem_desc_sw128(sQ + k * 32, 1024, 0), make_smem_desc_sw128(sK + k * 32, 1024, 0),
-                       IDESC_S, k != 0);
-        umma_commit(s_full);
-        mbar_wait(p_full, j & 1);
-        tcgen05_fence_after();
+          for (uint32_t k = 0; k < D / 16; ++k)
+            umma_bf16_ss(tmem_S, make_smem_desc_sw128(sQ + k * 32, 1024, 0), make_smem_desc_sw128(sK + k * 32, 1024, 0),
+                         IDESC_S, k != 0);
+          umma_commit(s_full);
+          if (j + 1 == nkv) umma_commit(q_empty);        // Q may be overwritten by the next item's load
+          mbar_wait(p_full, itc & 1);
+          tcgen05_fence_after();
 #pragma unroll
-        for (uint32_t k = 0; k < BKV / 16; ++k)
-          umma_bf16_ss(tmem_O, make_smem_desc_sw128(sP + (k >> 2) * TILE + (k & 3) * 32, 1024, 0),
-                       make_smem_desc_sw128(sV + k * 2048, 1024, TILE), IDESC_PV, k != 0);
-        umma_commit(&kv_empty[s]);
-        umma_commit(o_full);
+          for (uint32_t k = 0; k < BKV / 16; ++k)
+            umma_bf16_ss(tmem_O, make_smem_desc_sw128(sP + (k >> 2) * TILE + (k & 3) * 32, 1024, 0),
+                         make_smem_desc_sw128(sV + k * 2048, 1024, TILE), IDESC_PV, k != 0);
+          umma_commit(&kv_empty[s]);
+          umma_commit(o_full);
+        }
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax / accumulate warps
     const uint32_t r = warp * 32 + lane;               // row within the query block == TMEM lane
-    const uint32_t q = q0 + r;
     const uint32_t lane_base = (warp * 32u) << 16;
     uint8_t* sP = smem + FwdSmem::P;
-    const uint32_t dkey = drop_key(p.seed, b, h);
-    float m = -INFINITY, l = 0.f;
-    float o[D];
+    uint32_t itc = 0;
+    for (uint32_t item = blockIdx.x; item < num_items; item += gridDim.x) {
+      uint32_t qb, h, b;
+      fwd_item(item, p, nq, qb, h, b);
+      const uint32_t nkv = p.causal ? min(qb + 1, nkv_total) : nkv_total;
+      const uint32_t q = qb * BQ + r;
+      const uint32_t dkey = drop_key(p.seed, b, h);
+      float m = -INFINITY, l = 0.f;
+      float o[D];
 #pragma unroll
-    for (int e = 0; e < (int)D; ++e) o[e] = 0.f;
-    for (uint32_t j = 0; j < nkv; ++j) {
-      const uint32_t k0 = j * BKV;
-      const bool need_mask = (p.causal && j == qb) || (k0 + BKV > p.T);
-      mbar_wait(s_full, j & 1);
-      tcgen05_fence_after();
-      // pass 1: row max of the RAW scores (scale > 0 commutes with max); masked variant only on the
-      // diagonal / tail block (warp-uniform branch outside the element loops)
-      float mx_raw = -INFINITY;
-      if (!need_mask) {
-#pragma unroll 1
-        for (uint32_t c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_S + lane_base + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e) mx_raw = fmaxf(mx_raw, __uint_as_float(v[e]));
-        }
-      } else {
-        const uint32_t klim = min(p.T, p.causal ? q + 1 : p.T);    // valid keys: kk < klim
-#pragma unroll 1
-        for (uint32_t c = 0; c < 4; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32b_x32(tmem_S + lane_base + c * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int e = 0; e < 32; ++e)
-            if (k0 + c * 32 + e < klim) mx_raw = fmaxf(mx_raw, __uint_as_float(v[e]));
-        }
-      }
-      const float m_new = fmaxf(m, mx_raw * p.scale_log2);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;      // fully-masked row guard
-      const float alpha = exp2f(m - m_use);                        // m = -inf -> 0
-      float lsum = 0.f;
-      // pass 2: P = exp2(s*scale - m), rowsum, (dropout as an AND-mask on the packed bf16), -> smem
-      const uint32_t klim2 = need_mask ? min(p.T, p.causal ? q + 1 : p.T) : 0xFFFFFFFFu;
-      const bool drop = p.p_drop > 0.f;
-      const uint32_t ridx = q * p.T + k0;
-#pragma unroll 1
-      for (uint32_t c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_S + lane_base + c * 32, v);
-        tmem_ld_wait();
-        uint32_t pk[16];
+      for (int e = 0; e < (int)D; ++e) o[e] = 0.f;
+      for (uint32_t j = 0; j < nkv; ++j, ++itc) {
+        const uint32_t k0 = j * BKV;
+        const bool need_mask = (p.causal && j == qb) || (k0 + BKV > p.T);
+        mbar_wait(s_full, itc & 1);
+        tcgen05_fence_after();
+        // pass 1: row max of the RAW scores (scale > 0 commutes with max); masked variant only on the
+        // diagonal / tail block (warp-uniform branch outside the element loops)
+        float mx_raw = -INFINITY;
         if (!need_mask) {
+#pragma unroll 1
+          for (uint32_t c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_S + lane_base + c * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float p0 = exp2f(fmaf(__uint_as_float(v[e]), p.scale_log2, -m_use));
-            const float p1 = exp2f(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -m_use));
-            lsum += p0 + p1;
-            pk[e >> 1] = pack_bf16(p0, p1);
+            for (int e = 0; e < 32; ++e) mx_raw = fmaxf(mx_raw, __uint_as_float(v[e]));
           }
         } else {
+          const uint32_t klim = min(p.T, p.causal ? q + 1 : p.T);    // valid keys: kk < klim
+#pragma unroll 1
+          for (uint32_t c = 0; c < 4; ++c) {
+            uint32_t v[32];
+            tmem_ld_32x32b_x32(tmem_S + lane_base + c * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const uint32_t kk = k0 + c * 32 + e;
-            const float p0 = (kk < klim2) ? exp2f(fmaf(__uint_as_float(v[e]), p.scale_log2, -m_use)) : 0.f;
-            const float p1 = (kk + 1 < klim2) ? exp2f(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -m_use)) : 0.f;
-            lsum += p0 + p1;
-            pk[e >> 1] = pack_bf16(p0, p1);
+            for (int e = 0; e < 32; ++e)
+              if (k0 + c * 32 + e < klim) mx_raw = fmaxf(mx_raw, __uint_as_float(v[e]));
           }
         }
-        if (drop) {
+        const float m_new = fmaxf(m, mx_raw * p.scale_log2);
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;      // fully-masked row guard
+        const float alpha = exp2f(m - m_use);                        // m = -inf -> 0
+        float lsum = 0.f;
+        // pass 2: P = exp2(s*scale - m), rowsum, (dropout as an AND-mask on the packed bf16), -> smem
+        const uint32_t klim2 = need_mask ? min(p.T, p.causal ? q + 1 : p.T) : 0xFFFFFFFFu;
+        const bool drop = p.p_drop > 0.f;
+        const uint32_t ridx = q * p.T + k0;
+#pragma unroll 1
+        for (uint32_t c = 0; c < 4; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_S + lane_base + c * 32, v);
+          tmem_ld_wait();
+          uint32_t pk[16];
+          if (!need_mask) {
 #pragma unroll
-          for (int e = 0; e < 16; ++e) pk[e] &= drop_mask_pair(drop_pair(dkey, ridx + c * 32 + 2 * e), p.drop_thr16);
+            for (int e = 0; e < 32; e += 2) {
+              const float p0 = exp2f(fmaf(__uint_as_float(v[e]), p.scale_log2, -m_use));
+              const float p1 = exp2f(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -m_use));
+              lsum += p0 + p1;
+              pk[e >> 1] = pack_bf16(p0, p1);
+            }
+          } else {
+#pragma unroll
+            for (int e = 0; e < 32; e += 2) {
+              const uint32_t kk = k0 + c * 32 + e;
+              const float p0 = (kk < klim2) ? exp2f(fmaf(__uint_as_float(v[e]), p.scale_log2, -m_use)) : 0.f;
+              const float p1 = (kk + 1 < klim2) ? exp2f(fmaf(__uint_as_float(v[e + 1]), p.scale_log2, -m_use)) : 0.f;
+              lsum += p0 + p1;
+              pk[e >> 1] = pack_bf16(p0, p1);
+            }
+          }
+          if (drop) {
+#pragma unroll
+            for (int e = 0; e < 16; ++e) pk[e] &= drop_mask_pair(drop_pair(dkey, ridx + c * 32 + 2 * e), p.drop_thr16);
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            st_tile_chunk(sP, r, c * 4 + g, make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
         }
+        l = l * alpha + lsum;
+        m = m_new;
+        tcgen05_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        // P·V result -> rescaled accumulation
+        mbar_wait(o_full, itc & 1);
+        tcgen05_fence_after();
 #pragma unroll
-        for (int g = 0; g < 4; ++g)
-          st_tile_chunk(sP, r, c * 4 + g, make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
+        for (uint32_t c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_O + lane_base + c * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 32; ++e) o[c * 32 + e] = o[c * 32 + e] * alpha + __uint_as_float(v[e]);
+        }
+        tcgen05_fence_before();
       }
-      l = l * alpha + lsum;
-      m = m_new;
-      tcgen05_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      // P·V result -> rescaled accumulation
-      mbar_wait(o_full, j & 1);
-      tcgen05_fence_after();
+      if (q < p.T) {
+        const float inv = l > 0.f ? p.drop_scale / l : 0.f;     // dropout 1/(1-p) folded here
+        __nv_bfloat16* op = p.out + ((static_cast<size_t>(b) * p.T + q) * p.H + h) * D;
 #pragma unroll
-      for (uint32_t c = 0; c < 2; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_O + lane_base + c * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 32; ++e) o[c * 32 + e] = o[c * 32 + e] * alpha + __uint_as_float(v[e]);
+        for (int g = 0; g < 8; ++g) {
+          uint4 pk;
+          pk.x = pack_bf16(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv); pk.y = pack_bf16(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv);
+          pk.z = pack_bf16(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv); pk.w = pack_bf16(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv);
+          *reinterpret_cast<uint4*>(op + g * 8) = pk;
+        }
+        p.lse[(static_cast<size_t>(b) * p.H + h) * p.T + q] = (l > 0.f) ? m + log2f(l) : -INFINITY;
       }
-      tcgen05_fence_before();
-    }
-    if (q < p.T) {
-      const float inv = l > 0.f ? p.drop_scale / l : 0.f;     // dropout 1/(1-p) folded here
-      __nv_bfloat16* op = p.out + ((static_cast<size_t>(b) * p.T + q) * p.H + h) * D;
-#pragma unroll
-      for (int g = 0; g < 8; ++g) {
-        uint4 pk;
-        pk.x = pack_bf16(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv); pk.y = pack_bf16(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv);
-        pk.z = pack_bf16(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv); pk.w = pack_bf16(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv);
-        *reinterpret_cast<uint4*>(op + g * 8) = pk;
-      }
-      p.lse[(static_cast<size_t>(b) * p.H + h) * p.T + q] = (l > 0.f) ? m + log2f(l) : -INFINITY;
     }
   }
   tcgen05_fence_before();
@@ -310,41 +342,53 @@ attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __re
 }
 
 struct BwdSmem {
-  static constexpr uint32_t K = 0, V = TILE, Q = 2 * TILE, DO = 4 * TILE, P = 6 * TILE, DS = 8 * TILE, BAR = 10 * TILE;
-  static constexpr uint32_t BYTES = 10 * TILE + 256;
+  // K/V double-buffered across work items, Q/dO 2-stage ring, P and dS tiles
+  static constexpr uint32_t K = 0, V = 2 * TILE, Q = 4 * TILE, DO = 6 * TILE, P = 8 * TILE, DS = 10 * TILE, BAR = 12 * TILE;
+  static constexpr uint32_t BYTES = 12 * TILE + 256;
 };
 
 constexpr uint32_t kBwdThreads = 320;   // 8 compute warps + TMA warp + MMA warp
+
+// work item -> (key block, head, batch); causal work per item shrinks with kb, so ascending kb = longest first
+QN_DEVICE void bwd_item(uint32_t item, const Params& p, uint32_t& kb, uint32_t& h, uint32_t& b) {
+  const uint32_t per_k = p.B * p.H;
+  kb = item / per_k;
+  const uint32_t r = item % per_k;
+  h = r % p.H;
+  b = r / p.H;
+}
 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
                 const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + BwdSmem::BAR);
-  uint64_t* kv_full = bars;         // 1
-  uint64_t* q_full = bars + 1;      // [2]
-  uint64_t* q_empty = bars + 3;     // [2]
-  uint64_t* sdp_full = bars + 5;
-  uint64_t* pds_full = bars + 6;    // count 8 (one per compute warp)
-  uint64_t* dq_full = bars + 7;     // [2]  (dQ accumulator is double-buffered in TMEM)
-  uint64_t* done = bars + 9;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 10);
+  uint64_t* kv_full = bars;         // [2]
+  uint64_t* kv_empty = bars + 2;    // [2]
+  uint64_t* q_full = bars + 4;      // [2]
+  uint64_t* q_empty = bars + 6;     // [2]
+  uint64_t* sdp_full = bars + 8;
+  uint64_t* pds_full = bars + 9;    // count 8 (one per compute warp)
+  uint64_t* dq_full = bars + 10;    // [2]  (dQ accumulator is double-buffered in TMEM)
+  uint64_t* done = bars + 12;       // all MMAs of a work item retired (dK / dV final)
+  uint64_t* dkdv_empty = bars + 13; // count 8: dK / dV accumulators read out
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 14);
 
   if ((smem_u32(smem) & 1023u) != 0 && threadIdx.x == 0) { printf("[quintnet_b200] attention smem misaligned\n"); __trap(); }
   const uint32_t warp = warp_id(), lane = lane_id();
-  const uint32_t kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const uint32_t k0 = kb * BKV;
   const uint32_t nq_total = (p.T + BQ - 1) / BQ;
-  const uint32_t qb_first = p.causal ? kb : 0;
-  const uint32_t niter = nq_total - qb_first;
+  const uint32_t nkb = (p.T + BKV - 1) / BKV;
+  const uint32_t num_items = nkb * p.H * p.B;
   constexpr uint32_t kTmaWarp = 8, kMmaWarp = 9;
 
   if (warp == kTmaWarp && lane == 0) {
     prefetch_tensormap(&tmap_qkv);
     prefetch_tensormap(&tmap_do);
-    mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&dq_full[i], 1); }
-    mbar_init(sdp_full, 1); mbar_init(pds_full, 8); mbar_init(done, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1);
+      mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); mbar_init(&dq_full[i], 1);
+    }
+    mbar_init(sdp_full, 1); mbar_init(pds_full, 8); mbar_init(done, 1); mbar_init(dkdv_empty, 8);
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc<512>(tmem_ptr);
@@ -357,63 +401,83 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
 
   if (warp == kTmaWarp) {
     if (lane == 0) {
-      mbar_arrive_expect_tx(kv_full, 2 * TILE);
-      tma_load_4d(smem + BwdSmem::K, &tmap_qkv, kv_full, 0, p.H + h, k0, b);
-      tma_load_4d(smem + BwdSmem::V, &tmap_qkv, kv_full, 0, 2 * p.H + h, k0, b);
-      for (uint32_t it = 0; it < niter; ++it) {
-        const uint32_t s = it & 1, ph = (it >> 1) & 1;
-        const uint32_t q0 = (qb_first + it) * BQ;
-        mbar_wait(&q_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&q_full[s], 2 * TILE);
-        tma_load_4d(smem + BwdSmem::Q + s * TILE, &tmap_qkv, &q_full[s], 0, h, q0, b);
-        tma_load_4d(smem + BwdSmem::DO + s * TILE, &tmap_do, &q_full[s], 0, h, q0, b);
+      uint32_t qc = 0, nitem = 0;
+      for (uint32_t item = blockIdx.x; item < num_items; item += gridDim.x, ++nitem) {
+        uint32_t kb, h, b;
+        bwd_item(item, p, kb, h, b);
+        const uint32_t qb_first = p.causal ? kb : 0, niter = nq_total - qb_first;
+        const uint32_t kvb = nitem & 1, kph = (nitem >> 1) & 1;
+        mbar_wait(&kv_empty[kvb], kph ^ 1);
+        mbar_arrive_expect_tx(&kv_full[kvb], 2 * TILE);
+        tma_load_4d(smem + BwdSmem::K + kvb * TILE, &tmap_qkv, &kv_full[kvb], 0, p.H + h, kb * BKV, b);
+        tma_load_4d(smem + BwdSmem::V + kvb * TILE, &tmap_qkv, &kv_full[kvb], 0, 2 * p.H + h, kb * BKV, b);
+        for (uint32_t it = 0; it < niter; ++it, ++qc) {
+          const uint32_t s = qc & 1, ph = (qc >> 1) & 1;
+          const uint32_t q0 = (qb_first + it) * BQ;
+          mbar_wait(&q_empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&q_full[s], 2 * TILE);
+          tma_load_4d(smem + BwdSmem::Q + s * TILE, &tmap_qkv, &q_full[s], 0, h, q0, b);
+          tma_load_4d(smem + BwdSmem::DO + s * TILE, &tmap_do, &q_full[s], 0, h, q0, b);
+        }
       }
     }
   } else if (warp == kMmaWarp) {
     if (lane == 0) {
-      const uint32_t sK = smem_u32(smem + BwdSmem::K), sV = smem_u32(smem + BwdSmem::V);
       const uint32_t sP = smem_u32(smem + BwdSmem::P), sDS = smem_u32(smem + BwdSmem::DS);
-      auto issue_s_dp = [&](uint32_t it) {            // S = Q·Kᵀ, dP = dO·Vᵀ of query block `it`
-        const uint32_t s = it & 1, ph = (it >> 1) & 1;
-        const uint32_t sQ = smem_u32(smem + BwdSmem::Q + s * TILE), sDO = smem_u32(smem + BwdSmem::DO + s * TILE);
-        mbar_wait(&q_full[s], ph);
-        tcgen05_fence_after();
+      uint32_t qc = 0, itc = 0, nitem = 0;
+      for (uint32_t item = blockIdx.x; item < num_items; item += gridDim.x, ++nitem) {
+        uint32_t kb, h, b;
+        bwd_item(item, p, kb, h, b);
+        const uint32_t qb_first = p.causal ? kb : 0, niter = nq_total - qb_first;
+        const uint32_t kvb = nitem & 1;
+        const uint32_t sK = smem_u32(smem + BwdSmem::K + kvb * TILE), sV = smem_u32(smem + BwdSmem::V + kvb * TILE);
+        auto issue_s_dp = [&](uint32_t q_count) {     // S = Q·Kᵀ, dP = dO·Vᵀ of the query block in ring slot q_count
+          const uint32_t s = q_count & 1, ph = (q_count >> 1) & 1;
+          const uint32_t sQ = smem_u32(smem + BwdSmem::Q + s * TILE), sDO = smem_u32(smem + BwdSmem::DO + s * TILE);
+          mbar_wait(&q_full[s], ph);
+          tcgen05_fence_after();
 #pragma unroll
-        for (uint32_t k = 0; k < D / 16; ++k)
-          umma_bf16_ss(tmem_S, make_smem_desc_sw128(sQ + k * 32, 1024, 0), make_smem_desc_sw128(sK + k * 32, 1024, 0),
-                       IDESC_S, k != 0);
+          for (uint32_t k = 0; k < D / 16; ++k)
+            umma_bf16_ss(tmem_S, make_smem_desc_sw128(sQ + k * 32, 1024, 0), make_smem_desc_sw128(sK + k * 32, 1024, 0),
+                         IDESC_S, k != 0);
 #pragma unroll
-        for (uint32_t k = 0; k < D / 16; ++k)
-          umma_bf16_ss(tmem_dP, make_smem_desc_sw128(sDO + k * 32, 1024, 0), make_smem_desc_sw128(sV + k * 32, 1024, 0),
-                       IDESC_S, k != 0);
-        umma_commit(sdp_full);
-      };
-      mbar_wait(kv_full, 0);
-      issue_s_dp(0);
-      for (uint32_t it = 0; it < niter; ++it) {
-        const uint32_t s = it & 1;
-        const uint32_t sQ = smem_u32(smem + BwdSmem::Q + s * TILE), sDO = smem_u32(smem + BwdSmem::DO + s * TILE);
-        mbar_wait(pds_full, it & 1);                 // P / dS of block `it` are in smem, S / dP TMEM consumed
-        tcgen05_fence_after();
-        // the next block's S / dP go FIRST so the compute warps can start on them while the tensor pipe
-        // is busy with this block's dV / dK / dQ
-        if (it + 1 < niter) issue_s_dp(it + 1);
+          for (uint32_t k = 0; k < D / 16; ++k)
+            umma_bf16_ss(tmem_dP, make_smem_desc_sw128(sDO + k * 32, 1024, 0), make_smem_desc_sw128(sV + k * 32, 1024, 0),
+                         IDESC_S, k != 0);
+          umma_commit(sdp_full);
+        };
+        mbar_wait(&kv_full[kvb], (nitem >> 1) & 1);
+        issue_s_dp(qc);
+        for (uint32_t it = 0; it < niter; ++it, ++qc, ++itc) {
+          const uint32_t s = qc & 1;
+          const uint32_t sQ = smem_u32(smem + BwdSmem::Q + s * TILE), sDO = smem_u32(smem + BwdSmem::DO + s * TILE);
+          mbar_wait(pds_full, itc & 1);                // P / dS of this block are in smem, S / dP TMEM consumed
+          tcgen05_fence_after();
+          // the next block's S / dP go FIRST so the compute warps can start on them while the tensor pipe
+          // is busy with this block's dV / dK / dQ
+          if (it + 1 < niter) issue_s_dp(qc + 1);
+          if (it == 0 && nitem > 0) {                  // previous item's dK / dV must have been read out
+            mbar_wait(dkdv_empty, (nitem - 1) & 1);
+            tcgen05_fence_after();
+          }
 #pragma unroll
-        for (uint32_t k = 0; k < BQ / 16; ++k)     // dV += Pᵀ · dO   (A = P as MN-major, B = dO as MN-major)
-          umma_bf16_ss(tmem_dV, make_smem_desc_sw128(sP + k * 2048, 1024, TILE), make_smem_desc_sw128(sDO + k * 2048, 1024, TILE),
-                       IDESC_TT, (it | k) != 0);
+          for (uint32_t k = 0; k < BQ / 16; ++k)     // dV += Pᵀ · dO   (A = P as MN-major, B = dO as MN-major)
+            umma_bf16_ss(tmem_dV, make_smem_desc_sw128(sP + k * 2048, 1024, TILE), make_smem_desc_sw128(sDO + k * 2048, 1024, TILE),
+                         IDESC_TT, (it | k) != 0);
 #pragma unroll
-        for (uint32_t k = 0; k < BQ / 16; ++k)     // dK += dSᵀ · Q
-          umma_bf16_ss(tmem_dK, make_smem_desc_sw128(sDS + k * 2048, 1024, TILE), make_smem_desc_sw128(sQ + k * 2048, 1024, TILE),
-                       IDESC_TT, (it | k) != 0);
+          for (uint32_t k = 0; k < BQ / 16; ++k)     // dK += dSᵀ · Q
+            umma_bf16_ss(tmem_dK, make_smem_desc_sw128(sDS + k * 2048, 1024, TILE), make_smem_desc_sw128(sQ + k * 2048, 1024, TILE),
+                         IDESC_TT, (it | k) != 0);
 #pragma unroll
-        for (uint32_t k = 0; k < BKV / 16; ++k)    // dQ = dS · K     (A = dS K-major, B = K as MN-major)
-          umma_bf16_ss(tmem_dQ + s * 64, make_smem_desc_sw128(sDS + (k >> 2) * TILE + (k & 3) * 32, 1024, 0),
-                       make_smem_desc_sw128(sK + k * 2048, 1024, TILE), IDESC_PV, k != 0);
-        umma_commit(&q_empty[s]);
-        umma_commit(&dq_full[s]);
+          for (uint32_t k = 0; k < BKV / 16; ++k)    // dQ = dS · K     (A = dS K-major, B = K as MN-major)
+            umma_bf16_ss(tmem_dQ + (itc & 1) * 64, make_smem_desc_sw128(sDS + (k >> 2) * TILE + (k & 3) * 32, 1024, 0),
+                         make_smem_desc_sw128(sK + k * 2048, 1024, TILE), IDESC_PV, k != 0);
+          umma_commit(&q_empty[s]);
+          umma_commit(&dq_full[itc & 1]);
+        }
+        umma_commit(&kv_empty[kvb]);
+        umma_commit(done);
       }
-      umma_commit(done);
     }
   } else {
     // ------------------------------------------------------------------ 8 compute warps
@@ -422,112 +486,121 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
     const uint32_t lane_base = (qtr * 32u) << 16;
     uint8_t* sP = smem + BwdSmem::P;
     uint8_t* sDS = smem + BwdSmem::DS;
-    const uint32_t dkey = drop_key(p.seed, b, h);
     const float c_ds = p.scale * p.drop_scale;
     const bool drop = p.p_drop > 0.f;
-    auto drain_dq = [&](uint32_t it) {                         // dQ block `it` -> fp32 atomics (32 columns per thread)
-      const uint32_t q = (qb_first + it) * BQ + r;
-      mbar_wait(&dq_full[it & 1], (it >> 1) & 1);
-      tcgen05_fence_after();
-      uint32_t v[32];
-      tmem_ld_32x32b_x32(tmem_dQ + (it & 1) * 64 + lane_base + half * 32, v);
-      tmem_ld_wait();
-      if (q < p.T) {
-        float* dq = p.dq_acc + ((static_cast<size_t>(b) * p.T + q) * p.H + h) * D + half * 32;
-#pragma unroll
-        for (int e = 0; e < 32; e += 4)
-          asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dq + e), "f"(__uint_as_float(v[e])),
-                       "f"(__uint_as_float(v[e + 1])), "f"(__uint_as_float(v[e + 2])), "f"(__uint_as_float(v[e + 3]))
-                       : "memory");
-      }
-      tcgen05_fence_before();
-    };
-    for (uint32_t it = 0; it < niter; ++it) {
-      const uint32_t qb = qb_first + it;
-      const uint32_t q = qb * BQ + r;
-      const bool q_ok = q < p.T;
-      const size_t stat = (static_cast<size_t>(b) * p.H + h) * p.T + (q_ok ? q : 0);
-      const float lse = q_ok ? p.lse[stat] : INFINITY;        // rows beyond T -> p = 0
-      const float dl2 = (q_ok ? p.delta[stat] : 0.f) / p.drop_scale;
-      const bool need_mask = (p.causal && qb == kb) || (k0 + BKV > p.T);
-      const uint32_t klim = need_mask ? min(p.T, p.causal ? q + 1 : p.T) : 0xFFFFFFFFu;
-      const uint32_t ridx = q * p.T + k0;
-      mbar_wait(sdp_full, it & 1);
-      tcgen05_fence_after();
-      // dS = (P·scale·rs) ⊙ (mask·dP − δ/rs);  dV uses mask·P (rs applied when dV is written)
-#pragma unroll 1
-      for (uint32_t cc = 0; cc < 2; ++cc) {
-        const uint32_t c = half * 2 + cc;                      // this warp's 32-column chunk
-        uint32_t sv[32], dv[32];
-        tmem_ld_32x32b_x32(tmem_S + lane_base + c * 32, sv);
-        tmem_ld_32x32b_x32(tmem_dP + lane_base + c * 32, dv);
-        tmem_ld_wait();
-        uint32_t pk[16], dk[16];
-#pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          float p0 = exp2f(fmaf(__uint_as_float(sv[e]), p.scale_log2, -lse));
-          float p1 = exp2f(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -lse));
-          if (need_mask) {
-            const uint32_t kk = k0 + c * 32 + e;
-            p0 = (kk < klim) ? p0 : 0.f;
-            p1 = (kk + 1 < klim) ? p1 : 0.f;
-          }
-          float d0 = __uint_as_float(dv[e]), d1 = __uint_as_float(dv[e + 1]);
-          uint32_t pw = pack_bf16(p0, p1);
-          if (drop) {
-            const uint32_t h2 = drop_pair(dkey, ridx + c * 32 + e);
-            const bool k0b = (h2 & 0xFFFFu) >= p.drop_thr16, k1b = (h2 >> 16) >= p.drop_thr16;
-            d0 = k0b ? d0 : 0.f;
-            d1 = k1b ? d1 : 0.f;
-            pw &= (k0b ? 0x0000FFFFu : 0u) | (k1b ? 0xFFFF0000u : 0u);
-          }
-          pk[e >> 1] = pw;
-          dk[e >> 1] = pack_bf16((p0 * c_ds) * (d0 - dl2), (p1 * c_ds) * (d1 - dl2));
-        }
-        // the P / dS smem tiles are still being read by the dV / dK / dQ MMAs of the previous query block:
-        // the register math above overlapped with them, the stores must wait for their completion
-        if (cc == 0 && it > 0) mbar_wait(&dq_full[(it - 1) & 1], ((it - 1) >> 1) & 1);
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          st_tile_chunk(sP, r, c * 4 + g, make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
-          st_tile_chunk(sDS, r, c * 4 + g, make_uint4(dk[g * 4 + 0], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]));
-        }
-      }
-      tcgen05_fence_before();
-      fence_proxy_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(pds_full);
-      if (it > 0) drain_dq(it - 1);                // dQ of the previous block: TMEM -> fp32 atomics
-    }
-    drain_dq(niter - 1);
-    // dK / dV of this key block (thread == key row): half 0 writes dK, half 1 writes dV
-    mbar_wait(done, 0);
-    tcgen05_fence_after();
-    const uint32_t kk = k0 + r;
-    {
-      const uint32_t which = half;                           // 0 -> dK (slot 1), 1 -> dV (slot 2)
-      const uint32_t taddr = (which == 0 ? tmem_dK : tmem_dV) + lane_base;
-      const float osc = (which == 1) ? p.drop_scale : 1.0f;  // dV carries the dropout 1/(1-p)
-      __nv_bfloat16* dst = p.dqkv + (((static_cast<size_t>(b) * p.T + (kk < p.T ? kk : 0)) * 3 + (which + 1)) * p.H + h) * D;
-#pragma unroll
-      for (uint32_t c = 0; c < 2; ++c) {
+    uint32_t itc = 0, nitem = 0;
+    for (uint32_t item = blockIdx.x; item < num_items; item += gridDim.x, ++nitem) {
+      uint32_t kb, h, b;
+      bwd_item(item, p, kb, h, b);
+      const uint32_t k0 = kb * BKV;
+      const uint32_t qb_first = p.causal ? kb : 0, niter = nq_total - qb_first;
+      const uint32_t dkey = drop_key(p.seed, b, h);
+      auto drain_dq = [&](uint32_t c_it, uint32_t qblk) {      // dQ block -> fp32 atomics (32 columns per thread)
+        const uint32_t q = qblk * BQ + r;
+        mbar_wait(&dq_full[c_it & 1], (c_it >> 1) & 1);
+        tcgen05_fence_after();
         uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + c * 32, v);
+        tmem_ld_32x32b_x32(tmem_dQ + (c_it & 1) * 64 + lane_base + half * 32, v);
         tmem_ld_wait();
-        if (kk < p.T) {
+        if (q < p.T) {
+          float* dq = p.dq_acc + ((static_cast<size_t>(b) * p.T + q) * p.H + h) * D + half * 32;
+#pragma unroll
+          for (int e = 0; e < 32; e += 4)
+            asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dq + e), "f"(__uint_as_float(v[e])),
+                         "f"(__uint_as_float(v[e + 1])), "f"(__uint_as_float(v[e + 2])), "f"(__uint_as_float(v[e + 3]))
+                         : "memory");
+        }
+        tcgen05_fence_before();
+      };
+      for (uint32_t it = 0; it < niter; ++it, ++itc) {
+        const uint32_t qb = qb_first + it;
+        const uint32_t q = qb * BQ + r;
+        const bool q_ok = q < p.T;
+        const size_t stat = (static_cast<size_t>(b) * p.H + h) * p.T + (q_ok ? q : 0);
+        const float lse = q_ok ? p.lse[stat] : INFINITY;        // rows beyond T -> p = 0
+        const float dl2 = (q_ok ? p.delta[stat] : 0.f) / p.drop_scale;
+        const bool need_mask = (p.causal && qb == kb) || (k0 + BKV > p.T);
+        const uint32_t klim = need_mask ? min(p.T, p.causal ? q + 1 : p.T) : 0xFFFFFFFFu;
+        const uint32_t ridx = q * p.T + k0;
+        mbar_wait(sdp_full, itc & 1);
+        tcgen05_fence_after();
+        // dS = (P·scale·rs) ⊙ (mask·dP − δ/rs);  dV uses mask·P (rs applied when dV is written)
+#pragma unroll 1
+        for (uint32_t cc = 0; cc < 2; ++cc) {
+          const uint32_t c = half * 2 + cc;                      // this warp's 32-column chunk
+          uint32_t sv[32], dv[32];
+          tmem_ld_32x32b_x32(tmem_S + lane_base + c * 32, sv);
+          tmem_ld_32x32b_x32(tmem_dP + lane_base + c * 32, dv);
+          tmem_ld_wait();
+          uint32_t pk[16], dk[16];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2) {
+            float p0 = exp2f(fmaf(__uint_as_float(sv[e]), p.scale_log2, -lse));
+            float p1 = exp2f(fmaf(__uint_as_float(sv[e + 1]), p.scale_log2, -lse));
+            if (need_mask) {
+              const uint32_t kk = k0 + c * 32 + e;
+              p0 = (kk < klim) ? p0 : 0.f;
+              p1 = (kk + 1 < klim) ? p1 : 0.f;
+            }
+            float d0 = __uint_as_float(dv[e]), d1 = __uint_as_float(dv[e + 1]);
+            uint32_t pw = pack_bf16(p0, p1);
+            if (drop) {
+              const uint32_t h2 = drop_pair(dkey, ridx + c * 32 + e);
+              const bool k0b = (h2 & 0xFFFFu) >= p.drop_thr16, k1b = (h2 >> 16) >= p.drop_thr16;
+              d0 = k0b ? d0 : 0.f;
+              d1 = k1b ? d1 : 0.f;
+              pw &= (k0b ? 0x0000FFFFu : 0u) | (k1b ? 0xFFFF0000u : 0u);
+            }
+            pk[e >> 1] = pw;
+            dk[e >> 1] = pack_bf16((p0 * c_ds) * (d0 - dl2), (p1 * c_ds) * (d1 - dl2));
+          }
+          // the P / dS smem tiles are still being read by the dV / dK / dQ MMAs of the previous query block:
+          // the register math above overlapped with them, the stores must wait for their completion
+          if (cc == 0 && itc > 0) mbar_wait(&dq_full[(itc - 1) & 1], ((itc - 1) >> 1) & 1);
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            uint4 pk;
-            pk.x = pack_bf16(__uint_as_float(v[g * 8 + 0]) * osc, __uint_as_float(v[g * 8 + 1]) * osc);
-            pk.y = pack_bf16(__uint_as_float(v[g * 8 + 2]) * osc, __uint_as_float(v[g * 8 + 3]) * osc);
-            pk.z = pack_bf16(__uint_as_float(v[g * 8 + 4]) * osc, __uint_as_float(v[g * 8 + 5]) * osc);
-            pk.w = pack_bf16(__uint_as_float(v[g * 8 + 6]) * osc, __uint_as_float(v[g * 8 + 7]) * osc);
-            *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = pk;
+            st_tile_chunk(sP, r, c * 4 + g, make_uint4(pk[g * 4 + 0], pk[g * 4 + 1], pk[g * 4 + 2], pk[g * 4 + 3]));
+            st_tile_chunk(sDS, r, c * 4 + g, make_uint4(dk[g * 4 + 0], dk[g * 4 + 1], dk[g * 4 + 2], dk[g * 4 + 3]));
+          }
+        }
+        tcgen05_fence_before();
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(pds_full);
+        if (it > 0) drain_dq(itc - 1, qb - 1);       // dQ of the previous block: TMEM -> fp32 atomics
+      }
+      drain_dq(itc - 1, qb_first + niter - 1);
+      // dK / dV of this key block (thread == key row): half 0 writes dK, half 1 writes dV
+      mbar_wait(done, nitem & 1);
+      tcgen05_fence_after();
+      const uint32_t kk = k0 + r;
+      {
+        const uint32_t which = half;                           // 0 -> dK (slot 1), 1 -> dV (slot 2)
+        const uint32_t taddr = (which == 0 ? tmem_dK : tmem_dV) + lane_base;
+        const float osc = (which == 1) ? p.drop_scale : 1.0f;  // dV carries the dropout 1/(1-p)
+        __nv_bfloat16* dst = p.dqkv + (((static_cast<size_t>(b) * p.T + (kk < p.T ? kk : 0)) * 3 + (which + 1)) * p.H + h) * D;
+#pragma unroll
+        for (uint32_t c = 0; c < 2; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + c * 32, v);
+          tmem_ld_wait();
+          if (kk < p.T) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              uint4 pk;
+              pk.x = pack_bf16(__uint_as_float(v[g * 8 + 0]) * osc, __uint_as_float(v[g * 8 + 1]) * osc);
+              pk.y = pack_bf16(__uint_as_float(v[g * 8 + 2]) * osc, __uint_as_float(v[g * 8 + 3]) * osc);
+              pk.z = pack_bf16(__uint_as_float(v[g * 8 + 4]) * osc, __uint_as_float(v[g * 8 + 5]) * osc);
+              pk.w = pack_bf16(__uint_as_float(v[g * 8 + 6]) * osc, __uint_as_float(v[g * 8 + 7]) * osc);
+              *reinterpret_cast<uint4*>(dst + c * 32 + g * 8) = pk;
+            }
           }
         }
       }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(dkdv_empty);
     }
-    tcgen05_fence_before();
   }
   tcgen05_fence_before();
   __syncthreads();
@@ -623,7 +696,14 @@ extern "C" int qn_attn_fwd(const void* qkv, void* out, float* lse, int B, int H,
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  dim3 grid((T + BQ - 1) / BQ, H, B);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const unsigned items = static_cast<unsigned>((T + BQ - 1) / BQ) * H * B;
+  const unsigned grid = items < 2u * num_sms ? items : 2u * num_sms;      // persistent: 2 CTAs per SM
   attn_fwd_kernel<<<grid, kThreads, FwdSmem::BYTES, s>>>(tm, p);
   return (int)cudaGetLastError();
 }
@@ -655,7 +735,14 @@ extern "C" int qn_attn_bwd(const void* qkv, const void* out, const void* dout, c
     if (e != cudaSuccess) return (int)e;
     configured = true;
   }
-  dim3 grid((T + BKV - 1) / BKV, H, B);
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const unsigned items = static_cast<unsigned>((T + BKV - 1) / BKV) * H * B;
+  const unsigned grid = items < static_cast<unsigned>(num_sms) ? items : num_sms;   // persistent: 1 CTA per SM
   attn_bwd_kernel<<<grid, kBwdThreads, BwdSmem::BYTES, s>>>(tq, tdo, p);
   const size_t groups = rows * (D / 8);
   attn_dq_convert_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, s>>>(dq_acc, p.dqkv, B, H, T);
