@@ -512,13 +512,26 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         }
         tcgen05_fence_before();
       };
+      // row statistics are software-pipelined one query block ahead: the loads of block it+1 are issued
+      // before the barrier waits of block it+1, so their DRAM latency never sits on the critical path
+      const float* lse_bh = p.lse + (static_cast<size_t>(b) * p.H + h) * p.T;
+      const float* dl_bh = p.delta + (static_cast<size_t>(b) * p.H + h) * p.T;
+      const float inv_rs = 1.0f / p.drop_scale;
+      float lse_nx, dl_nx;
+      {
+        const uint32_t q1 = qb_first * BQ + r;
+        lse_nx = q1 < p.T ? lse_bh[q1] : INFINITY;               // rows beyond T -> p = 0
+        dl_nx = q1 < p.T ? dl_bh[q1] * inv_rs : 0.f;
+      }
       for (uint32_t it = 0; it < niter; ++it, ++itc) {
         const uint32_t qb = qb_first + it;
         const uint32_t q = qb * BQ + r;
-        const bool q_ok = q < p.T;
-        const size_t stat = (static_cast<size_t>(b) * p.H + h) * p.T + (q_ok ? q : 0);
-        const float lse = q_ok ? p.lse[stat] : INFINITY;        // rows beyond T -> p = 0
-        const float dl2 = (q_ok ? p.delta[stat] : 0.f) / p.drop_scale;
+        const float lse = lse_nx, dl2 = dl_nx;
+        if (it + 1 < niter) {
+          const uint32_t q1 = q + BQ;
+          lse_nx = q1 < p.T ? lse_bh[q1] : INFINITY;
+          dl_nx = q1 < p.T ? dl_bh[q1] * inv_rs : 0.f;
+        }
         const bool need_mask = (p.causal && qb == kb) || (k0 + BKV > p.T);
         const uint32_t klim = need_mask ? min(p.T, p.causal ? q + 1 : p.T) : 0xFFFFFFFFu;
         const uint32_t ridx = q * p.T + k0;
