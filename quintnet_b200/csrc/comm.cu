@@ -30,7 +30,7 @@ QN_DEVICE void block_barrier(const PeerPtrs& pp, uint32_t epoch) {
   if (threadIdx.x < pp.world) {
     const int peer = threadIdx.x;
     __threadfence_system();
-    st_release_sys(pp.sig[peer] + blockIdx.x * COMM_MAX_RANKS + pp.rank, epoch);
+    st_relaxed_sys(pp.sig[peer] + blockIdx.x * COMM_MAX_RANKS + pp.rank, epoch);   // fence above = release
     wait_flag_ge(pp.sig[pp.rank] + blockIdx.x * COMM_MAX_RANKS + peer, epoch);
   }
   __syncthreads();

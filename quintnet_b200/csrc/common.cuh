@@ -15,9 +15,10 @@
 #define QN_DEVICE __device__ __forceinline__
 
 #ifndef QN_WATCHDOG_CYCLES
-// ~2.5 s at 2 GHz: a barrier that is not released by then is a bug → trap, so a
-// broken pipeline turns into a CUDA error instead of hanging the GPU.
-#define QN_WATCHDOG_CYCLES (5000000000LL)
+// ~20 s at 2 GHz: a barrier / peer flag that is not released by then is a bug (or a dead peer) → trap, so
+// a broken pipeline turns into a CUDA error instead of hanging the GPU.  Long enough to ride out host-side
+// skew between ranks (lazy NCCL communicator creation, allocator stalls).
+#define QN_WATCHDOG_CYCLES (40000000000LL)
 #endif
 
 namespace qn {
@@ -289,6 +290,10 @@ QN_DEVICE uint32_t keep_mask8_fast(uint32_t key, uint64_t i8, uint32_t thr16) {
 // ----------------------------------------------------------------------------
 QN_DEVICE void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// plain system-scope store (use after an explicit __threadfence_system(): avoids a second MEMBAR.SYS)
+QN_DEVICE void st_relaxed_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 QN_DEVICE uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;

@@ -243,7 +243,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       __syncwarp();
       if (lane == 0)
         for (int pr = 1; pr < tc.world; ++pr)
-          st_release_sys(tc.ag_flags[(tc.rank + pr) % tc.world] + tc.rank * units + u, tc.seq);
+          st_relaxed_sys(tc.ag_flags[(tc.rank + pr) % tc.world] + tc.rank * units + u, tc.seq);
     }
   } else if (warp >= kEpiWarp0) {
     // ---------------------------------------------------------------- epilogue (8 warps)
@@ -262,11 +262,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (npend == 0) return;
       __threadfence_system();
       __syncwarp();
-      if (lane == 0) {
-        st_release_sys(pend0, tc.seq);
-        if (npend > 1) st_release_sys(pend1, tc.seq);
-        if (npend > 2) st_release_sys(pend2, tc.seq);
-        if (npend > 3) st_release_sys(pend3, tc.seq);
+      if (lane == 0) {                       // one fence above covers all four flags
+        st_relaxed_sys(pend0, tc.seq);
+        if (npend > 1) st_relaxed_sys(pend1, tc.seq);
+        if (npend > 2) st_relaxed_sys(pend2, tc.seq);
+        if (npend > 3) st_relaxed_sys(pend3, tc.seq);
       }
       npend = 0;
     };

@@ -49,6 +49,26 @@ class PipelineTrainer:
         else:
             raise ValueError(f"unknown schedule_type {schedule_type!r} (use '1f1b' or 'afab')")
         self.schedule_type = schedule_type
+        self._warmup_p2p()
+
+    def _warmup_p2p(self) -> None:
+        """Exchange one tiny tensor with each pipeline neighbour so the (lazy) p2p communicators exist
+        before the first timed / fused step — keeps ranks from drifting seconds apart on step 1."""
+        if self.pp_group is None or self.world_size < 2:
+            return
+        dev = self.device if isinstance(self.device, torch.device) else torch.device(self.device)
+        ops_, keep = [], []
+        for delta in (+1, -1):
+            peer_rank = self.rank + delta
+            if 0 <= peer_rank < self.world_size:
+                peer = dist.get_global_rank(self.pp_group, peer_rank)
+                s, r = torch.ones(8, device=dev), torch.empty(8, device=dev)
+                keep += [s, r]
+                ops_ += [dist.P2POp(dist.isend, s, peer, self.pp_group), dist.P2POp(dist.irecv, r, peer, self.pp_group)]
+        for w in dist.batch_isend_irecv(ops_):
+            w.wait()
+        if dev.type == "cuda":
+            torch.cuda.synchronize()
 
     # ------------------------------------------------------------- loss helpers
     def clm_loss(self, logits: torch.Tensor, labels: torch.Tensor):
