@@ -268,3 +268,8 @@ extern "C" int qn_ipc_open_handle(const void* handle64, void** out) {
 }
 extern "C" int qn_malloc(void** out, long long bytes) { return (int)cudaMalloc(out, (size_t)bytes); }
 extern "C" int qn_memset0(void* p, long long bytes, cudaStream_t s) { return (int)cudaMemsetAsync(p, 0, (size_t)bytes, s); }
+
+// Run-time deadline (in SM cycles) of the peer-flag waits in this translation unit; see common.cuh.
+extern "C" int qn_comm_set_flag_watchdog(long long cycles) {
+  return static_cast<int>(cudaMemcpyToSymbol(qn::g_flag_watchdog_cycles, &cycles, sizeof(cycles)));
+}

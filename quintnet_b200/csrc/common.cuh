@@ -308,10 +308,14 @@ QN_DEVICE uint32_t ld_relaxed_sys(const uint32_t* p) {
   asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Deadline of the peer-flag spin loops, adjustable at run time (qn_*_set_flag_watchdog) so the fault-injection
+// test can prove the watchdog fires without waiting out the production deadline.  One copy per translation unit.
+__attribute__((unused)) static __device__ long long g_flag_watchdog_cycles = QN_WATCHDOG_CYCLES;
+
 QN_DEVICE void wait_flag_ge(const uint32_t* p, uint32_t target) {
   const long long t0 = clock64();
   while (static_cast<int32_t>(ld_acquire_sys(p) - target) < 0) {
-    if (clock64() - t0 > QN_WATCHDOG_CYCLES) {
+    if (clock64() - t0 > g_flag_watchdog_cycles) {
       printf("[quintnet_b200] peer-flag watchdog: block %d thread %d target %u have %u\n", blockIdx.x, threadIdx.x,
              target, ld_relaxed_sys(p));
       __trap();

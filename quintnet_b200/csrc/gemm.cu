@@ -764,3 +764,8 @@ extern "C" int qn_gemm_rs_bf16(const void* a, const void* b, void* c_local, void
   if (!b_mn) return launch<128, false, false, FUSE_RS>(ta, tb, tcm, tcm, p, max_ctas, stream, &tx, &comm);
   return launch<128, false, true, FUSE_RS>(ta, tb, tcm, tcm, p, max_ctas, stream, &tx, &comm);
 }
+
+// Run-time deadline (in SM cycles) of the peer-flag waits in this translation unit; see common.cuh.
+extern "C" int qn_gemm_set_flag_watchdog(long long cycles) {
+  return static_cast<int>(cudaMemcpyToSymbol(qn::g_flag_watchdog_cycles, &cycles, sizeof(cycles)));
+}

@@ -129,6 +129,8 @@ def lib() -> Optional[ctypes.CDLL]:
 _I, _L, _F, _P = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_p
 _U = ctypes.c_ulonglong
 _SIGNATURES = {
+    "qn_comm_set_flag_watchdog": [ctypes.c_longlong],
+    "qn_gemm_set_flag_watchdog": [ctypes.c_longlong],
     "qn_gemm_bf16": [_P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _P, _P, _L, _I, _I, _P],
     "qn_gemm_bf16_splitk": [_P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _P],
     "qn_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],

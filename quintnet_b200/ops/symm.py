@@ -189,10 +189,31 @@ def available(group) -> bool:
 
 
 # ------------------------------------------------------------------ collectives
+def set_flag_watchdog(seconds: float, sm_clock_hz: float = 1.9e9) -> None:
+    """Deadline of the in-kernel peer-flag waits (default ≈ 20 s).  A wait that outlives it traps, which turns
+    a dead or diverged peer into a CUDA error on the survivors instead of a hung GPU."""
+    lib = native.require()
+    cycles = int(seconds * sm_clock_hz)
+    for fn in ("qn_comm_set_flag_watchdog", "qn_gemm_set_flag_watchdog"):
+        native.check(getattr(lib, fn)(cycles), fn)
+
+
+def _fault_injected(kind: str, rank: int) -> bool:
+    """Test hook: ``QUINTNET_FAULT=drop_collective:<rank>`` makes that rank silently skip its next in-kernel
+    collective — the peers' flag waits must then hit the watchdog."""
+    spec = os.environ.get("QUINTNET_FAULT", "")
+    if not spec:
+        return False
+    what, _, who = spec.partition(":")
+    return what == kind and (who == "" or int(who) == rank)
+
+
 def all_reduce_(buf_off: Tuple[SymmBuffer, int], t: torch.Tensor, scale: float = 1.0,
                 use_multicast: bool = True, blocks: Optional[int] = None) -> None:
     """In-place SUM all-reduce (× ``scale``) of symmetric tensor ``t`` by K1."""
     b, off = buf_off
+    if _fault_injected("drop_collective", b.rank):
+        return
     arr, sig = b.ptr_arrays(off)
     mc = (b.mc_ptr + off) if (use_multicast and b.mc_ptr) else None
     rc = native.require().qn_allreduce(arr, sig, mc, b.rank, b.world, t.numel(), _DT[t.dtype], float(scale),

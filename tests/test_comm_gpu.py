@@ -190,3 +190,40 @@ def _sp_mlp(rank, world):
 
 def test_sequence_parallel_mlp_fused():
     run_distributed(_sp_mlp, 2, backend="nccl")
+
+
+def _watchdog_fault(rank, world, marker):
+    """Fault injection: rank 1 silently drops its all-reduce; rank 0's in-kernel flag wait must hit
+    the watchdog and surface as a CUDA error instead of hanging the GPU."""
+    import os
+    import time
+    from quintnet_b200.ops import symm
+    dev = torch.device("cuda", rank)
+    t = symm.alloc(1 << 16, torch.float32, dev, dist.group.WORLD)
+    t.fill_(1.0)
+    symm.set_flag_watchdog(0.25)
+    torch.cuda.synchronize()
+    dist.barrier()
+    os.environ["QUINTNET_FAULT"] = "drop_collective:1"
+    symm.all_reduce_(symm.lookup(t), t, 1.0)
+    if rank == 0:
+        t0 = time.time()
+        try:
+            torch.cuda.synchronize()
+            outcome = "no-error"
+        except RuntimeError as e:          # trap -> launch failure on the survivor
+            outcome = f"fired after {time.time() - t0:.2f}s: {str(e).splitlines()[0]}"
+        with open(marker, "w") as f:
+            f.write(outcome)
+    else:
+        time.sleep(4.0)                    # keep the peer mapping alive while rank 0 spins
+    os._exit(0)                            # the CUDA context of rank 0 is gone; skip the collective teardown
+
+
+def test_flag_watchdog_fires_on_dropped_collective(tmp_path):
+    marker = str(tmp_path / "watchdog.txt")
+    run_distributed(_watchdog_fault, 2, marker, backend="nccl", timeout=120)
+    with open(marker) as f:
+        outcome = f.read()
+    print(outcome)
+    assert outcome.startswith("fired"), outcome

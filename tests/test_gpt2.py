@@ -182,3 +182,27 @@ def test_3d_2x2x2():
 
 def test_3d_2x2x2_zero1_sequence_parallel():
     run_distributed(_run_parallel, 8, [2, 2, 2], ["dp", "tp", "pp"], "1f1b", 1, True, 16, timeout=400)
+
+
+def _replay(rank, world, out_dir):
+    """Deterministic replay: the same seed and data give bitwise-identical parameters twice."""
+    from quintnet_b200.utils.data import dict_collate
+    M, batch, steps = 4, 8, 2
+    pg = init_process_groups("cpu", [2], ["pp"])
+    digests = []
+    for _ in range(2):
+        data = SyntheticTokens(batch * steps, seq_len=16, vocab_size=96, seed=11, pad_id=0, min_fill=0.6)
+        cfg = _train_cfg([2], ["pp"], "1f1b", 0, False, M, batch)
+        cfg["model_config"] = dict(CFG, embd_pdrop=0.1, attn_pdrop=0.1, resid_pdrop=0.1)   # RNG in the loop too
+        torch.manual_seed(7)
+        model = get_strategy("3d", pg, cfg, checkpoint_path=None, is_staged=True).apply(None)
+        loader = torch.utils.data.DataLoader(data, batch_size=batch // M, shuffle=False, collate_fn=dict_collate)
+        tr = GPT2Trainer(model, loader, None, cfg, pg, GPT2Config(**cfg["model_config"]))
+        for _ in range(steps):
+            tr.train_step()
+        digests.append(torch.cat([p.detach().float().flatten() for p in tr.gpt2_stage.parameters()]))
+    assert torch.equal(digests[0], digests[1]), (digests[0] - digests[1]).abs().max()
+
+
+def test_deterministic_replay(tmp_path):
+    run_distributed(_replay, 2, str(tmp_path))
