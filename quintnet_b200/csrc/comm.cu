@@ -273,3 +273,91 @@ extern "C" int qn_memset0(void* p, long long bytes, cudaStream_t s) { return (in
 extern "C" int qn_comm_set_flag_watchdog(long long cycles) {
   return static_cast<int>(cudaMemcpyToSymbol(qn::g_flag_watchdog_cycles, &cycles, sizeof(cycles)));
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// NVLink push micro-benchmark (scripts/bench_nvlink_push.py): how fast can `blocks x threads` threads copy a
+// local buffer into peer memory with 16-byte stores, `DEPTH` loads in flight per thread.  seg_vecs > 0 writes
+// `seg_vecs` contiguous vectors and then jumps `seg_stride` vectors (the row-segment pattern of a GEMM epilogue
+// scattering a [rows x 64] slab into a wider matrix).
+// ---------------------------------------------------------------------------------------------------------
+namespace qn {
+template <int DEPTH>
+__global__ void push_bench_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long nvec, int seg_vecs,
+                                  long long seg_stride) {
+  const long long tid = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long nthr = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long base = tid; base < nvec; base += nthr * DEPTH) {
+    uint4 v[DEPTH];
+#pragma unroll
+    for (int j = 0; j < DEPTH; ++j) {
+      const long long i = base + j * nthr;
+      if (i < nvec) v[j] = ld_nc_v4(src + i);
+    }
+#pragma unroll
+    for (int j = 0; j < DEPTH; ++j) {
+      const long long i = base + j * nthr;
+      if (i < nvec) {
+        const long long o = seg_vecs > 0 ? (i / seg_vecs) * seg_stride + (i % seg_vecs) : i;
+        st_v4(dst + o, v[j]);
+      }
+    }
+  }
+  __threadfence_system();
+}
+}  // namespace qn
+
+namespace qn {
+// Same copy, but staged through shared memory with bulk async copies (one thread per CTA drives it): chunks of
+// `chunk` bytes, STAGES deep, loads issued two chunks ahead of the stores.
+template <int STAGES>
+__global__ void push_bulk_kernel(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long bytes, int chunk) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  __shared__ uint64_t full[STAGES];
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < STAGES; ++i) mbar_init(&full[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  constexpr int LA = 2;
+  const long long nchunks = bytes / chunk;
+  const long long mine = (nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  for (long long it = 0; it < mine + LA; ++it) {
+    if (it < mine) {
+      const int s = it % STAGES;
+      tma_store_wait_read<1>();                      // the store that last read this stage has drained it
+      mbar_arrive_expect_tx(&full[s], chunk);
+      bulk_load_1d(sm + s * chunk, src + (blockIdx.x + it * gridDim.x) * chunk, chunk, &full[s]);
+    }
+    if (it >= LA) {
+      const long long j = it - LA;
+      const int s = j % STAGES;
+      mbar_wait(&full[s], (j / STAGES) & 1);
+      bulk_store_1d(dst + (blockIdx.x + j * gridDim.x) * chunk, sm + s * chunk, chunk);
+      tma_store_commit();
+    }
+  }
+  tma_store_wait_all<0>();
+  __threadfence_system();
+}
+}  // namespace qn
+
+extern "C" int qn_push_bench_bulk(const void* src, void* dst, long long bytes, int blocks, int chunk, cudaStream_t s) {
+  constexpr int STAGES = 4;
+  auto k = qn::push_bulk_kernel<STAGES>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, STAGES * chunk);
+  k<<<blocks, 32, STAGES * chunk, s>>>(static_cast<const uint8_t*>(src), static_cast<uint8_t*>(dst), bytes, chunk);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int qn_push_bench(const void* src, void* dst, long long bytes, int blocks, int threads, int depth,
+                             int seg_vecs, long long seg_stride, cudaStream_t s) {
+  const long long nvec = bytes / 16;
+  const uint4* a = static_cast<const uint4*>(src);
+  uint4* b = static_cast<uint4*>(dst);
+  if (depth >= 16) qn::push_bench_kernel<16><<<blocks, threads, 0, s>>>(a, b, nvec, seg_vecs, seg_stride);
+  else if (depth >= 8) qn::push_bench_kernel<8><<<blocks, threads, 0, s>>>(a, b, nvec, seg_vecs, seg_stride);
+  else if (depth >= 4) qn::push_bench_kernel<4><<<blocks, threads, 0, s>>>(a, b, nvec, seg_vecs, seg_stride);
+  else qn::push_bench_kernel<1><<<blocks, threads, 0, s>>>(a, b, nvec, seg_vecs, seg_stride);
+  return static_cast<int>(cudaGetLastError());
+}

@@ -16,6 +16,7 @@
 // main loop of tile i+1.  Tiles are walked in a grouped order for L2 reuse.
 #include "common.cuh"
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -61,6 +62,9 @@ struct TpComm {
   uint32_t* ag_flags[TP_MAX];         // AG: every rank's per-32-row flags [M / 32]
   __nv_bfloat16* stage[TP_MAX];       // RS: every rank's staging buffer [world][rows_per_rank][N]
   uint32_t* rs_flags[TP_MAX];         // RS: every rank's flags [mb_per_rank][4][N/64][world]
+  uint32_t debug;                     // QN_TP_DEBUG timing-attribution knobs (results are WRONG when set):
+                                      //   1 RS: skip the peer wait + add    2 RS: remote stores go to local memory
+                                      //   4 AG: skip the flag waits         8 AG: skip the push
 };
 
 QN_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -144,7 +148,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    {
       uint32_t stage = 0, phase = 0;
       for (uint32_t work = blockIdx.x; work < num_work; work += gridDim.x) {
         const uint32_t tile = work / splits, split = work - tile * splits;
@@ -156,11 +160,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         bool a_remote = false;
         if constexpr (FUSE == FUSE_AG) {
           a_remote = (m_blk / tc.mb_per_rank) != static_cast<uint32_t>(tc.rank);
-          if (a_remote) {                 // the peer's pushes of these 128 rows must have landed
-            for (uint32_t u = 0; u < 4; ++u) wait_flag_ge(tc.ag_flags[tc.rank] + m_blk * 4 + u, tc.seq);
+          if (a_remote && !(tc.debug & 4u)) {   // the peer's pushes of these 128 rows must have landed
+            if (lane < 4) wait_flag_ge(tc.ag_flags[tc.rank] + m_blk * 4 + lane, tc.seq);   // 4 units polled in parallel
+            __syncwarp();
             fence_proxy_async_all();      // generic-proxy (NVLink) writes -> async-proxy (TMA) reads
           }
         }
+        if (lane != 0) continue;
         for (uint32_t kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
@@ -226,17 +232,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------ all-gather push (this rank's shard -> every peer)
     const uint32_t units = tc.rows_per_rank / 32;
     const uint32_t vec_per_unit = 32 * p.K / 8;                 // 16-byte vectors per 32-row unit
-    for (uint32_t u = blockIdx.x * 2 + (warp - 2); u < units; u += gridDim.x * 2) {
+    for (uint32_t u = blockIdx.x * 2 + (warp - 2); u < units && !(tc.debug & 8u); u += gridDim.x * 2) {
       const uint4* src = reinterpret_cast<const uint4*>(tc.x_local + static_cast<size_t>(u) * 32 * p.K);
       const size_t dst_off = (static_cast<size_t>(tc.rank) * tc.rows_per_rank + u * 32) * p.K;
-      for (uint32_t i = lane; i < vec_per_unit; i += 32 * 8) {
-        uint4 v[8];
+      // 16 x 16 B in flight per lane: the copy is latency-bound per warp, so depth is what shortens it
+      for (uint32_t i = lane; i < vec_per_unit; i += 32 * 16) {
+        uint4 v[16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) if (i + j * 32 < vec_per_unit) v[j] = ld_nc_v4(src + i + j * 32);
-        for (int pr = 1; pr < tc.world; ++pr) {
+        for (int j = 0; j < 16; ++j) if (i + j * 32 < vec_per_unit) v[j] = ld_nc_v4(src + i + j * 32);
+        // pr = 0 is this rank's own gather buffer: after the kernel it holds the complete gathered operand,
+        // which the weight-gradient GEMM reads in place (no host-side reassembly copies)
+        for (int pr = 0; pr < tc.world; ++pr) {
           uint4* dst = reinterpret_cast<uint4*>(tc.gather[(tc.rank + pr) % tc.world] + dst_off);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) if (i + j * 32 < vec_per_unit) st_v4(dst + i + j * 32, v[j]);
+          for (int j = 0; j < 16; ++j) if (i + j * 32 < vec_per_unit) st_v4(dst + i + j * 32, v[j]);
         }
       }
       __threadfence_system();
@@ -330,7 +339,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
             }
           }
-          if (owner == static_cast<uint32_t>(tc.rank)) {
+          if (owner == static_cast<uint32_t>(tc.rank) && !(tc.debug & 1u)) {
             flush_pending();     // everything this warp sent must be visible before it starts waiting
             // reduce: add every peer's partial of this [32 x 64] slab (flag acquire -> TMA load -> smem)
             uint64_t* ab = &aux_bar[warp - kEpiWarp0];
@@ -371,7 +380,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           } else {
             // scatter: coalesced 16-byte NVLink stores of the bf16 partial slab into the owner's staging buffer
             __syncwarp();
-            __nv_bfloat16* dst = tc.stage[owner] + (static_cast<size_t>(tc.rank) * tc.rows_per_rank + m_loc) * p.N + nc;
+            const uint32_t tgt = (tc.debug & 2u) ? static_cast<uint32_t>(tc.rank) : owner;
+            __nv_bfloat16* dst = tc.stage[tgt] + (static_cast<size_t>(tc.rank) * tc.rows_per_rank + m_loc) * p.N + nc;
 #pragma unroll
             for (uint32_t i = 0; i < 8; ++i) {
               const uint32_t r = i * 4 + (lane >> 3), c = lane & 7;
@@ -380,7 +390,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                 st_v4(dst + static_cast<size_t>(r) * p.N + c * 8, v);
               }
             }
-            uint32_t* fl = tc.rs_flags[owner] + fidx + tc.rank;
+            uint32_t* fl = tc.rs_flags[tgt] + fidx + tc.rank;
             if (npend == 0) pend0 = fl; else if (npend == 1) pend1 = fl; else if (npend == 2) pend2 = fl; else pend3 = fl;
             if (++npend == 4) flush_pending();
           }
@@ -687,6 +697,8 @@ static int fill_comm(TpComm& c, int rank, int world, unsigned seq, int M) {
   if (world < 2 || world > TP_MAX || M % (128 * world)) return 915;
   c.rank = rank; c.world = world; c.seq = seq;
   c.rows_per_rank = M / world; c.mb_per_rank = c.rows_per_rank / 128;
+  const char* dbg = getenv("QN_TP_DEBUG");
+  c.debug = dbg ? static_cast<uint32_t>(atoi(dbg)) : 0u;
   return 0;
 }
 }  // namespace qn

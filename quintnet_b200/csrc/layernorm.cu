@@ -6,6 +6,8 @@
 // tiny kernel folds the per-CTA partials.
 #include "common.cuh"
 
+#include <cstdlib>
+
 namespace qn {
 
 template <typename T> struct Vec;  // 16-byte vector of T
@@ -210,6 +212,197 @@ layernorm_bwd_dgdb_kernel(const T* __restrict__ dy, const T* __restrict__ x, con
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// Fused backward for bf16 (the training path): dx (+ dropout'(dx)), dgamma and dbeta in ONE pass over dy / x / dadd.
+// Row blocks of 8 rows are streamed into shared memory by 1-D bulk async copies (rows are contiguous, so a block
+// is one copy per tensor) through a 2-stage mbarrier ring, which keeps ~100 KB per SM in flight without holding
+// it in registers.  Phase 1: one warp per row computes the two row means.  Phase 2: each thread owns 8 columns
+// (one 16-byte vector) for half of the rows, writes dx with fully coalesced stores and accumulates dgamma / dbeta
+// for its columns in 16 registers over every row the CTA ever sees; one vector `red` per thread at the end.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int LNF_R = 8, LNF_STAGES = 2, LNF_THREADS = 256;
+
+template <int CV, bool HAS_ADD>
+__global__ void __launch_bounds__(LNF_THREADS)
+ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                    const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean_in,
+                    const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ dadd,
+                    __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop, float* __restrict__ acc,
+                    int rows, int cols, const LnDropout dr) {
+  extern __shared__ __align__(128) uint8_t lnf_smem[];
+  __shared__ uint64_t full[LNF_STAGES];
+  __shared__ float s_stat[LNF_STAGES][LNF_R][4];          // mean, rstd, c1, c2 per row
+  constexpr int NT = HAS_ADD ? 3 : 2;
+  const int row_bytes = cols * 2;
+  const int tens_bytes = LNF_R * row_bytes;
+  const int stage_bytes = NT * tens_bytes;
+  uint8_t* s_gamma = lnf_smem + LNF_STAGES * stage_bytes;
+  const int nvec = cols >> 3;
+  const int nblk = (rows + LNF_R - 1) / LNF_R;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int c = tid & 127, h = tid >> 7;
+  const uint32_t dkey = drop_key32(dr.seed, dr.offset);
+
+  for (int i = tid; i < nvec; i += LNF_THREADS)
+    reinterpret_cast<uint4*>(s_gamma)[i] = reinterpret_cast<const uint4*>(gamma)[i];
+  if (tid == 0) {
+    for (int i = 0; i < LNF_STAGES; ++i) mbar_init(&full[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  auto issue = [&](int blk, int st) {
+    const int r0 = blk * LNF_R;
+    const uint32_t bytes = static_cast<uint32_t>(min(LNF_R, rows - r0)) * row_bytes;
+    uint8_t* sb = lnf_smem + st * stage_bytes;
+    mbar_arrive_expect_tx(&full[st], bytes * NT);
+    bulk_load_1d(sb, dy + static_cast<size_t>(r0) * cols, bytes, &full[st]);
+    bulk_load_1d(sb + tens_bytes, x + static_cast<size_t>(r0) * cols, bytes, &full[st]);
+    if (HAS_ADD) bulk_load_1d(sb + 2 * tens_bytes, dadd + static_cast<size_t>(r0) * cols, bytes, &full[st]);
+  };
+  if (tid == 0) {
+    for (int st = 0; st < LNF_STAGES; ++st) {
+      const int blk = blockIdx.x + st * gridDim.x;
+      if (blk < nblk) issue(blk, st);
+    }
+  }
+  float g2[CV][8], ag[CV][8], ab[CV][8];
+#pragma unroll
+  for (int j = 0; j < CV; ++j) {
+    const int vi = c + 128 * j;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { ag[j][e] = 0.f; ab[j][e] = 0.f; g2[j][e] = 0.f; }
+    if (vi < nvec) Vec<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(s_gamma) + vi * 8, g2[j]);
+  }
+
+  int it = 0;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x, ++it) {
+    const int st = it % LNF_STAGES;
+    const uint32_t ph = (it / LNF_STAGES) & 1;
+    const int r0 = blk * LNF_R;
+    const int nr = min(LNF_R, rows - r0);
+    float mean = 0.f, rstd = 0.f;
+    if (warp < nr) { mean = mean_in[r0 + warp]; rstd = rstd_in[r0 + warp]; }   // latency hides behind the wait
+    mbar_wait(&full[st], ph);
+    const uint8_t* sb = lnf_smem + st * stage_bytes;
+    // ---- phase 1: warp -> row: c1 = mean(dy*g), c2 = mean(dy*g*xhat)
+    if (warp < nr) {
+      const __nv_bfloat16* sdy = reinterpret_cast<const __nv_bfloat16*>(sb + warp * row_bytes);
+      const __nv_bfloat16* sx = reinterpret_cast<const __nv_bfloat16*>(sb + tens_bytes + warp * row_bytes);
+      float c1 = 0.f, c2 = 0.f;
+      for (int vi = lane; vi < nvec; vi += 32) {
+        float d[8], xv[8], g[8];
+        Vec<__nv_bfloat16>::load(sdy + vi * 8, d);
+        Vec<__nv_bfloat16>::load(sx + vi * 8, xv);
+        Vec<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(s_gamma) + vi * 8, g);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float dyg = d[e] * g[e];
+          c1 += dyg;
+          c2 = fmaf(dyg, (xv[e] - mean) * rstd, c2);
+        }
+      }
+      c1 = warp_sum(c1) / cols;
+      c2 = warp_sum(c2) / cols;
+      if (lane == 0) { s_stat[st][warp][0] = mean; s_stat[st][warp][1] = rstd; s_stat[st][warp][2] = c1; s_stat[st][warp][3] = c2; }
+    }
+    __syncthreads();
+    // ---- phase 2: thread -> 8 columns x 4 rows
+#pragma unroll 1
+    for (int rr = 0; rr < LNF_R / 2; ++rr) {
+      const int r = h * (LNF_R / 2) + rr;
+      if (r >= nr) break;
+      const float rmean = s_stat[st][r][0], rrstd = s_stat[st][r][1], c1 = s_stat[st][r][2], c2 = s_stat[st][r][3];
+      const size_t grow = static_cast<size_t>(r0 + r);
+#pragma unroll
+      for (int j = 0; j < CV; ++j) {
+        const int vi = c + 128 * j;
+        if (vi < nvec) {
+          float d[8], xv[8], o[8];
+          Vec<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(sb + r * row_bytes) + vi * 8, d);
+          Vec<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(sb + tens_bytes + r * row_bytes) + vi * 8, xv);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            const float xh = (xv[e] - rmean) * rrstd;
+            ag[j][e] = fmaf(d[e], xh, ag[j][e]);
+            ab[j][e] += d[e];
+            o[e] = rrstd * (d[e] * g2[j][e] - c1 - xh * c2);
+          }
+          if (HAS_ADD) {
+            float a[8];
+            Vec<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(sb + 2 * tens_bytes + r * row_bytes) + vi * 8, a);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) o[e] += a[e];
+          }
+          Vec<__nv_bfloat16>::store(dx + grow * cols + vi * 8, o);
+          if (dx_drop != nullptr) {
+            if (dr.threshold != 0) {
+              const uint32_t m = keep_mask8_fast(dkey, grow * nvec + vi, dr.threshold);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = ((m >> e) & 1) ? o[e] * dr.scale : 0.f;
+            }
+            Vec<__nv_bfloat16>::store(dx_drop + grow * cols + vi * 8, o);
+          }
+        }
+      }
+    }
+    __syncthreads();                                       // every thread is done with this stage
+    if (tid == 0) {
+      const int nb = blk + LNF_STAGES * gridDim.x;
+      if (nb < nblk) issue(nb, st);
+    }
+  }
+  // ---- dgamma / dbeta: fold the two row halves through shared memory, one vector reduction per thread
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(lnf_smem);          // [128 * CV][16]; the ring is idle now
+  if (h == 1) {
+#pragma unroll
+    for (int j = 0; j < CV; ++j) {
+      const int vi = c + 128 * j;
+      if (vi < nvec) {                                     // the scratch is only nvec * 64 bytes deep
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { red[vi * 16 + e] = ag[j][e]; red[vi * 16 + 8 + e] = ab[j][e]; }
+      }
+    }
+  }
+  __syncthreads();
+  if (h == 0) {
+#pragma unroll
+    for (int j = 0; j < CV; ++j) {
+      const int vi = c + 128 * j;
+      if (vi < nvec) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { ag[j][e] += red[vi * 16 + e]; ab[j][e] += red[vi * 16 + 8 + e]; }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(acc + vi * 8 + q * 4), "f"(ag[j][q * 4 + 0]),
+                       "f"(ag[j][q * 4 + 1]), "f"(ag[j][q * 4 + 2]), "f"(ag[j][q * 4 + 3]) : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(acc + cols + vi * 8 + q * 4), "f"(ab[j][q * 4 + 0]),
+                       "f"(ab[j][q * 4 + 1]), "f"(ab[j][q * 4 + 2]), "f"(ab[j][q * 4 + 3]) : "memory");
+        }
+      }
+    }
+  }
+}
+
+template <int CV, bool HAS_ADD>
+static int launch_ln_bwd_fused(const void* dy, const void* x, const void* g, const float* mean, const float* rstd,
+                               const void* dadd, void* dx, void* dx_drop, float* acc, int rows, int cols,
+                               const LnDropout dr, cudaStream_t s) {
+  const int nt = HAS_ADD ? 3 : 2;
+  const int smem = LNF_STAGES * nt * LNF_R * cols * 2 + cols * 2;
+  auto k = ln_bwd_fused_kernel<CV, HAS_ADD>;
+  static bool attr_done = false;
+  if (!attr_done) { cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_done = true; }
+  const int per_sm = max(1, min(4, (220 * 1024) / (smem + 1024)));
+  const int nblk = (rows + LNF_R - 1) / LNF_R;
+  const int grid = min(nblk, 148 * per_sm);
+  using B = __nv_bfloat16;
+  k<<<grid, LNF_THREADS, smem, s>>>((const B*)dy, (const B*)x, (const B*)g, mean, rstd, (const B*)dadd, (B*)dx,
+                                   (B*)dx_drop, acc, rows, cols, dr);
+  return static_cast<int>(cudaGetLastError());
+}
+
 template <typename T>
 __global__ void ln_finalize_kernel(const float* __restrict__ acc, T* __restrict__ dgamma, T* __restrict__ dbeta, int cols) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -247,6 +440,18 @@ static int ln_bwd(const void* dy, const void* x, const void* g, const float* mea
   constexpr int VN = Vec<T>::N;
   if (cols % VN || cols > 32 * LN_MAXV * VN) return 920;
   (void)nparts;
+  if (sizeof(T) == 2 && cols <= 2048 && rows >= 64 && getenv("QN_LN_BWD_SPLIT") == nullptr) {
+    // fused single-pass kernel (bf16): fp32 accumulators [2 * cols] in the workspace, then bf16 conversion
+    cudaMemsetAsync(workspace, 0, 2ull * cols * sizeof(float), s);
+    int rc;
+    if (cols <= 1024) rc = dadd ? launch_ln_bwd_fused<1, true>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s)
+                                : launch_ln_bwd_fused<1, false>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s);
+    else rc = dadd ? launch_ln_bwd_fused<2, true>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s)
+                   : launch_ln_bwd_fused<2, false>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s);
+    if (rc) return rc;
+    ln_finalize_kernel<T><<<(cols + 255) / 256, 256, 0, s>>>(workspace, (T*)dgamma, (T*)dbeta, cols);
+    return static_cast<int>(cudaGetLastError());
+  }
   int grid = (rows + LN_WARPS - 1) / LN_WARPS;
   if (grid > 148 * 16) grid = 148 * 16;
   const int mv = (cols / VN + 31) / 32;

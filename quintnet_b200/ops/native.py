@@ -130,6 +130,8 @@ _I, _L, _F, _P = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_void_
 _U = ctypes.c_ulonglong
 _SIGNATURES = {
     "qn_comm_set_flag_watchdog": [ctypes.c_longlong],
+    "qn_push_bench": [_P, _P, _L, _I, _I, _I, _I, _L, _P],
+    "qn_push_bench_bulk": [_P, _P, _L, _I, _I, _P],
     "qn_gemm_set_flag_watchdog": [ctypes.c_longlong],
     "qn_gemm_bf16": [_P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _P, _P, _L, _I, _I, _P],
     "qn_gemm_bf16_splitk": [_P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _P],

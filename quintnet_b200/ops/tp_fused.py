@@ -85,8 +85,14 @@ def can_fuse(rows_total: int, group, *dims) -> bool:
 
 
 def _ag_gemm(ws: _Workspace, x_local: torch.Tensor, b: torch.Tensor, b_mn: bool, N: int, K: int, epilogue: int,
-             bias, z, out_full_x: bool):
-    """returns (Y [M, N], X_full [M, K] or None)"""
+             bias, z, out_full_x: bool, transient: bool = False):
+    """returns (Y [M, N], X_full [M, K] or None).
+
+    The kernel leaves the complete gathered operand in this rank's symmetric gather buffer (peers' rows arrive
+    by NVLink push, own rows are written by the same push warps).  ``transient=True`` returns that buffer as a
+    view — valid until the next-but-one all-gather launch of this workspace recycles it, i.e. long enough for
+    the weight-gradient GEMM that immediately follows in backward; otherwise one copy is taken (forward:
+    the operand must survive until backward)."""
     rows = x_local.shape[0]
     M = rows * ws.world
     ws.ensure(M * K * 2)
@@ -101,16 +107,9 @@ def _ag_gemm(ws: _Workspace, x_local: torch.Tensor, b: torch.Tensor, b_mn: bool,
     native.count()
     x_full = None
     if out_full_x:
-        # keep the gathered operand for the weight-gradient GEMM (the symmetric buffer is recycled two
-        # launches later): peers' rows arrived by NVLink push, own rows come from x_local — M*K*2 bytes moved
-        g = ws.gather[par].tensor[: M * K * 2].view(torch.bfloat16).view(M, K)
-        x_full = torch.empty((M, K), dtype=torch.bfloat16, device=x_local.device)
-        lo, hi = ws.rank * rows, (ws.rank + 1) * rows
-        if lo > 0:
-            x_full[:lo].copy_(g[:lo])
-        if hi < M:
-            x_full[hi:].copy_(g[hi:])
-        x_full[lo:hi].copy_(x_local)
+        x_full = ws.gather[par].tensor[: M * K * 2].view(torch.bfloat16).view(M, K)
+        if not transient:
+            x_full = x_full.clone()
     return y, x_full
 
 
@@ -191,7 +190,7 @@ class _LinearReduceScatter(torch.autograd.Function):
         M = x2.shape[0]
         need_full = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
         # dX = AG(dY_local) · W   (W [N, K] stored [K_red = N, N_out = K] -> MN-major B)
-        dx, dy_full = _ag_gemm(ws, dy2, w, True, K, N, EPI_NONE, None, None, need_full)
+        dx, dy_full = _ag_gemm(ws, dy2, w, True, K, N, EPI_NONE, None, None, need_full, transient=True)
         dw = gemm(dy_full, x2, N, K, M, a_mn=True, b_mn=True) if ctx.needs_input_grad[1] else None
         db = colsum(dy_full) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx.view(ctx.xshape), dw, db, None
@@ -227,7 +226,7 @@ class _SequenceParallelMLP(torch.autograd.Function):
         ws = _ws(ctx.group, dy.device)
         M = x_full.shape[0]
         # dZ = (AG(dY_local) · W2) ⊙ gelu'(z)   — gelu' applied in the fused kernel's epilogue
-        dz, dy_full = _ag_gemm(ws, dy2, w2, True, I, O, EPI_MUL_AUX, None, g, True)
+        dz, dy_full = _ag_gemm(ws, dy2, w2, True, I, O, EPI_MUL_AUX, None, g, True, transient=True)
         dw2 = gemm(dy_full, a, O, I, M, a_mn=True, b_mn=True)
         db2 = colsum(dy_full) if ctx.has_b2 else None
         dx = _gemm_rs(ws, dz, w1, True, E, I, None).view(ctx.xshape)             # dX_local = RS(dZ · W1)

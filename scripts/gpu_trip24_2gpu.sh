@@ -1,0 +1,3 @@
+#!/bin/bash
+mkdir -p gpurun_out
+echo "== nvlink push bench"; timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29871 scripts/bench_nvlink_push.py 2>&1 | grep " us\|Error\|error\|16 MiB" | tee gpurun_out/nvlink_push.log

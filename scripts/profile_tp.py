@@ -28,4 +28,14 @@ if rank == 0:
     print(f"total device ms {tot/1e3:.1f} for {M} micro-batches")
     for e in sorted(evs, key=lambda e: -e.device_time_total)[:34]:
         print(f"{e.device_time_total/tot*100:5.1f}%  {e.device_time_total/1e3:9.2f} ms  x{e.count:5d}  {e.key[:100]}")
+    # per-launch durations of the GEMM kernels (different layer shapes share a template instance)
+    import collections
+    per = collections.defaultdict(list)
+    for e in prof.events():
+        if "gemm_bf16_kernel" in e.name and e.device_time > 0:
+            per[e.name[:60]].append(e.device_time)
+    for k, v in per.items():
+        v = sorted(v)
+        q = [v[int(i * (len(v) - 1) / 10)] for i in range(11)]
+        print(f"{k}  n={len(v)}  deciles(us)=" + " ".join(f"{x:.0f}" for x in q))
 torch.distributed.barrier()
