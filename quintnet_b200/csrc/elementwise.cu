@@ -86,7 +86,20 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ acc, int 
   const int c0 = blockIdx.x * 64 + cv * 8;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (c0 < cols) {
-    for (int r = blockIdx.y * 32 + rl; r < rows; r += gridDim.y * 32) {
+    // four independent 16-byte loads in flight per thread: the sweep is latency-bound otherwise
+    const int step = gridDim.y * 32;
+    int r = blockIdx.y * 32 + rl;
+    for (; r + 3 * step < rows; r += 4 * step) {
+      uint4 u[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) u[k] = ld_nc_v4(x + (size_t)(r + k * step) * ld + c0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = unpack_bf16(u[k].x), b = unpack_bf16(u[k].y), c = unpack_bf16(u[k].z), d = unpack_bf16(u[k].w);
+        s[0] += a.x; s[1] += a.y; s[2] += b.x; s[3] += b.y; s[4] += c.x; s[5] += c.y; s[6] += d.x; s[7] += d.y;
+      }
+    }
+    for (; r < rows; r += step) {
       float f[8];
       load8(x + (size_t)r * ld + c0, f);
 #pragma unroll

@@ -62,6 +62,7 @@ struct TpComm {
   uint32_t* ag_flags[TP_MAX];         // AG: every rank's per-32-row flags [M / 32]
   __nv_bfloat16* stage[TP_MAX];       // RS: every rank's staging buffer [world][rows_per_rank][N]
   uint32_t* rs_flags[TP_MAX];         // RS: every rank's flags [mb_per_rank][4][N/64][world]
+  uint32_t comm_ctas;                 // AG: the last `comm_ctas` CTAs of the grid only push (0: two push warps per CTA)
   uint32_t debug;                     // QN_TP_DEBUG timing-attribution knobs (results are WRONG when set):
                                       //   1 RS: skip the peer wait + add    2 RS: remote stores go to local memory
                                       //   4 AG: skip the flag waits         8 AG: skip the push
@@ -111,6 +112,68 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
+  // FUSE_AG with dedicated communication CTAs: the last `comm_ctas` CTAs never touch the tensor cores.  One
+  // thread per CTA pumps this rank's shard through a shared-memory ring with 1-D bulk async copies: load an
+  // 8-row unit, bulk-store it into every peer's gather buffer over NVLink and into the local one, and publish
+  // the unit's flag once its store group has completed.  Units are dealt round-robin over the comm CTAs, so the
+  // rows arrive in order and the consumers' remote tiles become ready progressively; no per-thread fences or
+  // register staging, and the compute CTAs' TMA / MMA pipelines do not share an SM with NVLink-bound stores.
+  const uint32_t n_comm = (FUSE == FUSE_AG) ? tc.comm_ctas : 0u;
+  const uint32_t n_cta = gridDim.x - n_comm;
+  if constexpr (FUSE == FUSE_AG) {
+    if (blockIdx.x >= n_cta) {
+      // two pump threads per CTA (lane 0 of warps 0 and 1), each with its own ring
+      constexpr uint32_t kPumps = 2, kRing = 6, kAhead = 3, kLag = 12;
+      __shared__ uint64_t comm_full[kPumps][kRing];
+      if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < kPumps * kRing; ++i) mbar_init(&comm_full[0][0] + i, 1);
+        fence_barrier_init();
+      }
+      __syncthreads();
+      if (warp >= kPumps || lane != 0 || (tc.debug & 8u)) return;
+      const uint32_t units = tc.rows_per_rank / 8;
+      const uint32_t unit_bytes = 16u * p.K;                     // 8 rows x K bf16
+      const uint32_t g = (blockIdx.x - n_cta) * kPumps + warp, G = n_comm * kPumps;
+      const uint32_t mine = (units > g) ? (units - g + G - 1) / G : 0u;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(tc.x_local);
+      uint8_t* ring = smem + warp * kRing * unit_bytes;
+      uint64_t* full = comm_full[warp];
+      const size_t shard_off = static_cast<size_t>(tc.rank) * tc.rows_per_rank * p.K * 2;
+      uint32_t published = 0;
+      auto publish = [&](uint32_t upto) {                        // flags of units [published, upto)
+        fence_proxy_async_all();
+        __threadfence_system();
+        for (uint32_t k = published; k < upto; ++k)
+          for (int pr = 1; pr < tc.world; ++pr)
+            st_relaxed_sys(tc.ag_flags[(tc.rank + pr) % tc.world] + tc.rank * units + g + k * G, tc.seq);
+        published = upto;
+      };
+      for (uint32_t it = 0; it < mine + kAhead; ++it) {
+        if (it < mine) {                                         // load unit `it` into its ring slot
+          const uint32_t st = it % kRing;
+          tma_store_wait_read<kRing - kAhead - 1>();             // the stores that read this slot have drained it
+          mbar_arrive_expect_tx(&full[st], unit_bytes);
+          bulk_load_1d(ring + st * unit_bytes, src + static_cast<size_t>(g + it * G) * unit_bytes, unit_bytes, &full[st]);
+        }
+        if (it >= kAhead) {                                      // store unit j to every gather buffer
+          const uint32_t j = it - kAhead, st = j % kRing;
+          mbar_wait(&full[st], (j / kRing) & 1);
+          const size_t off = shard_off + static_cast<size_t>(g + j * G) * unit_bytes;
+          for (int pr = 0; pr < tc.world; ++pr)
+            bulk_store_1d(reinterpret_cast<uint8_t*>(tc.gather[(tc.rank + pr) % tc.world]) + off, ring + st * unit_bytes,
+                          unit_bytes);
+          tma_store_commit();
+          if ((j & 3u) == 3u && j >= kLag) {                     // every 4th unit: publish what has surely landed
+            tma_store_wait_all<kLag>();                          // groups <= j - kLag are complete (acked by the peer)
+            publish(j - kLag + 1);
+          }
+        }
+      }
+      tma_store_wait_all<0>();
+      publish(mine);
+      return;
+    }
+  }
   const uint32_t tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
   const uint32_t tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const uint32_t num_tiles = tiles_m * tiles_n;
@@ -150,7 +213,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------------------ TMA producer
     {
       uint32_t stage = 0, phase = 0;
-      for (uint32_t work = blockIdx.x; work < num_work; work += gridDim.x) {
+      for (uint32_t work = blockIdx.x; work < num_work; work += n_cta) {
         const uint32_t tile = work / splits, split = work - tile * splits;
         const uint32_t kb_begin = split * kb_per_split, kb_end = min(num_kb_total, kb_begin + kb_per_split);
         uint32_t m_blk, n_blk;
@@ -161,7 +224,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if constexpr (FUSE == FUSE_AG) {
           a_remote = (m_blk / tc.mb_per_rank) != static_cast<uint32_t>(tc.rank);
           if (a_remote && !(tc.debug & 4u)) {   // the peer's pushes of these 128 rows must have landed
-            if (lane < 4) wait_flag_ge(tc.ag_flags[tc.rank] + m_blk * 4 + lane, tc.seq);   // 4 units polled in parallel
+            if (lane < 16) wait_flag_ge(tc.ag_flags[tc.rank] + m_blk * 16 + lane, tc.seq);  // 16 8-row units in parallel
             __syncwarp();
             fence_proxy_async_all();      // generic-proxy (NVLink) writes -> async-proxy (TMA) reads
           }
@@ -204,7 +267,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       constexpr uint32_t A_KSTEP = A_MN ? UMMA_K * 128 : UMMA_K * 2;
       constexpr uint32_t B_KSTEP = B_MN ? UMMA_K * 128 : UMMA_K * 2;
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      for (uint32_t work = blockIdx.x; work < num_work; work += gridDim.x) {
+      for (uint32_t work = blockIdx.x; work < num_work; work += n_cta) {
         const uint32_t split = work % splits;
         const uint32_t kb_begin = split * kb_per_split, kb_end = min(num_kb_total, kb_begin + kb_per_split);
         mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -228,7 +291,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-  } else if (FUSE == FUSE_AG && (warp == 2 || warp == 3)) {
+  } else if (FUSE == FUSE_AG && n_comm == 0 && (warp == 2 || warp == 3)) {
     // ------------------------------------------------ all-gather push (this rank's shard -> every peer)
     const uint32_t units = tc.rows_per_rank / 32;
     const uint32_t vec_per_unit = 32 * p.K / 8;                 // 16-byte vectors per 32-row unit
@@ -250,9 +313,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       __threadfence_system();
       __syncwarp();
-      if (lane == 0)
+      if (lane < 4)                                        // flags are per 8 rows: this unit covers four
         for (int pr = 1; pr < tc.world; ++pr)
-          st_relaxed_sys(tc.ag_flags[(tc.rank + pr) % tc.world] + tc.rank * units + u, tc.seq);
+          st_relaxed_sys(tc.ag_flags[(tc.rank + pr) % tc.world] + (tc.rank * units + u) * 4 + lane, tc.seq);
     }
   } else if (warp >= kEpiWarp0) {
     // ---------------------------------------------------------------- epilogue (8 warps)
@@ -279,7 +342,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       npend = 0;
     };
-    for (uint32_t work = blockIdx.x; work < num_work; work += gridDim.x) {
+    for (uint32_t work = blockIdx.x; work < num_work; work += n_cta) {
       const uint32_t tile = work / splits;
       uint32_t m_blk, n_blk;
       tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
@@ -571,6 +634,12 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   TpComm c0{};
   if (FUSE != FUSE_NONE && comm == nullptr) return 914;
+  if (FUSE == FUSE_AG && comm->comm_ctas > 0) {              // compute CTAs + dedicated communication CTAs
+    const int ncomm = static_cast<int>(comm->comm_ctas);
+    const int avail = (max_ctas > 0 && max_ctas < g_num_sms ? max_ctas : g_num_sms) - ncomm;
+    if (avail < 1) return 917;
+    grid = (static_cast<int>(tiles) < avail ? static_cast<int>(tiles) : avail) + ncomm;
+  }
   kern<<<grid, kNumThreads, C::SMEM_BYTES, stream>>>(ta, tb, tc, tz, tx ? *tx : tc, p, comm ? *comm : c0);
   return static_cast<int>(cudaGetLastError());
 }
@@ -693,12 +762,16 @@ extern "C" int qn_gemm_bf16_splitk(const void* a, const void* b, void* c, float*
 
 // ------------------------------------------------------------------------------- fused TP entry points
 namespace qn {
+constexpr uint32_t kDefaultCommCtas = 0;
 static int fill_comm(TpComm& c, int rank, int world, unsigned seq, int M) {
   if (world < 2 || world > TP_MAX || M % (128 * world)) return 915;
   c.rank = rank; c.world = world; c.seq = seq;
   c.rows_per_rank = M / world; c.mb_per_rank = c.rows_per_rank / 128;
   const char* dbg = getenv("QN_TP_DEBUG");
   c.debug = dbg ? static_cast<uint32_t>(atoi(dbg)) : 0u;
+  const char* cc = getenv("QN_TP_COMM_CTAS");
+  c.comm_ctas = cc ? static_cast<uint32_t>(atoi(cc)) : kDefaultCommCtas;
+  if (c.comm_ctas > 64) c.comm_ctas = 64;
   return 0;
 }
 }  // namespace qn
@@ -715,6 +788,8 @@ extern "C" int qn_gemm_ag_bf16(const void* x_local, void* const* gather, void* c
   if (int rc = fill_comm(comm, rank, world, seq, M)) return rc;
   if ((K % 8) || (ldb % 8) || (ldc % 8)) return 910;
   comm.x_local = static_cast<const __nv_bfloat16*>(x_local);
+  if (comm.comm_ctas && (12ll * 16 * K > 192 * 1024 || (reinterpret_cast<uintptr_t>(x_local) & 15)))
+    comm.comm_ctas = 0;                                        // ring slot = 8 rows x K must fit 8-deep in smem
   for (int r = 0; r < world; ++r) {
     comm.gather[r] = static_cast<__nv_bfloat16*>(gather[r]);
     comm.ag_flags[r] = static_cast<uint32_t*>(ag_flags[r]);

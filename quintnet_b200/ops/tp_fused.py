@@ -79,7 +79,7 @@ def available(group) -> bool:
 def can_fuse(rows_total: int, group, *dims) -> bool:
     """``rows_total`` = M of the (gathered) token matrix; dims = the K / N sizes involved."""
     P = dist.get_world_size(group)
-    flags_needed = max(rows_total // 32, (rows_total // P // 128) * 4 * ((max(dims) + 63) // 64) * P) * 4
+    flags_needed = max(rows_total // 8, (rows_total // P // 128) * 4 * ((max(dims) + 63) // 64) * P) * 4
     return (rows_total % (128 * P) == 0 and all(int(d) % 8 == 0 for d in dims) and P <= 8
             and flags_needed <= _FLAG_BYTES)
 

@@ -79,16 +79,17 @@ for name, kind, N, K, b_mn, epi in CASES:
     e1.record(); torch.cuda.synchronize()
     if rank == 0:
         print(f"{name} plain GEMM (no comm, no epilogue) back-to-back {e0.elapsed_time(e1) * 1e3 / 12:6.1f} us  dbg=-", flush=True)
-for dbg in (0, 1, 3, 4, 12):
-    os.environ["QN_TP_DEBUG"] = str(dbg)
-    for name, kind, N, K, b_mn, epi in CASES:
-        if kind == "ag" and dbg in (1, 3): continue
-        if kind == "rs" and dbg in (4, 12): continue
-        t, tb = run_case(kind, N, K, b_mn, epi)
-        flops = 2.0 * M * N * K
-        out[f"{name} dbg={dbg}"] = {"us_isolated": round(t, 1), "us_back_to_back": round(tb, 1), "ideal_us_1350TF": round(flops / 1350e12 * 1e6, 1)}
-        if rank == 0:
-            print(f"{name} dbg={dbg:2d}: isolated {t:6.1f} us  back-to-back {tb:6.1f} us  (compute ideal {flops / 1350e12 * 1e6:5.1f} us)", flush=True)
+for comm in (0, 12, 16, 20):
+    os.environ["QN_TP_COMM_CTAS"] = str(comm)
+    for dbg in (0,):
+        os.environ["QN_TP_DEBUG"] = str(dbg)
+        for name, kind, N, K, b_mn, epi in CASES:
+            if kind == "rs" and (dbg != 0 or comm != 0): continue
+            t, tb = run_case(kind, N, K, b_mn, epi)
+            out[f"{name} comm={comm} dbg={dbg}"] = {"us_isolated": round(t, 1), "us_back_to_back": round(tb, 1)}
+            if rank == 0:
+                print(f"{name} comm={comm:2d} dbg={dbg:2d}: isolated {t:6.1f} us  back-to-back {tb:6.1f} us", flush=True)
+os.environ["QN_TP_COMM_CTAS"] = "0"
 os.environ["QN_TP_DEBUG"] = "0"
 if rank == 0:
     os.makedirs("gpurun_out", exist_ok=True)
