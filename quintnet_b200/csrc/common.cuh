@@ -138,6 +138,16 @@ QN_DEVICE void tmem_dealloc(uint32_t taddr) {  // same warp that allocated
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
 }
 
+// D[tmem] (+)= A[smem desc] * B[smem desc], fp8 (e4m3 / e5m2 per the instruction descriptor) inputs, fp32 accumulate
+QN_DEVICE void umma_f8_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // D[tmem] (+)= A[smem desc] * B[smem desc], bf16 inputs, fp32 accumulate
 QN_DEVICE void umma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -192,6 +202,12 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N, u
                                                         uint32_t b_mn_major) {
   return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn_major << 15) | (b_mn_major << 16) | ((N >> 3) << 17) |
          ((M >> 4) << 24);
+}
+
+// E4M3 x E4M3 -> F32 (kind::f8f6f4): a_format = b_format = 0, K-major operands, UMMA_K = 32 elements (= 32 bytes,
+// the same byte geometry as bf16's 16 x 2 bytes, so tiles, swizzle and descriptors are shared)
+__host__ __device__ constexpr uint32_t make_idesc_e4m3(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
 
 // ----------------------------------------------------------------------------

@@ -202,3 +202,52 @@ extern "C" int qn_rope(const void* x, void* y, const float* cosp, const float* s
                                                    sb, sh, st, backward ? -1.0f : 1.0f);
   return (int)cudaGetLastError();
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Row-wise FP8 (e4m3) quantisation for the FP8 GEMM: one warp per row, amax over the row, q = x * 448 / amax,
+// scale_out[row] = amax / 448 (the dequantisation factor the GEMM epilogue multiplies back in).
+// ---------------------------------------------------------------------------------------------------------
+#include <cuda_fp8.h>
+namespace qn {
+__global__ void __launch_bounds__(256)
+quantize_rowwise_e4m3_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ q, float* __restrict__ scale_out,
+                             int rows, int cols, long long ldx, long long ldq) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const __nv_bfloat16* xr = x + (size_t)row * ldx;
+  const int nvec = cols >> 3;
+  float amax = 0.f;
+  for (int v = lane; v < nvec; v += 32) {
+    float f[8];
+    load8(xr + v * 8, f);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) amax = fmaxf(amax, fabsf(f[e]));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  const float inv = amax > 0.f ? 448.0f / amax : 1.0f;
+  if (lane == 0) scale_out[row] = amax > 0.f ? amax / 448.0f : 1.0f;
+  uint8_t* qr = q + (size_t)row * ldq;
+  for (int v = lane; v < nvec; v += 32) {                 // second sweep hits L1/L2
+    float f[8];
+    load8(xr + v * 8, f);
+    uint2 o;
+    const uint32_t p0 = __nv_cvt_float2_to_fp8x2(make_float2(f[0] * inv, f[1] * inv), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t p1 = __nv_cvt_float2_to_fp8x2(make_float2(f[2] * inv, f[3] * inv), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t p2 = __nv_cvt_float2_to_fp8x2(make_float2(f[4] * inv, f[5] * inv), __NV_SATFINITE, __NV_E4M3);
+    const uint32_t p3 = __nv_cvt_float2_to_fp8x2(make_float2(f[6] * inv, f[7] * inv), __NV_SATFINITE, __NV_E4M3);
+    o.x = p0 | (p1 << 16);
+    o.y = p2 | (p3 << 16);
+    *reinterpret_cast<uint2*>(qr + v * 8) = o;
+  }
+}
+}  // namespace qn
+
+extern "C" int qn_quantize_rowwise_e4m3(const void* x, void* q, float* scale_out, int rows, int cols, long long ldx,
+                                        long long ldq, cudaStream_t s) {
+  if ((cols % 8) || (ldx % 8) || (ldq % 8)) return 940;
+  qn::quantize_rowwise_e4m3_kernel<<<(rows + 7) / 8, 256, 0, s>>>((const __nv_bfloat16*)x, (uint8_t*)q, scale_out, rows,
+                                                                 cols, ldx, ldq);
+  return (int)cudaGetLastError();
+}

@@ -39,6 +39,11 @@ struct GemmParams {
   uint32_t splits;             // split-K factor (>1: fp32 partials are atomically added into acc32)
   float* acc32;                // [M, ld32] fp32, zero-initialised by the caller
   uint32_t ld32;
+  // FP8 (e4m3) operands with row-wise scaling: A and B hold fp8 bytes (K counts byte PAIRS here, so every tile,
+  // descriptor and TMA box is byte-identical to the bf16 path); C = (A8 · B8ᵀ) * scale_a[row] * scale_b[col]
+  int fp8;
+  const float* scale_a;        // [M] dequantisation scale of each A row
+  const float* scale_b;        // [N] dequantisation scale of each B row (= output column)
 };
 
 // Fused tensor-parallel collectives (FUSE template parameter of the kernel):
@@ -282,7 +287,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (uint32_t k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(sa + k * A_KSTEP, 1024, A_LBO);
             const uint64_t bdesc = make_smem_desc_sw128(sb + k * B_KSTEP, 1024, B_LBO);
-            umma_bf16_ss(tmem_d, adesc, bdesc, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            if (p.fp8) umma_f8_ss(tmem_d, adesc, bdesc, make_idesc_e4m3(BLOCK_M, BLOCK_N), ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            else umma_bf16_ss(tmem_d, adesc, bdesc, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
           if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -501,6 +507,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tmem_ld_wait();
           float* f = reinterpret_cast<float*>(acc);
           const uint32_t nh = nc + hcol * 32;
+          if (p.fp8) {                                     // dequantise: per-row scale of A x per-column scale of B
+            const float sa = (m0 + lane < p.M) ? p.scale_a[m0 + lane] : 0.f;
+#pragma unroll
+            for (uint32_t v = 0; v < 8; ++v) {
+              if (nh + v * 4 < p.N) {
+                const float4 sb = *reinterpret_cast<const float4*>(p.scale_b + nh + v * 4);
+                f[v * 4 + 0] *= sa * sb.x; f[v * 4 + 1] *= sa * sb.y; f[v * 4 + 2] *= sa * sb.z; f[v * 4 + 3] *= sa * sb.w;
+              }
+            }
+          }
           if (p.epilogue != EPI_NONE && p.bias != nullptr) {
 #pragma unroll
             for (uint32_t v = 0; v < 4; ++v) {
@@ -855,4 +871,44 @@ extern "C" int qn_gemm_rs_bf16(const void* a, const void* b, void* c_local, void
 // Run-time deadline (in SM cycles) of the peer-flag waits in this translation unit; see common.cuh.
 extern "C" int qn_gemm_set_flag_watchdog(long long cycles) {
   return static_cast<int>(cudaMemcpyToSymbol(qn::g_flag_watchdog_cycles, &cycles, sizeof(cycles)));
+}
+
+// FP8 forward GEMM with row-wise ("1 x K block") scaling:  C[M, N] (bf16) = epilogue( (A8 · B8ᵀ) ⊙ (sa ⊗ sb) )
+//   a8 [M, K] and b8 [N, K] hold e4m3 bytes, K-major, leading dimensions in bytes (multiples of 16);
+//   scale_a [M], scale_b [N] fp32 dequantisation scales (qn_quantize_rowwise_e4m3 produces both tensors).
+//   epilogue: EPI_NONE / EPI_BIAS / EPI_BIAS_GELU (z = gelu'(pre-activation) as in the bf16 kernel).
+extern "C" int qn_gemm_fp8(const void* a8, const void* b8, void* c, int M, int N, int K, long long lda, long long ldb,
+                           long long ldc, const float* scale_a, const float* scale_b, int epilogue, const void* bias,
+                           void* z, long long ldz, int block_n, cudaStream_t stream) {
+  using namespace qn;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((K % 16) || (lda % 16) || (ldb % 16) || (ldc % 8) || (N % 4) || (reinterpret_cast<uintptr_t>(a8) & 15) ||
+      (reinterpret_cast<uintptr_t>(b8) & 15) || (reinterpret_cast<uintptr_t>(c) & 15) ||
+      (reinterpret_cast<uintptr_t>(scale_b) & 15))
+    return 910;
+  if (epilogue != EPI_NONE && epilogue != EPI_BIAS && epilogue != EPI_BIAS_GELU) return 911;
+  if (block_n == 0) {
+    const long long t256 = static_cast<long long>((M + 127) / 128) * ((N + 255) / 256);
+    block_n = (N > 128 && t256 >= 96) ? 256 : 128;
+  }
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K / 2;                       // byte pairs: the kernel's K loop walks 128-byte tile rows
+  p.bias = static_cast<const __nv_bfloat16*>(bias);
+  p.epilogue = epilogue;
+  p.has_z = (epilogue == EPI_BIAS_GELU && z != nullptr) ? 1 : 0;
+  p.fp8 = 1; p.scale_a = scale_a; p.scale_b = scale_b;
+  if (epilogue != EPI_NONE && bias != nullptr && (N % 8)) return 912;
+  CUtensorMap ta, tb, tc, tz;
+  int rc;
+  if ((rc = make_tmap(&ta, a8, M, K / 2, lda / 2, 64, BLOCK_M))) return rc;
+  if ((rc = make_tmap(&tb, b8, N, K / 2, ldb / 2, 64, block_n))) return rc;
+  if ((rc = make_tmap(&tc, c, M, N, ldc, 64, 32))) return rc;
+  if (p.has_z) {
+    if ((ldz % 8) || (reinterpret_cast<uintptr_t>(z) & 15)) return 913;
+    if ((rc = make_tmap(&tz, z, M, N, ldz, 64, 32))) return rc;
+  } else {
+    tz = tc;
+  }
+  if (block_n == 256) return launch<256, false, false>(ta, tb, tc, tz, p, 0, stream);
+  return launch<128, false, false>(ta, tb, tc, tz, p, 0, stream);
 }

@@ -30,16 +30,17 @@ class GPT2Attention(nn.Module):
         self.num_heads_local = self.num_heads // tp_size
         self.embed_dim_local = self.embed_dim // tp_size
         sp = bool(getattr(config, "sequence_parallel", False)) and tp_size > 1
+        fp8 = bool(getattr(config, "fp8_linear", False))
         if c_attn_bias is None and c_attn_weight is not None:
             c_attn_bias = torch.zeros(3 * self.embed_dim_local)
         self.c_attn = ColumnParallelLinear(device, tp_group, self.embed_dim, 3 * self.embed_dim_local,
                                            weight_slice=c_attn_weight, bias_slice=c_attn_bias,
-                                           gather_output=False, sequence_parallel=sp, dtype=dtype)
+                                           gather_output=False, sequence_parallel=sp, dtype=dtype, fp8=fp8)
         if c_proj_bias is None and c_proj_weight is None:
             c_proj_bias = torch.zeros(self.embed_dim)
         self.c_proj = RowParallelLinear(device, tp_group, self.embed_dim_local, self.embed_dim,
                                         weight_slice=c_proj_weight, bias_slice=c_proj_bias,
-                                        input_is_parallel=True, sequence_parallel=sp, dtype=dtype)
+                                        input_is_parallel=True, sequence_parallel=sp, dtype=dtype, fp8=fp8)
         self.attn_pdrop, self.resid_pdrop = config.attn_pdrop, config.resid_pdrop
         self.attn_dropout = nn.Dropout(config.attn_pdrop)
         self.resid_dropout = nn.Dropout(config.resid_pdrop)

@@ -24,6 +24,7 @@ class GPT2Config:
     rope_base: float = 10000.0
     sequence_parallel: bool = False   # token-sharded TP (fused AG->GEMM / GEMM->RS)
     pp_layer_counts: Optional[list] = None   # explicit layers per pipeline stage (default: even split)
+    fp8_linear: bool = False          # forward projections on e4m3 operands with row-wise scales (bf16 backward)
 
     def __post_init__(self):
         if self.n_inner is None:

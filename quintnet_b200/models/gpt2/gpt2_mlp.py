@@ -26,23 +26,24 @@ class GPT2MLP(nn.Module):
         self.inner_dim_local = self.inner_dim // tp_size
         self.tp_rank, self.tp_size, self.tp_group, self.device = tp_rank, tp_size, tp_group, device
         sp = bool(getattr(config, "sequence_parallel", False)) and tp_size > 1
+        fp8 = self.fp8 = bool(getattr(config, "fp8_linear", False))
         if c_fc_bias is None and c_fc_weight is not None:
             c_fc_bias = torch.zeros(self.inner_dim_local)
         self.c_fc = ColumnParallelLinear(device, tp_group, self.embed_dim, self.inner_dim_local,
                                          weight_slice=c_fc_weight, bias_slice=c_fc_bias,
                                          gather_output=False, sequence_parallel=sp,
-                                         activation="gelu", dtype=dtype)
+                                         activation="gelu", dtype=dtype, fp8=fp8)
         if c_proj_bias is None and c_proj_weight is None:
             c_proj_bias = torch.zeros(self.embed_dim)
         self.c_proj = RowParallelLinear(device, tp_group, self.inner_dim_local, self.embed_dim,
                                         weight_slice=c_proj_weight, bias_slice=c_proj_bias,
-                                        input_is_parallel=True, sequence_parallel=sp, dtype=dtype)
+                                        input_is_parallel=True, sequence_parallel=sp, dtype=dtype, fp8=fp8)
         self.resid_pdrop = config.resid_pdrop
         self.dropout = nn.Dropout(config.resid_pdrop)
 
     def forward(self, hidden_states: torch.Tensor, residual: Optional[torch.Tensor] = None,
                 raw: bool = False) -> torch.Tensor:
-        if not self.c_fc.sequence_parallel:
+        if not self.c_fc.sequence_parallel and not self.fp8:
             # whole MLP as ONE autograd op (GELU and GELU' fused into GEMM epilogues); the TP conjugate
             # collectives f / g wrap it exactly as they wrap the two separate layers
             x = Copy_To_Parallel.apply(hidden_states, self.tp_group)
@@ -51,7 +52,8 @@ class GPT2MLP(nn.Module):
             return h if raw else ops.dropout_add(h, residual, self.resid_pdrop, self.training)
         from ...parallel.tensor_parallel.layers import _fused_tp_ok
         rows_total = (hidden_states.numel() // hidden_states.shape[-1]) * self.tp_size
-        if _fused_tp_ok(hidden_states, self.tp_group, rows_total, self.embed_dim, self.inner_dim_local):
+        if self.c_fc.sequence_parallel and not self.fp8 and \
+                _fused_tp_ok(hidden_states, self.tp_group, rows_total, self.embed_dim, self.inner_dim_local):
             from ...ops import tp_fused
             h = tp_fused.sequence_parallel_mlp(hidden_states, self.c_fc.proj.weight, self.c_fc.proj.bias,
                                                self.c_proj.proj.weight, self.c_proj.bias, self.tp_group)

@@ -25,11 +25,17 @@ def _use_native(name: str, *tensors) -> bool:
 
 
 # ----------------------------------------------------------------- linear
-def linear(x, w, b=None, act: Optional[str] = None):
-    """y = act(x @ w.T + b);  w is [out, in] (nn.Linear layout)."""
+def linear(x, w, b=None, act: Optional[str] = None, fp8: bool = False):
+    """y = act(x @ w.T + b);  w is [out, in] (nn.Linear layout).  ``fp8=True``: forward GEMM on e4m3 operands
+    with row-wise (1 x K block) scales — fp8 tensor cores on B200, an exact emulation of the same quantisation
+    on the reference path."""
     if _use_native("gemm", x) and x.dtype == torch.bfloat16:
         from . import cuda_ops
+        if fp8 and cuda_ops.fp8_ok(x.shape[-1], w.shape[0]):
+            return cuda_ops.linear_fp8(x, w, b, act)
         return cuda_ops.linear(x, w, b, act)
+    if fp8:
+        return reference.linear_fp8(x, w, b, act)
     return reference.linear(x, w, b, act)
 
 

@@ -122,6 +122,71 @@ class _Linear(torch.autograd.Function):
         return dx, dw, db, None
 
 
+def quantize_rowwise(x2: torch.Tensor):
+    """bf16 [R, C] -> (e4m3 bytes [R, C] as uint8, fp32 dequantisation scale [R]); one scale per row
+    (a 1 x C block), amax-based, saturating."""
+    R, C = x2.shape
+    q = torch.empty((R, C), dtype=torch.uint8, device=x2.device)
+    sc = torch.empty((R,), dtype=torch.float32, device=x2.device)
+    rc = native.require().qn_quantize_rowwise_e4m3(x2.data_ptr(), q.data_ptr(), sc.data_ptr(), R, C, x2.stride(0), C,
+                                                   native.stream())
+    native.check(rc, "qn_quantize_rowwise_e4m3")
+    native.count()
+    return q, sc
+
+
+def fp8_ok(K: int, N: int) -> bool:
+    return K % 16 == 0 and N % 8 == 0
+
+
+def gemm_fp8(a8: torch.Tensor, sa: torch.Tensor, b8: torch.Tensor, sb: torch.Tensor, M: int, N: int, K: int, *,
+             epilogue: int = EPI_NONE, bias: Optional[torch.Tensor] = None, z: Optional[torch.Tensor] = None,
+             out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C[M, N] (bf16) = epilogue((A8 · B8ᵀ) * sa[:, None] * sb[None, :]) on the fp8 tensor cores
+    (tcgen05.mma kind::f8f6f4, fp32 accumulation in TMEM)."""
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.bfloat16, device=a8.device)
+    rc = native.require().qn_gemm_fp8(a8.data_ptr(), b8.data_ptr(), out.data_ptr(), M, N, K, a8.stride(0), b8.stride(0),
+                                      out.stride(0), sa.data_ptr(), sb.data_ptr(), epilogue, native.ptr(bias),
+                                      native.ptr(z), z.stride(0) if z is not None else 0, 0, native.stream())
+    native.check(rc, f"qn_gemm_fp8(M={M},N={N},K={K})")
+    native.count()
+    return out
+
+
+class _LinearFP8(torch.autograd.Function):
+    """Forward in FP8 (e4m3 activations and weights, row-wise scales, fp32 accumulation); backward in bf16 from
+    the saved bf16 operands — the usual mixed recipe (the gradient GEMMs keep the wider format)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        K, N = x.shape[-1], w.shape[0]
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        wq = w if w.dtype == torch.bfloat16 else w.to(torch.bfloat16)
+        a8, sa = quantize_rowwise(x2)
+        b8, sb = quantize_rowwise(wq)
+        z = None
+        if act == "gelu":
+            z = torch.empty((M, N), dtype=torch.bfloat16, device=x.device)
+            y = gemm_fp8(a8, sa, b8, sb, M, N, K, epilogue=EPI_BIAS_GELU, bias=b, z=z)
+        elif act is None:
+            y = gemm_fp8(a8, sa, b8, sb, M, N, K, epilogue=EPI_BIAS if b is not None else EPI_NONE, bias=b)
+        else:
+            raise ValueError(f"native fp8 linear: unsupported activation {act}")
+        ctx.save_for_backward(x2, wq, z)
+        ctx.act, ctx.has_bias, ctx.xshape, ctx.wdtype = act, b is not None, x.shape, w.dtype
+        return y.view(*x.shape[:-1], N)
+
+    backward = _Linear.backward
+
+
+def linear_fp8(x, w, b=None, act: Optional[str] = None):
+    return _LinearFP8.apply(x, w, b, act)
+
+
 class _FusedMLP(torch.autograd.Function):
     """y = (gelu(x·W1ᵀ + b1))·W2ᵀ + b2 with the GELU fused into the first GEMM's epilogue (forward) and
     gelu' fused into the dgrad GEMM's epilogue (backward): no stand-alone activation kernels."""

@@ -23,6 +23,20 @@ def linear(x, w, b=None, act: Optional[str] = None):
     return y
 
 
+def fake_quant_rowwise_e4m3(t: torch.Tensor) -> torch.Tensor:
+    """Row-wise amax-scaled e4m3 quantise -> dequantise (the numerics of the FP8 GEMM operands), with a
+    straight-through gradient so backward stays in the wide format like the native op."""
+    t2 = t.detach().float()
+    amax = t2.abs().amax(dim=-1, keepdim=True)
+    scale = torch.where(amax > 0, amax / 448.0, torch.ones_like(amax))
+    q = (t2 / scale).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float() * scale
+    return t + (q.to(t.dtype) - t).detach()
+
+
+def linear_fp8(x, w, b=None, act: Optional[str] = None):
+    return linear(fake_quant_rowwise_e4m3(x), fake_quant_rowwise_e4m3(w), b, act)
+
+
 def layer_norm(x, w, b, eps: float = 1e-5):
     return F.layer_norm(x, (x.shape[-1],), w, b, eps)
 

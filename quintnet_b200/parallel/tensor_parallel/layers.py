@@ -48,9 +48,10 @@ class ColumnParallelLinear(nn.Module):
                  bias_slice: Optional[torch.Tensor] = None,
                  gather_output: bool = True, sync_gradients: bool = True,
                  gather_mode: str = "slice", sequence_parallel: bool = False,
-                 activation: Optional[str] = None, dtype: Optional[torch.dtype] = None):
+                 activation: Optional[str] = None, dtype: Optional[torch.dtype] = None, fp8: bool = False):
         super().__init__()
         self.device, self.tp_group = local_device, tp_group
+        self.fp8 = fp8            # forward GEMM on row-wise-scaled e4m3 operands (SURVEY 2.3 "FP8 option")
         self.in_features, self.out_features_per_rank = in_features, out_features_per_rank
         self.gather_output, self.sync_gradients = gather_output, sync_gradients
         self.gather_mode, self.sequence_parallel = gather_mode, sequence_parallel
@@ -72,15 +73,15 @@ class ColumnParallelLinear(nn.Module):
         if self.sequence_parallel and group_size(self.tp_group) > 1:
             # x is token-sharded along dim 0: all-gather -> GEMM
             rows_total = (x.numel() // x.shape[-1]) * group_size(self.tp_group)
-            if _fused_tp_ok(x, self.tp_group, rows_total, w.shape[0], w.shape[1]) and \
+            if not self.fp8 and _fused_tp_ok(x, self.tp_group, rows_total, w.shape[0], w.shape[1]) and \
                     (b is None or b.dtype == torch.bfloat16):
                 from ...ops import tp_fused
                 return tp_fused.allgather_linear(x, w, b, self.tp_group, self.activation)
             xg = All_Gather.apply(x, self.tp_group, "reduce_scatter", 0)
-            return ops.linear(xg, w, b, self.activation)
+            return ops.linear(xg, w, b, self.activation, fp8=self.fp8)
         if self.sync_gradients:
             x = Copy_To_Parallel.apply(x, self.tp_group)
-        y = ops.linear(x, w, b, self.activation)
+        y = ops.linear(x, w, b, self.activation, fp8=self.fp8)
         if self.gather_output:
             y = All_Gather.apply(y, self.tp_group, self.gather_mode, -1)
         return y
@@ -97,9 +98,10 @@ class RowParallelLinear(nn.Module):
                  weight_slice: Optional[torch.Tensor] = None,
                  bias_slice: Optional[torch.Tensor] = None,
                  input_is_parallel: bool = True, sequence_parallel: bool = False,
-                 dtype: Optional[torch.dtype] = None):
+                 dtype: Optional[torch.dtype] = None, fp8: bool = False):
         super().__init__()
         self.device, self.tp_group = local_device, tp_group
+        self.fp8 = fp8
         self.in_features_per_rank, self.out_features = in_features_per_rank, out_features
         self.input_is_parallel, self.sequence_parallel = input_is_parallel, sequence_parallel
         self.proj = nn.Linear(in_features_per_rank, out_features, bias=False,
@@ -123,13 +125,13 @@ class RowParallelLinear(nn.Module):
         w = self.proj.weight
         if self.sequence_parallel and n > 1:
             rows_total = x.numel() // x.shape[-1]
-            if _fused_tp_ok(x, self.tp_group, rows_total, w.shape[0], w.shape[1]) and \
+            if not self.fp8 and _fused_tp_ok(x, self.tp_group, rows_total, w.shape[0], w.shape[1]) and \
                     (self.bias is None or self.bias.dtype == torch.bfloat16):
                 from ...ops import tp_fused
                 return tp_fused.linear_reduce_scatter(x, w, self.bias, self.tp_group)
-            y = ops.linear(x, w, self.bias)          # bias joins rank 0's partial sum
+            y = ops.linear(x, w, self.bias, fp8=self.fp8)          # bias joins rank 0's partial sum
             return ReduceScatter.apply(y, self.tp_group, 0)
-        y = ops.linear(x, w, self.bias)
+        y = ops.linear(x, w, self.bias, fp8=self.fp8)
         return All_Reduce.apply(y, self.tp_group)
 
     def extra_repr(self) -> str:

@@ -206,3 +206,18 @@ def _replay(rank, world, out_dir):
 
 def test_deterministic_replay(tmp_path):
     run_distributed(_replay, 2, str(tmp_path))
+
+
+def test_fp8_linear_option_cpu():
+    """fp8_linear: projections run on (emulated) e4m3 operands; the model still matches the bf16/fp32 one closely
+    and trains."""
+    torch.manual_seed(0)
+    cfg8 = GPT2Config(**dict(CFG, fp8_linear=True))
+    m8, m = GPT2Model(cfg8, seed=1), GPT2Model(GPT2Config(**CFG), seed=1)
+    ids = torch.randint(1, 96, (4, 16))
+    l8, n8 = m8(ids, labels=ids)
+    l, n = m(ids, labels=ids)
+    assert abs(float(l8 / n8) - float(l / n)) < 0.05 * float(l / n)
+    (l8 / n8).backward()
+    assert all(torch.isfinite(p.grad).all() for p in m8.parameters() if p.grad is not None)
+    assert m8.blocks[0].mlp.c_fc.fp8 and m8.blocks[0].attn.c_proj.fp8

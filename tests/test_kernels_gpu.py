@@ -309,3 +309,41 @@ def test_dropout_add_layernorm_fused():
         assert _rel(x.grad, xr.grad) < 6e-2, (p, _rel(x.grad, xr.grad))
         assert _rel(r.grad, rr.grad) < 3e-2
         assert _rel(w.grad, wr.grad) < 3e-2 and _rel(b.grad, br.grad) < 3e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 512, 256), (1000, 768, 1024), (4096, 3072, 1024)])
+def test_fp8_quantize_and_gemm(M, N, K):
+    """e4m3 row-wise quantiser and the kind::f8f6f4 GEMM vs an fp32 emulation of the same quantisation."""
+    from quintnet_b200.ops import cuda_ops, reference
+    torch.manual_seed(21)
+    a = torch.randn(M, K, device="cuda", dtype=torch.bfloat16)
+    a[:, :7] *= 30.0                       # outliers: the per-row scale has to absorb them
+    w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+    qa, sa = cuda_ops.quantize_rowwise(a)
+    qw, sw = cuda_ops.quantize_rowwise(w)
+    deq = qa.view(torch.float8_e4m3fn).float() * sa[:, None]
+    emu = reference.fake_quant_rowwise_e4m3(a.float())
+    assert _rel(deq, emu) < 5e-3          # x * (448 / amax) vs x / (amax / 448): one-ulp ties round differently
+    assert torch.allclose(sa, a.float().abs().amax(dim=1) / 448.0, rtol=1e-3)
+    y = cuda_ops.gemm_fp8(qa, sa, qw, sw, M, N, K)
+    ref = emu @ reference.fake_quant_rowwise_e4m3(w.float()).t()
+    assert _rel(y, ref) < 1e-2, _rel(y, ref)
+    assert _rel(y, a.float() @ w.float().t()) < 6e-2          # and it is a usable approximation of the real product
+
+
+@pytest.mark.parametrize("act", [None, "gelu"])
+def test_fp8_linear_autograd(act):
+    from quintnet_b200 import ops
+    from quintnet_b200.ops import reference
+    torch.manual_seed(22)
+    x = torch.randn(8, 128, 1024, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    w = (torch.randn(2048, 1024, device="cuda") * 0.03).to(torch.bfloat16).requires_grad_(True)
+    b = torch.randn(2048, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    y = ops.linear(x, w, b, act, fp8=True)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+    yr = reference.linear_fp8(xr, wr, br, act)
+    yr.backward(dy.float())
+    assert _rel(y, yr) < 2e-2, _rel(y, yr)
+    assert _rel(x.grad, xr.grad) < 5e-2 and _rel(w.grad, wr.grad) < 5e-2 and _rel(b.grad, br.grad) < 2e-2
