@@ -75,13 +75,16 @@ struct TpComm {
 
 QN_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <uint32_t BLOCK_N>
+template <uint32_t BLOCK_N, bool CTA2 = false>
 struct Cfg {
+  // CTA2: a pair of CTAs (cta_group::2) owns a 256 x BLOCK_N tile; each CTA stages its own 128 rows of A and HALF of
+  // the B rows, so a pipeline stage is 32 KB instead of 48 KB per SM (a third less L2 -> SM traffic per flop).
+  static constexpr uint32_t B_ROWS = CTA2 ? BLOCK_N / 2 : BLOCK_N;
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
-  static constexpr uint32_t B_BYTES = BLOCK_N * BLOCK_K * 2;        // 16/32 KB
+  static constexpr uint32_t B_BYTES = B_ROWS * BLOCK_K * 2;         // 16/32 KB
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr uint32_t EPI_BYTES = 8 * 4096;                   // 8 epilogue warps x (32 rows x 128 B)
-  static constexpr uint32_t kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr uint32_t kStages = (BLOCK_N == 256 && !CTA2) ? 4 : 6;
   static constexpr uint32_t BAR_BYTES = 256;
   static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +align slack
   static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;                // 256 / 512
@@ -97,12 +100,13 @@ QN_DEVICE void tile_coords(uint32_t tile, uint32_t tiles_m, uint32_t tiles_n, ui
   n_blk = in_group / gsize;
 }
 
-template <uint32_t BLOCK_N, bool A_MN, bool B_MN, int FUSE>
+template <uint32_t BLOCK_N, bool A_MN, bool B_MN, int FUSE, bool CTA2 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_z,
                  const __grid_constant__ CUtensorMap tmap_x, const GemmParams p, const TpComm tc) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, CTA2>;
+  static_assert(!CTA2 || FUSE == FUSE_NONE, "CTA pairs: plain GEMM only");
   constexpr uint32_t kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -124,7 +128,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   // rows arrive in order and the consumers' remote tiles become ready progressively; no per-thread fences or
   // register staging, and the compute CTAs' TMA / MMA pipelines do not share an SM with NVLink-bound stores.
   const uint32_t n_comm = (FUSE == FUSE_AG) ? tc.comm_ctas : 0u;
-  const uint32_t n_cta = gridDim.x - n_comm;
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;               // 0 = leader of the CTA pair
+  const uint32_t n_cta = CTA2 ? gridDim.x / 2 : gridDim.x - n_comm;      // persistent workers (CTAs or CTA pairs)
+  const uint32_t worker = CTA2 ? blockIdx.x / 2 : blockIdx.x;
+  constexpr uint32_t TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
   if constexpr (FUSE == FUSE_AG) {
     if (blockIdx.x >= n_cta) {
       // two pump threads per CTA (lane 0 of warps 0 and 1), each with its own ring
@@ -179,7 +186,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       return;
     }
   }
-  const uint32_t tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const uint32_t tiles_m = (p.M + TILE_M - 1) / TILE_M;
   const uint32_t tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const uint32_t num_tiles = tiles_m * tiles_n;
   const uint32_t num_kb_total = (p.K + BLOCK_K - 1) / BLOCK_K;
@@ -203,14 +210,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (uint32_t i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], CTA2 ? 16 : 8);        // CTA pair: the epilogue warps of BOTH CTAs release the leader
     }
     for (uint32_t i = 0; i < 8; ++i) mbar_init(&aux_bar[i], 1);
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<C::TMEM_COLS>(tmem_ptr);
+  if (warp == 2) {
+    if constexpr (CTA2) tmem_alloc_2cta<C::TMEM_COLS>(tmem_ptr); else tmem_alloc<C::TMEM_COLS>(tmem_ptr);
+  }
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // barriers of both CTAs are live before any remote arrive
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -218,13 +227,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // ------------------------------------------------------------ TMA producer
     {
       uint32_t stage = 0, phase = 0;
-      for (uint32_t work = blockIdx.x; work < num_work; work += n_cta) {
+      for (uint32_t work = worker; work < num_work; work += n_cta) {
         const uint32_t tile = work / splits, split = work - tile * splits;
         const uint32_t kb_begin = split * kb_per_split, kb_end = min(num_kb_total, kb_begin + kb_per_split);
         uint32_t m_blk, n_blk;
         tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
         m_blk = (m_blk + m_shift) % tiles_m;
-        const int32_t m0 = m_blk * BLOCK_M, n0 = n_blk * BLOCK_N;
+        // CTA pair: this CTA stages rows [rank*128, +128) of the 256-row A tile and B rows [rank*B_ROWS, +B_ROWS)
+        const int32_t m0 = m_blk * TILE_M + cta_rank * BLOCK_M, n0 = n_blk * BLOCK_N + cta_rank * (CTA2 ? C::B_ROWS : 0u);
         bool a_remote = false;
         if constexpr (FUSE == FUSE_AG) {
           a_remote = (m_blk / tc.mb_per_rank) != static_cast<uint32_t>(tc.rank);
@@ -239,8 +249,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           const int32_t k0 = kb * BLOCK_K;
+          if constexpr (CTA2) {
+            // both CTAs load into their own smem; all bytes are counted on the LEADER's full barrier, which the
+            // leader arms for the pair (the MMA issuer is the only consumer of it)
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
+            if constexpr (!A_MN) {
+              tma_load_2d_2cta(sa, &tmap_a, &full_bar[stage], k0, m0);
+            } else {
+#pragma unroll
+              for (uint32_t j = 0; j < BLOCK_M / 64; ++j)
+                tma_load_2d_2cta(sa + j * (BLOCK_K * 128), &tmap_a, &full_bar[stage], m0 + 64 * j, k0);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d_2cta(sb, &tmap_b, &full_bar[stage], k0, n0);         // box {64 K, B_ROWS}
+            } else {
+#pragma unroll
+              for (uint32_t j = 0; j < C::B_ROWS / 64; ++j)
+                tma_load_2d_2cta(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + 64 * j, k0);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           if constexpr (FUSE == FUSE_AG) {
             if (a_remote) tma_load_2d(sa, &tmap_x, &full_bar[stage], k0, m0);
             else tma_load_2d(sa, &tmap_a, &full_bar[stage], k0, m0 - tc.rank * static_cast<int32_t>(tc.rows_per_rank));
@@ -264,15 +295,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(BLOCK_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+    if (lane == 0 && cta_rank == 0) {                 // CTA pair: only the leader issues (for both SMs)
+      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
       // K-major: 8-row groups are 1024 B apart, one atom along K.  MN-major: 8-K-row groups 1024 B apart,
       // 64-wide MN atoms BLOCK_K*128 B apart.
       constexpr uint32_t A_LBO = A_MN ? BLOCK_K * 128 : 0, B_LBO = B_MN ? BLOCK_K * 128 : 0;
       constexpr uint32_t A_KSTEP = A_MN ? UMMA_K * 128 : UMMA_K * 2;
       constexpr uint32_t B_KSTEP = B_MN ? UMMA_K * 128 : UMMA_K * 2;
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
-      for (uint32_t work = blockIdx.x; work < num_work; work += n_cta) {
+      for (uint32_t work = worker; work < num_work; work += n_cta) {
         const uint32_t split = work % splits;
         const uint32_t kb_begin = split * kb_per_split, kb_end = min(num_kb_total, kb_begin + kb_per_split);
         mbar_wait(&tmem_empty[as], aphase ^ 1);
@@ -287,13 +318,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (uint32_t k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(sa + k * A_KSTEP, 1024, A_LBO);
             const uint64_t bdesc = make_smem_desc_sw128(sb + k * B_KSTEP, 1024, B_LBO);
-            if (p.fp8) umma_f8_ss(tmem_d, adesc, bdesc, make_idesc_e4m3(BLOCK_M, BLOCK_N), ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            if constexpr (CTA2) umma_bf16_ss_2cta(tmem_d, adesc, bdesc, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            else if (p.fp8) umma_f8_ss(tmem_d, adesc, bdesc, make_idesc_e4m3(BLOCK_M, BLOCK_N), ((kb - kb_begin) | k) != 0 ? 1u : 0u);
             else umma_bf16_ss(tmem_d, adesc, bdesc, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty_bar[stage]);            // frees the smem slot when these MMAs retire
+          // frees the smem slot when these MMAs retire (CTA pair: in both CTAs, each has its own producer)
+          if constexpr (CTA2) umma_commit_2cta(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[as]);                 // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (CTA pair: the epilogues of both CTAs)
+        if constexpr (CTA2) umma_commit_2cta(&tmem_full[as]); else umma_commit(&tmem_full[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -348,12 +382,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       npend = 0;
     };
-    for (uint32_t work = blockIdx.x; work < num_work; work += n_cta) {
+    for (uint32_t work = worker; work < num_work; work += n_cta) {
       const uint32_t tile = work / splits;
       uint32_t m_blk, n_blk;
       tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
       m_blk = (m_blk + m_shift) % tiles_m;
-      const uint32_t m0 = m_blk * BLOCK_M + q * 32, n0 = n_blk * BLOCK_N;
+      const uint32_t m0 = m_blk * TILE_M + cta_rank * BLOCK_M + q * 32, n0 = n_blk * BLOCK_N;
       mbar_wait(&tmem_full[as], aphase);
       tcgen05_fence_after();
 #pragma unroll 1
@@ -571,7 +605,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       // all TMEM reads of this accumulator stage are done -> hand it back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[as]);
+      if (lane == 0) {
+        if constexpr (CTA2) mbar_arrive_leader(&tmem_empty[as]); else mbar_arrive(&tmem_empty[as]);
+      }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if constexpr (FUSE == FUSE_RS) flush_pending();
@@ -579,10 +615,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // the peer may still read this CTA's smem / signal its barriers
   if (warp == 2) {
     tcgen05_fence_after();
-    tmem_dealloc<C::TMEM_COLS>(tmem_base);
+    if constexpr (CTA2) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base); else tmem_dealloc<C::TMEM_COLS>(tmem_base);
   }
 }
 
@@ -627,6 +663,56 @@ static int make_tmap(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t co
 }
 
 static int g_num_sms = 0;
+constexpr int kDefault2Cta = 1;           // QN_GEMM_2CTA overrides: 0 off, 1 auto, 2 every BLOCK_N = 256 launch
+
+// CTA pairs or single CTAs?  A pair finishes a 256 x 256 tile ~1.25x faster than two CTAs finish two 128 x 256
+// tiles (a third less L2 -> SM traffic), so pairs win unless wave quantisation on 74 pairs is much worse than on
+// 148 CTAs.
+static bool use_cta_pairs(int M, int N, int block_n, int splits, int max_ctas) {
+  static const int mode = [] { const char* e = getenv("QN_GEMM_2CTA"); return e ? atoi(e) : kDefault2Cta; }();
+  if (!mode || block_n != 256 || max_ctas != 0) return false;
+  if (mode >= 2) return true;
+  if (M < 256 || N < 256) return false;
+  const long long w2 = static_cast<long long>((M + 255) / 256) * ((N + 255) / 256) * splits;
+  const long long w1 = static_cast<long long>((M + 127) / 128) * ((N + 255) / 256) * splits;
+  const double eff2 = static_cast<double>(w2) / (74.0 * ((w2 + 73) / 74));
+  const double eff1 = static_cast<double>(w1) / (148.0 * ((w1 + 147) / 148));
+  return eff2 * 1.2 >= eff1;
+}
+
+// CTA-pair (cta_group::2) launch: clusters of 2 CTAs, one 256 x 256 tile per cluster and step
+template <bool A_MN, bool B_MN>
+static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tz,
+                       const GemmParams& p, cudaStream_t stream) {
+  using C = Cfg<256, true>;
+  auto kern = gemm_bf16_kernel<256, A_MN, B_MN, FUSE_NONE, true>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    configured = true;
+  }
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  const uint32_t tiles = ((p.M + 255) / 256) * ((p.N + 255) / 256) * (p.splits > 1 ? p.splits : 1);
+  const uint32_t pairs = static_cast<uint32_t>(g_num_sms / 2);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs), 1, 1);
+  cfg.blockDim = dim3(kNumThreads, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  TpComm c0{};
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tz, tc, p, c0);
+  return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
+}
 
 template <uint32_t BLOCK_N, bool A_MN, bool B_MN, int FUSE = FUSE_NONE>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tz,
@@ -689,9 +775,10 @@ extern "C" int qn_gemm_bf16(const void* a, const void* b, void* c, int M, int N,
 
   CUtensorMap ta, tb, tc, tz;
   int rc;
+  const bool two_cta = use_cta_pairs(M, N, block_n, 1, max_ctas);
   if (!a_mn) rc = make_tmap(&ta, a, M, K, lda, 64, BLOCK_M); else rc = make_tmap(&ta, a, K, M, lda, 64, BLOCK_K);
   if (rc) return rc;
-  if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
+  if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, two_cta ? 128 : block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
   if (rc) return rc;
   rc = make_tmap(&tc, c, M, N, ldc, 64, 32);
   if (rc) return rc;
@@ -709,6 +796,12 @@ extern "C" int qn_gemm_bf16(const void* a, const void* b, void* c, int M, int N,
     if (a_mn && !b_mn) return launch<BN, true, false>(ta, tb, tc, tz, p, max_ctas, stream);               \
     return launch<BN, true, true>(ta, tb, tc, tz, p, max_ctas, stream);                                   \
   } while (0)
+  if (two_cta) {
+    if (!a_mn && !b_mn) return launch_2cta<false, false>(ta, tb, tc, tz, p, stream);
+    if (!a_mn && b_mn) return launch_2cta<false, true>(ta, tb, tc, tz, p, stream);
+    if (a_mn && !b_mn) return launch_2cta<true, false>(ta, tb, tc, tz, p, stream);
+    return launch_2cta<true, true>(ta, tb, tc, tz, p, stream);
+  }
   if (block_n == 256) QN_DISPATCH(256);
   QN_DISPATCH(128);
 #undef QN_DISPATCH
@@ -754,7 +847,8 @@ extern "C" int qn_gemm_bf16_splitk(const void* a, const void* b, void* c, float*
   int rc;
   if (!a_mn) rc = make_tmap(&ta, a, M, K, lda, 64, BLOCK_M); else rc = make_tmap(&ta, a, K, M, lda, 64, BLOCK_K);
   if (rc) return rc;
-  if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
+  const bool two_cta = use_cta_pairs(M, N, block_n, splits, 0);
+  if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, two_cta ? 128 : block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
   if (rc) return rc;
   if ((rc = make_tmap(&tcm, c, M, N, ldc, 64, 32))) return rc;
 #define QN_DISPATCH_SK(BN)                                                                               \
@@ -764,7 +858,12 @@ extern "C" int qn_gemm_bf16_splitk(const void* a, const void* b, void* c, float*
     else if (a_mn && !b_mn) rc = launch<BN, true, false>(ta, tb, tcm, tcm, p, 0, stream);                 \
     else rc = launch<BN, true, true>(ta, tb, tcm, tcm, p, 0, stream);                                     \
   } while (0)
-  if (block_n == 256) QN_DISPATCH_SK(256); else QN_DISPATCH_SK(128);
+  if (two_cta) {
+    if (!a_mn && !b_mn) rc = launch_2cta<false, false>(ta, tb, tcm, tcm, p, stream);
+    else if (!a_mn && b_mn) rc = launch_2cta<false, true>(ta, tb, tcm, tcm, p, stream);
+    else if (a_mn && !b_mn) rc = launch_2cta<true, false>(ta, tb, tcm, tcm, p, stream);
+    else rc = launch_2cta<true, true>(ta, tb, tcm, tcm, p, stream);
+  } else if (block_n == 256) QN_DISPATCH_SK(256); else QN_DISPATCH_SK(128);
 #undef QN_DISPATCH_SK
   if (rc) return rc;
   if (splits > 1) {
