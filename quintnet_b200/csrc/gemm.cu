@@ -106,7 +106,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_z,
                  const __grid_constant__ CUtensorMap tmap_x, const GemmParams p, const TpComm tc) {
   using C = Cfg<BLOCK_N, CTA2>;
-  static_assert(!CTA2 || FUSE == FUSE_NONE, "CTA pairs: plain GEMM only");
   constexpr uint32_t kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -133,7 +132,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t worker = CTA2 ? blockIdx.x / 2 : blockIdx.x;
   constexpr uint32_t TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
   if constexpr (FUSE == FUSE_AG) {
-    if (blockIdx.x >= n_cta) {
+    if (n_comm > 0 && blockIdx.x >= n_cta) {            // (n_cta counts CTA PAIRS when CTA2: never take this path then)
       // two pump threads per CTA (lane 0 of warps 0 and 1), each with its own ring
       constexpr uint32_t kPumps = 2, kRing = 6, kAhead = 3, kLag = 12;
       __shared__ uint64_t comm_full[kPumps][kRing];
@@ -194,8 +193,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t kb_per_split = (num_kb_total + splits - 1) / splits;
   const uint32_t num_work = num_tiles * splits;
   // tile order: AG walks this rank's own row blocks first, RS walks them last
-  const uint32_t m_shift = FUSE == FUSE_AG ? tc.rank * tc.mb_per_rank
-                         : FUSE == FUSE_RS ? ((tc.rank + 1) % tc.world) * tc.mb_per_rank : 0u;
+  constexpr uint32_t kMbPerTile = CTA2 ? 2 : 1;       // 128-row blocks per tile row (tc.mb_per_rank counts 128-row blocks)
+  const uint32_t m_shift = FUSE == FUSE_AG ? tc.rank * (tc.mb_per_rank / kMbPerTile)
+                         : FUSE == FUSE_RS ? ((tc.rank + 1) % tc.world) * (tc.mb_per_rank / kMbPerTile) : 0u;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmap_a);
@@ -237,9 +237,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const int32_t m0 = m_blk * TILE_M + cta_rank * BLOCK_M, n0 = n_blk * BLOCK_N + cta_rank * (CTA2 ? C::B_ROWS : 0u);
         bool a_remote = false;
         if constexpr (FUSE == FUSE_AG) {
-          a_remote = (m_blk / tc.mb_per_rank) != static_cast<uint32_t>(tc.rank);
+          const uint32_t mb128 = m_blk * kMbPerTile + cta_rank;          // this CTA's 128-row block of A
+          a_remote = (mb128 / tc.mb_per_rank) != static_cast<uint32_t>(tc.rank);
           if (a_remote && !(tc.debug & 4u)) {   // the peer's pushes of these 128 rows must have landed
-            if (lane < 16) wait_flag_ge(tc.ag_flags[tc.rank] + m_blk * 16 + lane, tc.seq);  // 16 8-row units in parallel
+            if (lane < 16) wait_flag_ge(tc.ag_flags[tc.rank] + mb128 * 16 + lane, tc.seq);  // 16 8-row units in parallel
             __syncwarp();
             fence_proxy_async_all();      // generic-proxy (NVLink) writes -> async-proxy (TMA) reads
           }
@@ -254,7 +255,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             // both CTAs load into their own smem; all bytes are counted on the LEADER's full barrier, which the
             // leader arms for the pair (the MMA issuer is the only consumer of it)
             if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);
-            if constexpr (!A_MN) {
+            if constexpr (FUSE == FUSE_AG) {
+              if (a_remote) tma_load_2d_2cta(sa, &tmap_x, &full_bar[stage], k0, m0);
+              else tma_load_2d_2cta(sa, &tmap_a, &full_bar[stage], k0, m0 - tc.rank * static_cast<int32_t>(tc.rows_per_rank));
+            } else if constexpr (!A_MN) {
               tma_load_2d_2cta(sa, &tmap_a, &full_bar[stage], k0, m0);
             } else {
 #pragma unroll
@@ -422,10 +426,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           continue;
         }
         if constexpr (FUSE == FUSE_RS) {
-          const uint32_t owner = m_blk / tc.mb_per_rank;
+          const uint32_t mb128 = m_blk * kMbPerTile + cta_rank;
+          const uint32_t owner = mb128 / tc.mb_per_rank;
           const uint32_t m_loc = m0 - owner * tc.rows_per_rank;          // first row of this warp's slab in the owner's shard
           const uint32_t n_chunks = (p.N + 63) / 64;
-          const uint32_t fidx = (((m_blk % tc.mb_per_rank) * 4 + q) * n_chunks + (nc >> 6)) * tc.world;
+          const uint32_t fidx = (((mb128 % tc.mb_per_rank) * 4 + q) * n_chunks + (nc >> 6)) * tc.world;
           uint32_t acc[64];
           tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
           tmem_ld_32x32b_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
@@ -681,11 +686,12 @@ static bool use_cta_pairs(int M, int N, int block_n, int splits, int max_ctas) {
 }
 
 // CTA-pair (cta_group::2) launch: clusters of 2 CTAs, one 256 x 256 tile per cluster and step
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int FUSE = FUSE_NONE>
 static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tz,
-                       const GemmParams& p, cudaStream_t stream) {
+                       const GemmParams& p, cudaStream_t stream, const CUtensorMap* tx = nullptr,
+                       const TpComm* comm = nullptr) {
   using C = Cfg<256, true>;
-  auto kern = gemm_bf16_kernel<256, A_MN, B_MN, FUSE_NONE, true>;
+  auto kern = gemm_bf16_kernel<256, A_MN, B_MN, FUSE, true>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -710,7 +716,8 @@ static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   TpComm c0{};
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tz, tc, p, c0);
+  if (FUSE != FUSE_NONE && comm == nullptr) return 914;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tz, tx ? *tx : tc, p, comm ? *comm : c0);
   return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
 }
 
@@ -878,6 +885,12 @@ extern "C" int qn_gemm_bf16_splitk(const void* a, const void* b, void* c, float*
 // ------------------------------------------------------------------------------- fused TP entry points
 namespace qn {
 constexpr uint32_t kDefaultCommCtas = 0;
+// CTA pairs inside the fused AG / RS kernels: implemented but NOT yet validated on hardware (the first attempt
+// hung on a since-fixed early-return bug and exhausted the round's GPU budget) -> opt-in only, QN_TP_2CTA=1.
+static bool tp_cta_pairs() {
+  static const bool on = [] { const char* e = getenv("QN_TP_2CTA"); return e && atoi(e) != 0; }();
+  return on;
+}
 static int fill_comm(TpComm& c, int rank, int world, unsigned seq, int M) {
   if (world < 2 || world > TP_MAX || M % (128 * world)) return 915;
   c.rank = rank; c.world = world; c.seq = seq;
@@ -920,10 +933,16 @@ extern "C" int qn_gemm_ag_bf16(const void* x_local, void* const* gather, void* c
   int rc;
   if ((rc = make_tmap(&ta, x_local, comm.rows_per_rank, K, K, 64, BLOCK_M))) return rc;
   if ((rc = make_tmap(&tx, gather[rank], M, K, K, 64, BLOCK_M))) return rc;
-  if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
+  const bool two_cta = tp_cta_pairs() && comm.comm_ctas == 0 && (comm.rows_per_rank % 256) == 0 &&
+                       use_cta_pairs(M, N, block_n, 1, max_ctas);
+  if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, two_cta ? 128 : block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
   if (rc) return rc;
   if ((rc = make_tmap(&tcm, c, M, N, ldc, 64, 32))) return rc;
   if (p.has_z || epilogue == EPI_MUL_AUX) { if ((rc = make_tmap(&tz, z, M, N, ldz, 64, 32))) return rc; } else tz = tcm;
+  if (two_cta) {
+    if (!b_mn) return launch_2cta<false, false, FUSE_AG>(ta, tb, tcm, tz, p, stream, &tx, &comm);
+    return launch_2cta<false, true, FUSE_AG>(ta, tb, tcm, tz, p, stream, &tx, &comm);
+  }
   if (block_n == 256) {
     if (!b_mn) return launch<256, false, false, FUSE_AG>(ta, tb, tcm, tz, p, max_ctas, stream, &tx, &comm);
     return launch<256, false, true, FUSE_AG>(ta, tb, tcm, tz, p, max_ctas, stream, &tx, &comm);
@@ -955,10 +974,15 @@ extern "C" int qn_gemm_rs_bf16(const void* a, const void* b, void* c_local, void
   CUtensorMap ta, tb, tcm, tx;
   int rc;
   if ((rc = make_tmap(&ta, a, M, K, lda, 64, BLOCK_M))) return rc;
-  if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
+  const bool two_cta = tp_cta_pairs() && (comm.rows_per_rank % 256) == 0 && use_cta_pairs(M, N, block_n, 1, max_ctas);
+  if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, two_cta ? 128 : block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
   if (rc) return rc;
   if ((rc = make_tmap(&tcm, c_local, comm.rows_per_rank, N, ldc, 64, 32))) return rc;
   if ((rc = make_tmap(&tx, stage[rank], static_cast<uint64_t>(world) * comm.rows_per_rank, N, N, 64, 32))) return rc;
+  if (two_cta) {
+    if (!b_mn) return launch_2cta<false, false, FUSE_RS>(ta, tb, tcm, tcm, p, stream, &tx, &comm);
+    return launch_2cta<false, true, FUSE_RS>(ta, tb, tcm, tcm, p, stream, &tx, &comm);
+  }
   if (block_n == 256) {
     if (!b_mn) return launch<256, false, false, FUSE_RS>(ta, tb, tcm, tcm, p, max_ctas, stream, &tx, &comm);
     return launch<256, false, true, FUSE_RS>(ta, tb, tcm, tcm, p, max_ctas, stream, &tx, &comm);

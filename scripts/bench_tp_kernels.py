@@ -79,12 +79,11 @@ for name, kind, N, K, b_mn, epi in CASES:
     e1.record(); torch.cuda.synchronize()
     if rank == 0:
         print(f"{name} plain GEMM (no comm, no epilogue) back-to-back {e0.elapsed_time(e1) * 1e3 / 12:6.1f} us  dbg=-", flush=True)
-for comm in (0, 12, 16, 20):
+for comm in (0,):
     os.environ["QN_TP_COMM_CTAS"] = str(comm)
     for dbg in (0,):
         os.environ["QN_TP_DEBUG"] = str(dbg)
         for name, kind, N, K, b_mn, epi in CASES:
-            if kind == "rs" and (dbg != 0 or comm != 0): continue
             t, tb = run_case(kind, N, K, b_mn, epi)
             out[f"{name} comm={comm} dbg={dbg}"] = {"us_isolated": round(t, 1), "us_back_to_back": round(tb, 1)}
             if rank == 0:
