@@ -1,7 +1,11 @@
 """autograd wrappers around the hand-written sm_100a kernels (ctypes → C ABI).
 
 Every function here has a plain-PyTorch twin in :mod:`.reference`; the GPU
-tests compare the two (fp32 oracle).  Layout conventions follow the kernels:
+tests compare the two (fp32 oracle).  What each op replaces in the reference (SURVEY §2.9 ids): ``linear`` / ``mlp``
+= the ``nn.Linear`` inside Column/RowParallelLinear (G1-G4: ``parallelism/tensor_parallel/layers.py:119,211``,
+``utils/GPT2/gpt2_mlp.py:143-155``); ``attention_qkvpacked`` = ``F.scaled_dot_product_attention`` (G6,
+``utils/GPT2/gpt2_attention.py:156-161``); ``layer_norm`` family = ``nn.LayerNorm`` (G7, ``gpt2_block.py:175,184``);
+``linear_cross_entropy`` = lm_head matmul + ``CrossEntropyLoss`` (G5 + G9, ``gpt2_stage.py:108``, ``schedule.py:325-328``).  Layout conventions follow the kernels:
 row-major contiguous bf16, leading dimensions multiples of 8 elements.
 """
 from __future__ import annotations

@@ -7,6 +7,8 @@ address space (and, when the fabric supports NVLS, a multicast address that
 fans out to / reduces over all copies inside the NVSwitch).  The sm_100a
 kernels take the raw peer pointers and do the communication themselves with
 ordinary ``ld``/``st`` (or ``multimem.*``) — no NCCL call on the data path.
+(The reference has no counterpart: all of its collectives are ``torch.distributed`` NCCL calls on the default
+stream — ``core/communication.py:416-424,515,576``, ``parallelism/data_parallel/backends/torch_backend.py:59,71``.)
 
 Rendezvous back-ends, tried in order:
   1. ``torch.distributed._symmetric_memory`` (CUDA VMM + fabric/fd handles;

@@ -8,6 +8,10 @@ activations itself: pushes of the local shard into the peers' gather buffers, or
 tiles into the owner's staging buffer, synchronised by release/acquire flags — no NCCL call.  The backward of
 one op is the other op (plus local wgrad GEMMs), so a Megatron sequence-parallel block issues exactly four
 fused GEMM+collective launches per direction.
+
+Reference call sites these replace: ``ColumnParallelLinear.forward`` (``parallelism/tensor_parallel/layers.py:101-131``,
+GEMM then optional ``All_Gather``) and ``RowParallelLinear.forward`` (``layers.py:198-221``, GEMM then
+``All_Reduce`` — collective C3 of SURVEY §2.9, ``core/communication.py:515``).
 """
 from __future__ import annotations
 

@@ -1,5 +1,8 @@
 """``FusedAdamW`` — AdamW over flat parameter/gradient buffers.
 
+(The reference uses ``optim.Adam`` for ViT, ``trainer.py:89``, and ``optim.AdamW(weight_decay=0.01)`` for GPT-2,
+``GPT2_Trainer.py:100-104``; its ``optimizers/`` package is docstring-only stubs, ``optimizers/__init__.py:1-12``.)
+
 On B200 the whole update of a bucket is ONE launch of the hand-written sm_100a
 kernel (K8, ``csrc/adamw.cu``): fp32 master/m/v, bf16 (or fp32) parameters,
 optional gradient scale read from a device scalar (the clip coefficient, so no

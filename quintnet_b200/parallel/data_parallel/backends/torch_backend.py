@@ -1,4 +1,9 @@
-"""torch.distributed backend (NCCL on CUDA, gloo on CPU) with async bucket ops."""
+"""torch.distributed backend (NCCL on CUDA, gloo on CPU) with async bucket ops.
+
+Reference: ``parallelism/data_parallel/backends/torch_backend.py:31-85`` (synchronous ``broadcast_tensor`` :59 /
+``all_reduce_tensor`` :71 behind the ``DistributedBackend`` ABC of ``backends/base.py:30-91``).  Here the bucket
+reduction is asynchronous (``async_op=True`` handle, scale applied on completion) so it overlaps with backward;
+on B200 the hot path is :mod:`.nccl` (in-kernel NVLink all-reduce) and this class is the gloo / fallback path."""
 from __future__ import annotations
 
 import torch

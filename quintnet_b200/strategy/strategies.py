@@ -1,3 +1,7 @@
+"""The seven named strategies (reference ``strategy/data_parallel_strategy.py:4``, ``tensor_parallel_strategy.py:4``,
+``pipeline_parallel_strategy.py:4``, ``dp_tp_strategy.py:4``, ``dp_pp_strategy.py:4``, ``tp_pp_strategy.py:4``,
+``hybrid_3d_strategy.py:13-47``; lookup ``strategy/__init__.py:81-105``).  Each one only names its coordinator;
+the composition order TP -> PP -> DP lives in :mod:`quintnet_b200.coordinators`."""
 from __future__ import annotations
 
 from typing import Optional
