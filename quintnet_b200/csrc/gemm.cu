@@ -322,8 +322,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (uint32_t k = 0; k < BLOCK_K / UMMA_K; ++k) {
             const uint64_t adesc = make_smem_desc_sw128(sa + k * A_KSTEP, 1024, A_LBO);
             const uint64_t bdesc = make_smem_desc_sw128(sb + k * B_KSTEP, 1024, B_LBO);
-            if constexpr (CTA2) umma_bf16_ss_2cta(tmem_d, adesc, bdesc, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
-            else if (p.fp8) umma_f8_ss(tmem_d, adesc, bdesc, make_idesc_e4m3(BLOCK_M, BLOCK_N), ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            if constexpr (CTA2) {
+              if (p.fp8) umma_f8_ss_2cta(tmem_d, adesc, bdesc, make_idesc_e4m3(TILE_M, BLOCK_N), ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+              else umma_bf16_ss_2cta(tmem_d, adesc, bdesc, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            } else if (p.fp8) umma_f8_ss(tmem_d, adesc, bdesc, make_idesc_e4m3(BLOCK_M, BLOCK_N), ((kb - kb_begin) | k) != 0 ? 1u : 0u);
             else umma_bf16_ss(tmem_d, adesc, bdesc, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
           }
           // frees the smem slot when these MMAs retire (CTA pair: in both CTAs, each has its own producer)
@@ -1023,8 +1025,12 @@ extern "C" int qn_gemm_fp8(const void* a8, const void* b8, void* c, int M, int N
   if (epilogue != EPI_NONE && bias != nullptr && (N % 8)) return 912;
   CUtensorMap ta, tb, tc, tz;
   int rc;
+  // CTA pairs for fp8: same kernel path as bf16 pairs with kind::f8f6f4.cta_group::2 — opt-in (QN_FP8_2CTA=1) until
+  // it has been validated on hardware
+  static const bool fp8_pairs = [] { const char* e = getenv("QN_FP8_2CTA"); return e && atoi(e) != 0; }();
+  const bool two_cta = fp8_pairs && use_cta_pairs(M, N, block_n, 1, 0);
   if ((rc = make_tmap(&ta, a8, M, K / 2, lda / 2, 64, BLOCK_M))) return rc;
-  if ((rc = make_tmap(&tb, b8, N, K / 2, ldb / 2, 64, block_n))) return rc;
+  if ((rc = make_tmap(&tb, b8, N, K / 2, ldb / 2, 64, two_cta ? 128 : block_n))) return rc;
   if ((rc = make_tmap(&tc, c, M, N, ldc, 64, 32))) return rc;
   if (p.has_z) {
     if ((ldz % 8) || (reinterpret_cast<uintptr_t>(z) & 15)) return 913;
@@ -1032,6 +1038,7 @@ extern "C" int qn_gemm_fp8(const void* a8, const void* b8, void* c, int M, int N
   } else {
     tz = tc;
   }
+  if (two_cta) return launch_2cta<false, false>(ta, tb, tc, tz, p, stream);
   if (block_n == 256) return launch<256, false, false>(ta, tb, tc, tz, p, 0, stream);
   return launch<128, false, false>(ta, tb, tc, tz, p, 0, stream);
 }

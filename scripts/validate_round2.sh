@@ -1,0 +1,17 @@
+#!/bin/bash
+# Round-2 hardware validation of everything that was written but could not be run in round 1.
+# EVERY step carries its own short `timeout` (a hung cluster barrier has no device-side watchdog); run under
+#   gpurun --gpus 2 --timeout 420 -- 'bash scripts/validate_round2.sh'
+# and never with a gpurun limit close to the remaining budget.
+mkdir -p gpurun_out
+step() { name=$1; shift; echo "== $name"; timeout --signal=KILL "$@" 2>&1 | tail -6; echo "   rc=$?"; }
+# 1. fp8 on CTA pairs (1 GPU)
+QN_FP8_2CTA=1 step "fp8 CTA pairs" 90 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x --timeout 60 -k fp8
+QN_FP8_2CTA=1 step "fp8 bench" 90 python scripts/bench_fp8.py
+# 2. fused TP kernels on CTA pairs (2 GPUs)
+QN_TP_2CTA=1 step "tp fused tests, CTA pairs" 120 python -m pytest tests/test_comm_gpu.py -q -m gpu -x --timeout 90 -k "tp_fused or sequence_parallel"
+QN_TP_2CTA=1 step "tp kernel microbench, CTA pairs" 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29861 scripts/bench_tp_kernels.py
+# 3. tp2 end to end
+run() { port=$1; shift; timeout --signal=KILL 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $port bench.py --gpus 2 --steps 3 --warmup 3 --no-e2e "$@" 2>&1 | grep '^{"metric\|Error\|error\|Traceback' | tail -3 | cut -c1-330; }
+echo "== tp2 SP fused, single-CTA fused kernels"; run 29841 --mesh 1,2,1
+echo "== tp2 SP fused, CTA-pair fused kernels"; QN_TP_2CTA=1 run 29842 --mesh 1,2,1

@@ -161,3 +161,24 @@ def _vit_trainer(rank, world, strategy, mesh_dim, mesh_name):
     ("3d", [2, 2, 2], ["dp", "tp", "pp"], 8)])
 def test_vit_trainer_all_strategies(strategy, mesh_dim, mesh_name, world):
     run_distributed(_vit_trainer, world, strategy, mesh_dim, mesh_name, timeout=400)
+
+
+def test_bench_contract_cpu():
+    """bench.py prints ONE JSON line with the keys the driver reads (CPU plumbing mode, tiny model)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--cpu", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    rec = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "impl"):
+        assert key in rec, key
+    assert rec["n_gpus"] == 1 and rec["steps"] == 1 and rec["higher_is_better"] is True and rec["scaling"] == "strong"
+    assert {"model", "global_batch", "seq_len", "parallelism", "l2"} <= set(rec["config"])
+    assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(rec["e2e"])
+    assert rec["value"] > 0 and rec["e2e"]["h2d_bytes_per_step"] > 0
