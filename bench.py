@@ -55,6 +55,8 @@ def parse_args():
     ap.add_argument("--seq-len", type=int, default=512)
     ap.add_argument("--vocab", type=int, default=50257)
     ap.add_argument("--schedule", default="1f1b")
+    ap.add_argument("--virtual-stages", type=int, default=int(os.environ.get("QN_BENCH_VIRTUAL_STAGES", "1")),
+                    help="model chunks per pipeline rank (interleaved 1F1B) for our arm; 1 = plain 1F1B")
     ap.add_argument("--zero", type=int, default=None, help="ZeRO stage for our arm (default 1 when dp>1)")
     ap.add_argument("--sequence-parallel", type=int, default=None)
     ap.add_argument("--cpu", action="store_true", help="gloo/CPU plumbing run (tiny model)")
@@ -209,6 +211,8 @@ def build_config(args, mesh, impl):
         cfg.update({"dtype": "float32" if args.cpu else "bfloat16", "zero_stage": zero,
                     "sequence_parallel": bool(sp) and tp > 1, "seed": 0, "weight_decay": 0.01,
                     "bucket_cap_mb": 128, "pp_balance": "auto"})
+        if args.virtual_stages > 1 and pp > 1 and M % pp == 0:
+            cfg["virtual_pipeline_stages"] = args.virtual_stages
     return cfg, M
 
 
@@ -328,7 +332,8 @@ def run_ours(args):
     if rank == 0:
         extra = {"zero_stage": cfg["zero_stage"], "sequence_parallel": cfg["sequence_parallel"],
                  "native_ops": sorted(native._enabled_set()) if native.available() else [],
-                 "last_loss": last.get("loss", (None, None))[0]}
+                 "last_loss": last.get("loss", (None, None))[0],
+                 "virtual_pipeline_stages": cfg.get("virtual_pipeline_stages", 1)}
         emit(args, mesh, M, ms, e2e, clocks, launches, "ours", "fp32" if args.cpu else "bf16", extra)
     dist.barrier()
     dist.destroy_process_group()

@@ -61,22 +61,32 @@ class Hybrid3DCoordinator(BaseCoordinator):
         model_config = mc if isinstance(mc, GPT2Config) else GPT2Config.from_dict(dict(mc))
         if cfg.get("sequence_parallel") is not None:
             model_config.sequence_parallel = bool(cfg["sequence_parallel"])
+        pp = pg.axis_size("pp")
+        V = int(cfg.get("virtual_pipeline_stages", 1) or 1) if pp > 1 else 1
+        n_stages = pp * V                     # virtual stage v * pp + rank lives on this rank (interleaved 1F1B)
         bal = cfg.get("pp_balance")
-        if bal is not None and pg.axis_size("pp") > 1:
+        if bal is not None and pp > 1:
             from ..parallel.pipeline_parallel.utils import balanced_gpt2_split
-            model_config.pp_layer_counts = (balanced_gpt2_split(model_config.n_layer, pg.axis_size("pp"))
+            model_config.pp_layer_counts = (balanced_gpt2_split(model_config.n_layer, n_stages)
                                             if bal == "auto" else [int(c) for c in bal])
         ckpt = getattr(self, "checkpoint_path", None)
-        if ckpt in (None, "", "random"):
-            sd = random_gpt2_state_dict(model_config, pg, device=device, seed=int(cfg.get("seed", 0)),
-                                        dtype=dtype)
-        else:
-            sd = load_gpt2_distributed(ckpt, pg, cfg, device, model_config, dtype=dtype)
-        stage = GPT2Stage.from_sharded_state_dict(
-            sd, model_config, pg.axis_rank("pp"), pg.axis_size("pp"), pg.axis_rank("tp"),
-            pg.axis_size("tp"), pg.get_group("tp"), pg.get_group("pp"), device, dtype=dtype,
-            tied_group=make_tied_group(pg))
-        stage.seq_len = int(cfg.get("max_seq_length", model_config.n_positions))
-        del sd
+        tied = make_tied_group(pg)
+        chunks = []
+        for v in range(V):
+            sid = v * pp + pg.axis_rank("pp")
+            if ckpt in (None, "", "random"):
+                sd = random_gpt2_state_dict(model_config, pg, device=device, seed=int(cfg.get("seed", 0)),
+                                            dtype=dtype, pp_rank=sid, pp_size=n_stages)
+            else:
+                sd = load_gpt2_distributed(ckpt, pg, cfg, device, model_config, dtype=dtype, pp_rank=sid,
+                                           pp_size=n_stages)
+            stage = GPT2Stage.from_sharded_state_dict(
+                sd, model_config, sid, n_stages, pg.axis_rank("tp"), pg.axis_size("tp"), pg.get_group("tp"),
+                pg.get_group("pp"), device, dtype=dtype, tied_group=tied)
+            stage.seq_len = int(cfg.get("max_seq_length", model_config.n_positions))
+            del sd
+            chunks.append(stage)
         self.model_config = model_config
-        return compose(None, pg, cfg, use_tp=False, use_pp=True, use_dp=True, stage_module=stage)
+        if V > 1:
+            return compose(None, pg, cfg, use_tp=False, use_pp=True, use_dp=True, stage_chunks=chunks)
+        return compose(None, pg, cfg, use_tp=False, use_pp=True, use_dp=True, stage_module=chunks[0])

@@ -65,9 +65,15 @@ def make_tied_group(pg_manager):
 
 
 def compose(model: Optional[nn.Module], pg_manager, config: dict, *, use_tp: bool, use_pp: bool,
-            use_dp: bool, stage_module: Optional[nn.Module] = None) -> nn.Module:
+            use_dp: bool, stage_module: Optional[nn.Module] = None, stage_chunks=None) -> nn.Module:
+    """``stage_chunks``: the V model chunks of this rank for the interleaved (virtual-stage) pipeline."""
     device = resolve_device(pg_manager, config)
     dtype = resolve_dtype(config)
+    if stage_chunks is not None:
+        from ..parallel.pipeline_parallel.interleaved import VirtualPipelineWrapper
+        model = VirtualPipelineWrapper(stage_chunks, pg_manager.device_mesh, pg_manager.axis_rank("pp"),
+                                       pg_manager.get_group("pp"), pg_manager.axis_size("pp"), device)
+        return wrap_data_parallel(model, pg_manager, config) if use_dp else model
     if model is not None:
         model = model.to(device=device, dtype=dtype) if dtype != torch.float32 else model.to(device)
     if use_tp and model is not None and pg_manager.axis_size("tp") > 1:

@@ -100,10 +100,15 @@ def shard_hf_tensors(get, config, tp_rank: int, tp_size: int, pp_rank: int, pp_s
 
 
 def load_gpt2_distributed(checkpoint_path: str, pg_manager, config: Optional[dict] = None, device=None,
-                          model_config=None, dtype=None) -> Dict[str, torch.Tensor]:
+                          model_config=None, dtype=None, pp_rank: Optional[int] = None,
+                          pp_size: Optional[int] = None) -> Dict[str, torch.Tensor]:
+    """``pp_rank`` / ``pp_size`` override the mesh coordinates (virtual pipeline stages load stage
+    ``v * pp + rank`` of ``pp * V``)."""
     from safetensors import safe_open
     cfg = _cfg(model_config if model_config is not None else (config or {}).get("model_config"))
-    tp_rank, tp_size, pp_rank, pp_size = _coords(pg_manager)
+    tp_rank, tp_size, mesh_pp_rank, mesh_pp_size = _coords(pg_manager)
+    pp_rank = mesh_pp_rank if pp_rank is None else pp_rank
+    pp_size = mesh_pp_size if pp_size is None else pp_size
     device = device if device is not None else torch.device("cpu")
     with safe_open(checkpoint_path, framework="pt", device="cpu") as f:
         keys = set(f.keys())

@@ -50,7 +50,7 @@ class GPT2Trainer(_TrainerBase):
             model=self.model, device_mesh=pg_manager.device_mesh, pp_rank=self.pp_rank,
             pp_group=pg_manager.get_group("pp"), criterion=self.criterion, device=self.device,
             optimizer=self.optimizer, max_grad_norm=self.max_grad_norm,
-            schedule_type=config.get("schedule", "1f1b"), task_type="clm", vocab_size=self.vocab_size,
+            schedule_type=self._schedule_name(config), task_type="clm", vocab_size=self.vocab_size,
             loss_scale=config.get("loss_scale", "mean"), shift_labels=self.shift_labels,
             pg_manager=pg_manager, compute_dtype=self.dtype)
         self.micro_loader = PipelineDataLoader(self.train_loader, self.grad_acc_steps, task_type="clm")
@@ -58,6 +58,14 @@ class GPT2Trainer(_TrainerBase):
         self.tensor_shapes = self._shapes(mb)
         if config.get("resume_from"):
             self.resume(config["resume_from"])
+
+    @staticmethod
+    def _schedule_name(config: dict) -> str:
+        """``virtual_pipeline_stages > 1`` implies the interleaved schedule."""
+        name = config.get("schedule", "1f1b")
+        if int(config.get("virtual_pipeline_stages", 1) or 1) > 1 and name == "1f1b":
+            return "1f1b_interleaved"
+        return name
 
     def _shapes(self, batch: int):
         if hasattr(self.gpt2_stage, "get_tensor_shapes"):

@@ -46,8 +46,13 @@ class PipelineTrainer:
             self.schedule = AllFwdAllBwdSchedule(self)
         elif schedule_type == "1f1b":
             self.schedule = OneFOneBSchedule(self)
+        elif schedule_type == "1f1b_interleaved":
+            from .interleaved import InterleavedOneFOneBSchedule
+            self.schedule = InterleavedOneFOneBSchedule(self)
         else:
-            raise ValueError(f"unknown schedule_type {schedule_type!r} (use '1f1b' or 'afab')")
+            raise ValueError(f"unknown schedule_type {schedule_type!r} (use '1f1b', 'afab' or '1f1b_interleaved')")
+        if hasattr(stage, "chunks") and schedule_type != "1f1b_interleaved":
+            raise ValueError("virtual pipeline stages need schedule '1f1b_interleaved'")
         self.schedule_type = schedule_type
         self._warmup_p2p()
 
@@ -109,6 +114,17 @@ class PipelineTrainer:
         ``tensor_shapes`` describes ONE validation batch.
         """
         self.model.eval()
+        if self.schedule_type == "1f1b_interleaved":
+            key = "input_ids" if self.task_type == "clm" else "images"
+            batches = []
+            for batch in val_loader:
+                if isinstance(batch, (tuple, list)):
+                    batch = {"images": batch[0], "labels": batch[1]}
+                if "image" in batch:
+                    batch = {"images": batch["image"], "labels": batch["label"]}
+                if batch[key].shape[0] == tensor_shapes[0]:          # fixed-shape p2p buffers: skip a ragged tail
+                    batches.append(batch)
+            return self.schedule.evaluate(batches, tensor_shapes, device, dtype)
         loss_acc = torch.zeros((), device=device)
         count = torch.zeros((), device=device)
         correct = torch.zeros((), device=device)

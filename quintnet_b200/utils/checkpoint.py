@@ -18,12 +18,21 @@ import numpy as np
 import torch
 
 
-def _names(out_dir: str, filename: str, pg_manager):
+def _names(out_dir: str, filename: str, pg_manager, stage_id: Optional[int] = None):
+    """``stage_id`` overrides the pp index in the file name: with V virtual pipeline stages per rank every model
+    chunk is written as its own shard ``…_pp{v * pp + rank}_tp{t}`` of a (pp·V)-stage pipeline, which is exactly
+    the layout the merge tool already understands."""
     base, ext = os.path.splitext(filename)
     pp, tp, dp = pg_manager.axis_rank("pp"), pg_manager.axis_rank("tp"), pg_manager.axis_rank("dp")
+    pp = pp if stage_id is None else stage_id
     shard = os.path.join(out_dir, f"{base}_pp{pp}_tp{tp}{ext or '.pt'}")
     opt = os.path.join(out_dir, f"{base}_pp{pp}_tp{tp}_dp{dp}.opt{ext or '.pt'}")
     return shard, opt
+
+
+def _chunks_of(stage_module):
+    """[(stage id, pipeline size, module)] — one entry, or V entries for a rank that owns V virtual stages."""
+    return None if not hasattr(stage_module, "chunks") else list(stage_module.chunks)
 
 
 def rng_state():
@@ -42,12 +51,24 @@ def set_rng_state(st):
 
 
 def save_shard(out_dir: str, filename: str, stage_module, optimizer, config, pg_manager,
-               extra: Optional[dict] = None) -> str:
+               extra: Optional[dict] = None, _stage: Optional[tuple] = None) -> str:
+    chunks = _chunks_of(stage_module)
+    if chunks is not None:                      # virtual pipeline stages: one shard per chunk, optimizer with chunk 0
+        pp, r, V = pg_manager.axis_size("pp"), pg_manager.axis_rank("pp"), len(chunks)
+        first = None
+        for v, chunk in enumerate(chunks):
+            path = save_shard(out_dir, filename, chunk, optimizer if v == 0 else None, config, pg_manager, extra,
+                              _stage=(v * pp + r, pp * V, V))
+            first = first or path
+        return first
     os.makedirs(out_dir, exist_ok=True)
-    shard, opt_path = _names(out_dir, filename, pg_manager)
+    shard, opt_path = _names(out_dir, filename, pg_manager, None if _stage is None else _stage[0])
     sharded_opt = getattr(optimizer, "handles_grad_clipping", False) and hasattr(optimizer, "shards")
-    info = {"pp_rank": pg_manager.axis_rank("pp"), "tp_rank": pg_manager.axis_rank("tp"),
-            "pp_size": pg_manager.axis_size("pp"), "tp_size": pg_manager.axis_size("tp"),
+    info = {"pp_rank": pg_manager.axis_rank("pp") if _stage is None else _stage[0],
+            "tp_rank": pg_manager.axis_rank("tp"),
+            "pp_size": pg_manager.axis_size("pp") if _stage is None else _stage[1],
+            "virtual_pipeline_stages": 1 if _stage is None else _stage[2],
+            "tp_size": pg_manager.axis_size("tp"),
             "dp_size": pg_manager.axis_size("dp"), "zero_stage": 1 if sharded_opt else 0,
             "pp_layer_counts": getattr(getattr(stage_module, "config", None), "pp_layer_counts", None)}
     if pg_manager.axis_rank("dp") == 0:
@@ -66,12 +87,22 @@ def save_shard(out_dir: str, filename: str, stage_module, optimizer, config, pg_
 
 
 def load_shard(prefix_path: str, stage_module, optimizer, pg_manager, map_location="cpu",
-               strict: bool = True) -> dict:
+               strict: bool = True, _stage: Optional[tuple] = None) -> dict:
+    chunks = _chunks_of(stage_module)
+    if chunks is not None:
+        pp, r, V = pg_manager.axis_size("pp"), pg_manager.axis_rank("pp"), len(chunks)
+        meta = {}
+        for v, chunk in enumerate(chunks):
+            m = load_shard(prefix_path, chunk, optimizer if v == 0 else None, pg_manager, map_location, strict,
+                           _stage=(v * pp + r, pp * V, V))
+            meta = meta or m
+        return meta
     out_dir, filename = os.path.split(prefix_path)
-    shard, opt_path = _names(out_dir or ".", filename, pg_manager)
+    shard, opt_path = _names(out_dir or ".", filename, pg_manager, None if _stage is None else _stage[0])
     payload = torch.load(shard, map_location="cpu", weights_only=False)
     info = payload["parallelism_info"]
-    if info["pp_size"] != pg_manager.axis_size("pp") or info["tp_size"] != pg_manager.axis_size("tp"):
+    want_pp = pg_manager.axis_size("pp") if _stage is None else _stage[1]
+    if info["pp_size"] != want_pp or info["tp_size"] != pg_manager.axis_size("tp"):
         raise ValueError(f"checkpoint was written for pp={info['pp_size']} tp={info['tp_size']}")
     stage_module.load_state_dict(payload["model_state_dict"], strict=strict)
     if optimizer is not None:

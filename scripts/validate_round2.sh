@@ -15,3 +15,6 @@ QN_TP_2CTA=1 step "tp kernel microbench, CTA pairs" 120 python -m torch.distribu
 run() { port=$1; shift; timeout --signal=KILL 240 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port $port bench.py --gpus 2 --steps 3 --warmup 3 --no-e2e "$@" 2>&1 | grep '^{"metric\|Error\|error\|Traceback' | tail -3 | cut -c1-330; }
 echo "== tp2 SP fused, single-CTA fused kernels"; run 29841 --mesh 1,2,1
 echo "== tp2 SP fused, CTA-pair fused kernels"; QN_TP_2CTA=1 run 29842 --mesh 1,2,1
+# 4. interleaved 1F1B (virtual pipeline stages) vs plain 1F1B at pp2 (CPU-validated; needs its first NCCL run)
+echo "== pp2 plain 1F1B"; run 29843 --mesh 1,1,2
+echo "== pp2 interleaved V=2"; run 29844 --mesh 1,1,2 --virtual-stages 2

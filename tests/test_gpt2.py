@@ -1,6 +1,7 @@
 """GPT-2: schema, TP (plain + sequence-parallel) == single device, PP schedules ==
 single process (loss AND post-step parameters), 3-D 2x2x2 parity."""
 import copy
+import os
 
 import torch
 import torch.distributed as dist
@@ -221,3 +222,138 @@ def test_fp8_linear_option_cpu():
     (l8 / n8).backward()
     assert all(torch.isfinite(p.grad).all() for p in m8.parameters() if p.grad is not None)
     assert m8.blocks[0].mlp.c_fc.fp8 and m8.blocks[0].attn.c_proj.fp8
+
+
+def test_interleaved_table_is_consistent():
+    """Every unit runs exactly once, after its dependency, and every send has its receive in the same tick."""
+    from quintnet_b200.parallel.pipeline_parallel.interleaved import bubble_fraction, build_table
+    for pp, V, M in ((2, 2, 4), (2, 2, 8), (4, 2, 8), (2, 3, 6), (4, 3, 12)):
+        table = build_table(pp, V, M)
+        S = pp * V
+        ran = {}
+        for r in range(pp):
+            for t, tick in enumerate(table[r]):
+                if tick.unit:
+                    kind, v, m = tick.unit
+                    key = (kind, v * pp + r, m)
+                    assert key not in ran
+                    ran[key] = t
+        assert len(ran) == 2 * S * M
+        for (kind, s, m), t in ran.items():
+            if kind == "F" and s > 0:
+                assert ran[("F", s - 1, m)] < t
+            if kind == "B":
+                assert ran[("F", s, m)] < t and (s == S - 1 or ran[("B", s + 1, m)] < t)
+        for t in range(len(table[0])):
+            sends = sorted((r, peer, cons) for r in range(pp) for peer, cons in table[r][t].sends)
+            recvs = sorted((peer, r, cons) for r in range(pp) for peer, cons in table[r][t].recvs)
+            assert sends == recvs
+            for r in range(pp):           # NCCL matches by order within a pair: at most one tensor per direction per tick
+                peers = [p for p, _ in table[r][t].sends]
+                assert len(peers) == len(set(peers))
+        assert bubble_fraction(pp, V, M) < bubble_fraction(pp, 1, M) + 1e-9
+
+
+def _run_interleaved(rank, world, zero, sp, mesh_dim, mesh_name, out_dir, batch=8):
+    from quintnet_b200.utils.data import dict_collate
+    M, steps, V = 4, 3, 2
+    dp = mesh_dim[mesh_name.index("dp")] if "dp" in mesh_name else 1
+    data = SyntheticTokens(batch * steps, seq_len=16, vocab_size=96, seed=11, pad_id=0,
+                           min_fill=0.6 if dp == 1 else 1.0)
+    ref_losses, ref_model = _single_process_reference(steps, M, batch, data)
+    cfg = _train_cfg(mesh_dim, mesh_name, "1f1b", zero, sp, M, batch)
+    cfg["virtual_pipeline_stages"] = V
+    cfg["output_dir"] = out_dir
+    pg = init_process_groups("cpu", mesh_dim, mesh_name)
+    model = get_strategy("3d", pg, cfg, checkpoint_path=None, is_staged=True).apply(None)
+    mb = batch // (M * dp)
+    d = pg.axis_rank("dp")
+    order = []
+    for s in range(steps):
+        for m in range(M):
+            start = s * batch + (m * dp + d) * mb
+            order.extend(range(start, start + mb))
+    loader = torch.utils.data.DataLoader(torch.utils.data.Subset(data, order), batch_size=mb, shuffle=False,
+                                         collate_fn=dict_collate)
+    tr = GPT2Trainer(model, loader, None, cfg, pg, GPT2Config(**CFG))
+    assert tr.pipeline_trainer.schedule_type == "1f1b_interleaved"
+    got = []
+    for s in range(steps):
+        loss, ppl = tr.train_step()
+        if loss is not None:
+            got.append(loss)
+    if got:
+        t = torch.tensor(got)
+        if dp > 1:
+            dist.all_reduce(t, group=pg.get_group("dp"))
+            t /= dp
+        assert torch.allclose(t, torch.tensor(ref_losses), atol=2e-3), (t, ref_losses)
+    chunks = tr.gpt2_stage.chunks
+    pp, r = pg.axis_size("pp"), pg.axis_rank("pp")
+    assert len(chunks) == V
+    if r == pp - 1:
+        assert torch.allclose(chunks[-1].ln_f.weight.float(), ref_model.ln_f.weight, atol=3e-3)
+    if r == 0:
+        assert torch.allclose(chunks[0].embedding.wpe.weight.float(), ref_model.embedding.wpe.weight, atol=3e-3)
+        assert torch.allclose(chunks[0].embedding.wte.weight.float(), ref_model.embedding.wte.weight, atol=3e-3)
+    for v, chunk in enumerate(chunks):          # 4 layers over 4 virtual stages: chunk v of rank r is layer v*pp + r
+        lid = v * pp + r
+        assert torch.allclose(chunk.blocks[0].ln_2.bias.float(), ref_model.blocks[lid].ln_2.bias, atol=3e-3)
+        if pg.axis_size("tp") == 1:
+            assert torch.allclose(chunk.blocks[0].mlp.c_fc.proj.bias.float(),
+                                  ref_model.blocks[lid].mlp.c_fc.proj.bias.float(), atol=3e-3)
+    # checkpoint: one shard per virtual stage, mergeable like a 4-stage pipeline; resume restores bitwise
+    tr._save_checkpoint("vp.pt")
+    dist.barrier()
+    before = torch.cat([p.detach().float().flatten() for p in tr.gpt2_stage.parameters()])
+    with torch.no_grad():
+        for p in tr.gpt2_stage.parameters():
+            p.add_(1.0)
+    tr.resume(os.path.join(out_dir, "vp.pt"))
+    after = torch.cat([p.detach().float().flatten() for p in tr.gpt2_stage.parameters()])
+    assert torch.equal(before, after)
+    if dist.get_rank() == 0:
+        names = sorted(f for f in os.listdir(out_dir) if f.startswith("vp_pp") and f.endswith(".pt") and "opt" not in f)
+        assert len(names) == pp * V * pg.axis_size("tp"), names
+
+
+def test_pp2_interleaved_virtual_stages(tmp_path):
+    run_distributed(_run_interleaved, 2, 0, False, [2], ["pp"], str(tmp_path))
+    # the 2 ranks x 2 chunks wrote 4 stage shards: they merge like a 4-stage pipeline into the HF layout
+    from quintnet_b200.tools.merge_checkpoints import merge_checkpoints
+    steps, M, batch = 3, 4, 8
+    data = SyntheticTokens(batch * steps, seq_len=16, vocab_size=96, seed=11, pad_id=0, min_fill=0.6)
+    _, ref_model = _single_process_reference(steps, M, batch, data)
+    hf = merge_checkpoints(str(tmp_path), str(tmp_path / "merged.pt"), "vp")
+    for i in range(4):
+        w = hf[f"transformer.h.{i}.mlp.c_fc.weight"]                     # HF Conv1D layout [in, out]
+        assert torch.allclose(w.float(), ref_model.blocks[i].mlp.c_fc.proj.weight.t().float(), atol=3e-3), i
+    assert torch.allclose(hf["transformer.wte.weight"].float(), ref_model.embedding.wte.weight.float(), atol=3e-3)
+
+
+def _eval_interleaved(rank, world):
+    """Forward-only (validation) pass of the virtual-stage pipeline == the single-process loss."""
+    from quintnet_b200.utils.data import dict_collate
+    data = SyntheticTokens(16, seq_len=16, vocab_size=96, seed=5, pad_id=0, min_fill=0.6)
+    ref = GPT2Model(GPT2Config(**CFG), seed=1)
+    cfg = _train_cfg([2], ["pp"], "1f1b", 0, False, 4, 8)
+    cfg["virtual_pipeline_stages"] = 2
+    pg = init_process_groups("cpu", [2], ["pp"])
+    model = get_strategy("3d", pg, cfg, checkpoint_path=None, is_staged=True).apply(None)
+    loader = torch.utils.data.DataLoader(data, batch_size=4, shuffle=False, collate_fn=dict_collate)
+    tr = GPT2Trainer(model, loader, loader, cfg, pg, GPT2Config(**CFG))
+    loss, ppl = tr.pipeline_trainer.evaluate(loader, tr._shapes(4), tr.device, tr.dtype)
+    if pg.axis_rank("pp") == 1:
+        with torch.no_grad():
+            ls, n = ref(data.input_ids, labels=data.labels)
+        assert abs(loss - float(ls / n)) < 2e-3, (loss, float(ls / n))
+    else:
+        assert loss is None
+
+
+def test_pp2_interleaved_evaluate():
+    run_distributed(_eval_interleaved, 2)
+
+
+def test_3d_2x2x2_interleaved_zero1_sp(tmp_path):
+    run_distributed(_run_interleaved, 8, 1, True, [2, 2, 2], ["dp", "tp", "pp"], str(tmp_path), 16, timeout=600)
