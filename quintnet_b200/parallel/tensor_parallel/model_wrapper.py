@@ -77,6 +77,12 @@ def apply_tensor_parallel(model: nn.Module, tp_size: int, tp_rank: int, tp_group
                 rewrite(child, full)
 
     rewrite(model)
+    if method_of_parallelism == "paired":
+        # attention modules whose Q/K/V became column-parallel WITHOUT a gather compute local heads only and must
+        # gather their output once (models.vit.Attention does that when it knows the group)
+        for m in model.modules():
+            if isinstance(getattr(m, "Q", None), ColumnParallelLinear) and getattr(m, "tp_group", 0) is None:
+                m.tp_group = tp_group
     model.to(device)
     if dist.is_initialized():
         dist.barrier()

@@ -142,9 +142,6 @@ def _vit_trainer(rank, world, strategy, mesh_dim, mesh_name):
     vl = make_loader(SyntheticMNIST(64, seed=1), mb, pg, shuffle=False)
     torch.manual_seed(0)
     model = Model(hidden_dim=32, depth=4, n_heads=4)
-    if strategy in ("tp", "dp_tp", "tp_pp", "3d") and cfg["tp_method"] == "paired":
-        for blk in model.blocks:
-            blk.attention.tp_group = pg.get_group("tp")
     model = get_strategy(strategy, pg, cfg).apply(model)
     tr = Trainer(model, tl, vl, cfg, pg)
     l0, _ = tr._train_epoch(0)

@@ -105,9 +105,6 @@ def _apply_tp_vit(rank, world):
         ref = Model(hidden_dim=32, depth=2, n_heads=4)
         torch.manual_seed(3)
         tp = Model(hidden_dim=32, depth=2, n_heads=4)
-        if method == "paired":
-            for blk in tp.blocks:
-                blk.attention.tp_group = g
         tp = apply_tensor_parallel(tp, world, rank, g, torch.device("cpu"), method_of_parallelism=method)
         x = torch.randn(4, 1, 28, 28)
         yr = ref(x)

@@ -1,0 +1,140 @@
+"""Utilities, tools and examples: datasets + collator, metrics, logging, profiling,
+single-device checkpoint evaluation, and the shipped examples in CPU / gloo mode."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+class _WordTokenizer:
+    """Whitespace tokenizer with the slice of the HF tokenizer API the collator uses."""
+    eos_token, pad_token = "<eos>", None
+
+    def __init__(self):
+        self.vocab = {"<eos>": 0}
+
+    def _ids(self, text):
+        return [self.vocab.setdefault(w, len(self.vocab)) for w in text.replace("<eos>", " <eos>").split()]
+
+    def __call__(self, texts, max_length=None, truncation=False, padding=None, return_tensors=None):
+        single = isinstance(texts, str)
+        rows = [self._ids(t)[:max_length] for t in ([texts] if single else texts)]
+        if padding == "max_length":
+            mask = [[1] * len(r) + [0] * (max_length - len(r)) for r in rows]
+            rows = [r + [0] * (max_length - len(r)) for r in rows]
+        else:
+            mask = [[1] * len(r) for r in rows]
+        if return_tensors == "pt":
+            return {"input_ids": torch.tensor(rows), "attention_mask": torch.tensor(mask)}
+        return {"input_ids": rows[0] if single else rows, "attention_mask": mask[0] if single else mask}
+
+
+def test_summarization_dataset_and_collator(tmp_path):
+    from quintnet_b200.utils.data import SummarizationCollator, SummarizationDataset
+    (tmp_path / "train.csv").write_text("article,highlights\nthe cat sat on the mat,cat sat\na dog ran,dog\n")
+    ds = SummarizationDataset(str(tmp_path), "train")
+    assert len(ds) == 2 and ds[0] == {"article": "the cat sat on the mat", "highlights": "cat sat"}
+    tok = _WordTokenizer()
+    batch = SummarizationCollator(tok, max_length=16)([ds[0], ds[1]])
+    assert batch["input_ids"].shape == (2, 16) and tok.pad_token == tok.eos_token
+    assert (batch["labels"][batch["attention_mask"] == 0] == -100).all()        # padding is not supervised
+    assert (batch["labels"][batch["attention_mask"] == 1] >= 0).all()           # the whole text is (reference behaviour)
+    masked = SummarizationCollator(tok, max_length=16, mask_prompt=True)([ds[0]])
+    n_prompt = len(tok("the cat sat on the mat\n\nTL;DR: ")["input_ids"])
+    assert (masked["labels"][0, :n_prompt] == -100).all() and (masked["labels"][0, n_prompt:n_prompt + 2] >= 0).all()
+
+
+def test_metrics_rouge_bleu():
+    from quintnet_b200.utils.metrics import compute_rouge_bleu
+    same = compute_rouge_bleu(["the cat sat on the mat"], ["the cat sat on the mat"])
+    diff = compute_rouge_bleu(["a dog ran away quickly today"], ["the cat sat on the mat"])
+    for key in ("rouge1", "rouge2", "rougeL", "bleu"):
+        assert key in same and same[key] >= diff[key]
+    assert same["rouge1"] > 0.99 and diff["rouge1"] < 0.2
+
+
+def test_loggers(tmp_path, monkeypatch):
+    from quintnet_b200.utils.logger import StepLogger, log_rank_0, setup_logger, setup_rank_logging
+    sl = StepLogger(str(tmp_path / "steps.jsonl"), rank=0)
+    sl.log(step=1, loss=2.5, tokens_per_s=1e5)
+    sl.log(step=2, loss=2.4)
+    rows = [json.loads(l) for l in (tmp_path / "steps.jsonl").read_text().splitlines()]
+    assert [r["step"] for r in rows] == [1, 2] and "time" in rows[0]
+    assert StepLogger(str(tmp_path / "other.jsonl"), rank=1).f is None          # rank 0 only
+    monkeypatch.setenv("RANK", "3")
+    out, err = sys.stdout, sys.stderr
+    try:
+        path = setup_rank_logging(str(tmp_path / "logs"))
+        print("hello from rank 3")
+        sys.stdout.flush()
+    finally:
+        sys.stdout, sys.stderr = out, err
+    assert path.endswith("rank_3.log") and "hello from rank 3" in open(path).read()
+    log_rank_0("not printed on rank 3", setup_logger("t"))
+
+
+def test_profiling_and_memory():
+    from quintnet_b200.utils.memory import clear_cache, get_memory_usage
+    from quintnet_b200.utils.profiling import DeviceTimer, nvtx_range, profile_memory, profile_time
+    sink = {}
+    with profile_time("mm", sink), profile_memory("mm_mem", sink), nvtx_range("mm"):
+        torch.randn(64, 64) @ torch.randn(64, 64)
+    assert sink["mm"] > 0 and sink["mm_mem"] >= 0
+    t = DeviceTimer()
+    with t.phase("fwd"):
+        torch.randn(32, 32).sum()
+    with t.phase("fwd"):
+        torch.randn(32, 32).sum()
+    rep = t.summary()
+    assert rep["fwd"] >= 0 and t._counts["fwd"] == 2
+    assert isinstance(get_memory_usage(), dict)
+    clear_cache()
+
+
+def test_eval_checkpoint_tool(tmp_path, capsys):
+    """tools/eval_checkpoint (the reference's test.py role): loss / perplexity of an HF-layout checkpoint."""
+    from quintnet_b200.core.distributed_loading import save_random_hf_checkpoint
+    from quintnet_b200.models.gpt2 import GPT2Config
+    from quintnet_b200.tools import eval_checkpoint
+    cfg = GPT2Config(vocab_size=128, n_positions=32, n_embd=64, n_layer=2, n_head=1)
+    path = save_random_hf_checkpoint(str(tmp_path / "tiny.safetensors"), cfg, seed=3)
+    eval_checkpoint.main(["--checkpoint", path, "--max_samples", "16"])
+    out = capsys.readouterr().out
+    assert "perplexity" in out
+    loss = float(out.split("loss")[1].split("|")[0])
+    assert 3.0 < loss < 7.0                                     # ~ln(128) = 4.85 for a random model
+
+
+@pytest.mark.parametrize("example,nproc", [("examples.simple_dp", 2), ("examples.simple_pp", 2), ("examples.simple_tp", 2)])
+def test_examples_run_on_cpu(example, nproc):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
+           "127.0.0.1", "--master-port", str(29300 + abs(hash(example)) % 500), "-m", example, "--cpu", "--synthetic",
+           "--epochs", "1", "--samples", "128"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
+    assert "Train Loss:" in out.stdout and "Val Loss:" in out.stdout          # the reference's de-facto print interface
+
+
+def test_gpt2_finetune_example_cpu(tmp_path):
+    """examples.gpt2_finetune end to end on 2 CPU ranks (pp=2): sharded random init -> fit -> val -> shard files."""
+    import yaml
+    cfg = {"batch_size": 8, "grad_acc_steps": 2, "num_epochs": 1, "learning_rate": 1e-3, "max_grad_norm": 1.0,
+           "num_workers": 0, "max_seq_length": 16, "max_target_length": 8, "max_samples": 32, "max_val_samples": 8,
+           "output_dir": str(tmp_path / "ckpt"), "compute_generation_metrics": False, "vocab_size": 96,
+           "mesh_dim": [1, 1, 2], "mesh_name": ["dp", "tp", "pp"], "strategy_name": "3d", "schedule": "1f1b",
+           "device_type": "cpu", "dtype": "float32",
+           "model_config": {"vocab_size": 96, "n_positions": 16, "n_embd": 32, "n_layer": 2, "n_head": 2}}
+    path = tmp_path / "tiny_gpt2.yaml"
+    path.write_text(yaml.safe_dump(cfg))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29877", "-m", "examples.gpt2_finetune", "--config", str(path), "--cpu", "--synthetic"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
+    assert "Train Loss:" in out.stdout and "Val Loss:" in out.stdout
+    files = sorted(os.listdir(tmp_path / "ckpt"))
+    assert "final_model_pp0_tp0.pt" in files and "final_model_pp1_tp0.pt" in files, files
