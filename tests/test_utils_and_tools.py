@@ -110,7 +110,8 @@ def test_eval_checkpoint_tool(tmp_path, capsys):
     assert 3.0 < loss < 7.0                                     # ~ln(128) = 4.85 for a random model
 
 
-@pytest.mark.parametrize("example,nproc", [("examples.simple_dp", 2), ("examples.simple_pp", 2), ("examples.simple_tp", 2)])
+@pytest.mark.parametrize("example,nproc", [("examples.simple_dp", 2), ("examples.simple_pp", 2), ("examples.simple_tp", 2),
+                                           ("examples.full_3d", 8)])
 def test_examples_run_on_cpu(example, nproc):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
            "127.0.0.1", "--master-port", str(29300 + abs(hash(example)) % 500), "-m", example, "--cpu", "--synthetic",
@@ -138,3 +139,17 @@ def test_gpt2_finetune_example_cpu(tmp_path):
     assert "Train Loss:" in out.stdout and "Val Loss:" in out.stdout
     files = sorted(os.listdir(tmp_path / "ckpt"))
     assert "final_model_pp0_tp0.pt" in files and "final_model_pp1_tp0.pt" in files, files
+
+
+def test_single_device_train_then_verify(tmp_path):
+    """examples.train_on_single_gpu writes model_checkpoint.pt; examples.verify_model reloads and re-measures it."""
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    out = subprocess.run([sys.executable, "-m", "examples.train_on_single_gpu", "--cpu", "--synthetic", "--epochs", "1",
+                          "--samples", "256"], capture_output=True, text=True, timeout=600, cwd=tmp_path, env=env)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
+    assert (tmp_path / "model_checkpoint.pt").exists()
+    out = subprocess.run([sys.executable, "-m", "examples.verify_model", "--synthetic", "--checkpoint",
+                          str(tmp_path / "model_checkpoint.pt")], capture_output=True, text=True, timeout=600,
+                         cwd=tmp_path, env=env)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
+    assert "0 missing, 0 unexpected" in out.stdout and "accuracy:" in out.stdout
