@@ -1,9 +1,7 @@
 """The seven concrete coordinators (reference ``coordinators/*.py``)."""
 from __future__ import annotations
 
-from typing import Optional
 
-import torch
 import torch.nn as nn
 
 from .main_coordinator import (BaseCoordinator, compose, make_tied_group, resolve_device, resolve_dtype)

@@ -16,7 +16,6 @@ import torch
 import torch.distributed as dist
 import torch.nn as nn
 
-from ..core.config import axis_size
 from ..parallel.data_parallel import BucketConfig, DataParallel, DistributedConfig
 from ..parallel.pipeline_parallel import PipelineParallelWrapper
 from ..parallel.tensor_parallel import apply_tensor_parallel

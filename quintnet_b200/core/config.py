@@ -4,8 +4,8 @@ from __future__ import annotations
 
 import copy
 import os
-from dataclasses import dataclass, field, asdict
-from typing import Any, Dict, List, Optional, Sequence
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional
 
 import yaml
 
@@ -52,7 +52,7 @@ def _coerce_numbers(obj):
             if any(c in obj for c in "eE.") and obj.replace(".", "", 1).replace("e", "", 1).replace(
                     "E", "", 1).replace("-", "").replace("+", "").isdigit():
                 return float(obj)
-        except Exception:
+        except ValueError:
             pass
     return obj
 

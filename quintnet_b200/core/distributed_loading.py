@@ -19,7 +19,7 @@ ranks for replicated tensors and consistent across TP slices.
 from __future__ import annotations
 
 import zlib
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 

@@ -8,7 +8,6 @@ from __future__ import annotations
 
 from typing import Dict, List, Optional, Sequence
 
-import torch
 import torch.distributed as dist
 
 from .mesh import DeviceMesh

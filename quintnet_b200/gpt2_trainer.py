@@ -13,13 +13,10 @@ from __future__ import annotations
 import math
 import os
 import time
-from typing import Optional
 
 import torch
-import torch.distributed as dist
 import torch.nn as nn
 
-from .optim import clip_grad_norm_global, zero_grads
 from .parallel.pipeline_parallel import PipelineDataLoader, PipelineTrainer
 from .parallel.pipeline_parallel.schedule import unwrap_stage
 from .trainer import _TrainerBase, build_optimizer

@@ -6,7 +6,6 @@ from __future__ import annotations
 from typing import Optional
 
 import torch
-import torch.nn as nn
 
 from .gpt2_config import GPT2Config
 from .gpt2_stage import GPT2Stage

@@ -10,7 +10,6 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-import sys
 from pathlib import Path
 from typing import List, Optional
 

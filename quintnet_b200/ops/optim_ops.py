@@ -2,7 +2,6 @@
 reference on CPU."""
 from __future__ import annotations
 
-import ctypes
 from typing import Optional
 
 import torch

@@ -6,7 +6,7 @@ oracle the sm_100a kernels are tested against (tests/test_kernels_gpu.py).
 from __future__ import annotations
 
 import math
-from typing import Optional, Tuple
+from typing import Optional
 
 import torch
 import torch.nn.functional as F

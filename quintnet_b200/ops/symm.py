@@ -111,7 +111,7 @@ def _torch_symm_alloc(nbytes: int, device, group):
     mc = 0
     try:
         mc = int(h.multicast_ptr or 0)
-    except Exception:
+    except (AttributeError, RuntimeError):       # no NVLS multicast on this fabric / torch build
         mc = 0
     return t, peer, sig, mc, h
 

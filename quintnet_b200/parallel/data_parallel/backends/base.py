@@ -4,7 +4,6 @@ bucket operations the overlapped engine needs."""
 from __future__ import annotations
 
 from abc import ABC, abstractmethod
-from typing import Optional
 
 import torch
 

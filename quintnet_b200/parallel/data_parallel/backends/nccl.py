@@ -5,7 +5,6 @@ is an empty stub.)"""
 from __future__ import annotations
 
 import torch
-import torch.distributed as dist
 
 from .base import Handle
 from .torch_backend import TorchDistributedBackend

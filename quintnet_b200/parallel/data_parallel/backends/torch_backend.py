@@ -6,7 +6,6 @@ reduction is asynchronous (``async_op=True`` handle, scale applied on completion
 on B200 the hot path is :mod:`.nccl` (in-kernel NVLink all-reduce) and this class is the gloo / fallback path."""
 from __future__ import annotations
 
-import torch
 import torch.distributed as dist
 
 from .base import DistributedBackend, Handle

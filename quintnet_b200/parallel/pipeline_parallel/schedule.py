@@ -28,7 +28,6 @@ from abc import ABC, abstractmethod
 from typing import List, Optional
 
 import torch
-import torch.distributed as dist
 
 from ...core.communication import (bidirectional_pipeline_communicate, drain_pipeline_sends,
                                    pipeline_communicate)

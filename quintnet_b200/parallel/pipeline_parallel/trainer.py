@@ -13,7 +13,6 @@ from typing import Optional
 
 import torch
 import torch.distributed as dist
-import torch.nn as nn
 
 from ... import ops
 from ...core.communication import drain_pipeline_sends, pipeline_communicate
@@ -140,7 +139,7 @@ class PipelineTrainer:
             if hasattr(self.model, "get_tensor_shapes"):
                 try:
                     shapes = tuple(self.model.get_tensor_shapes(bsz))
-                except Exception:
+                except (RuntimeError, AttributeError):      # stage without static shapes: keep the caller's
                     pass
             x = pipeline_communicate("recv_forward", self.pp_group, self.rank, device, dtype,
                                      self.is_first_stage, self.is_last_stage, shapes=shapes)

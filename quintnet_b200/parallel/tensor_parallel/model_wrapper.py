@@ -10,7 +10,6 @@ issues.
 """
 from __future__ import annotations
 
-import torch
 import torch.distributed as dist
 import torch.nn as nn
 

@@ -3,7 +3,6 @@ rank/size are taken from the TP *group* when one is given (the reference
 returns global values)."""
 from __future__ import annotations
 
-import torch
 import torch.distributed as dist
 
 

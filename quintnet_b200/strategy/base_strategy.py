@@ -1,7 +1,7 @@
 """Strategy API: string name → coordinator (reference ``strategy/``, 306 LoC)."""
 from __future__ import annotations
 
-from abc import ABC, abstractmethod
+from abc import ABC
 from typing import Optional
 
 import torch.nn as nn

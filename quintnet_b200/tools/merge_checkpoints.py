@@ -16,7 +16,6 @@ from __future__ import annotations
 import argparse
 import os
 import re
-from collections import defaultdict
 from typing import Dict, Tuple
 
 import torch

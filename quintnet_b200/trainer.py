@@ -9,10 +9,8 @@ gradients are really synchronised over DP, metrics are accumulated on device,
 """
 from __future__ import annotations
 
-import math
 import os
 import time
-from typing import Optional
 
 import torch
 import torch.distributed as dist

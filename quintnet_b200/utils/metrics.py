@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import math
 from collections import Counter
-from typing import Dict, List, Optional
+from typing import Dict, List
 
 import torch
 
