@@ -19,6 +19,7 @@ import torch.nn as nn
 
 from .parallel.pipeline_parallel import PipelineDataLoader, PipelineTrainer
 from .parallel.pipeline_parallel.schedule import unwrap_stage
+from .utils.logger import StepLogger
 from .trainer import _TrainerBase, build_optimizer
 from .utils import checkpoint as ckpt
 
@@ -36,6 +37,7 @@ class GPT2Trainer(_TrainerBase):
         self.optimizer = build_optimizer(model, config, pg_manager, default="adamw", weight_decay=0.01)
         self.criterion = nn.CrossEntropyLoss(ignore_index=-100)
         self.gpt2_stage = unwrap_stage(model)
+        self.step_logger = None
         self.shift_labels = bool(config.get("shift_labels", True))
         if hasattr(self.gpt2_stage, "shift_labels"):
             self.gpt2_stage.shift_labels = self.shift_labels
@@ -121,14 +123,24 @@ class GPT2Trainer(_TrainerBase):
         n_steps = max(len(self.train_loader) // self.grad_acc_steps, 1)
         tot, n = 0.0, 0
         log_every = int(self.config.get("log_interval", 0) or 0)
+        # per-step records come from the rank that sees the loss (last stage, dp 0, tp 0); its host read of the
+        # loss closes the step, so wall time around train_step is the step time
+        reporter = self.is_last_stage and self.pg_manager.axis_rank("dp") == 0 and self.pg_manager.axis_rank("tp") == 0
+        if reporter and self.step_logger is None and self.config.get("log_jsonl"):
+            self.step_logger = StepLogger(self.config["log_jsonl"], rank=0)
+        tokens_per_step = int(self.config["batch_size"]) * self.max_seq_length
         for step in range(n_steps):
+            t_step = time.perf_counter()
             loss, ppl = self.train_step()
             if loss is not None:
                 tot, n = tot + loss, n + 1
-                if log_every and (step + 1) % log_every == 0 and self.is_last_stage \
-                        and self.pg_manager.axis_rank("dp") == 0 and self.pg_manager.axis_rank("tp") == 0:
+                if log_every and (step + 1) % log_every == 0 and reporter:
                     print(f"  step {step + 1}/{n_steps} loss {loss:.4f} ppl {ppl:.2f}", flush=True)
-                self.logger.log(step=self.global_step, loss=loss)
+                if reporter and self.step_logger is not None:
+                    dt = time.perf_counter() - t_step
+                    self.step_logger.log(step=self.global_step, loss=loss, ppl=ppl, step_ms=dt * 1e3,
+                                         tokens_per_s=tokens_per_step / dt,
+                                         lr=self.optimizer.param_groups[0]["lr"] if hasattr(self.optimizer, "param_groups") else None)
             si = int(self.config.get("save_interval", 0) or 0)
             if si and self.global_step % si == 0:
                 self._save_checkpoint(f"step{self.global_step}.pt")

@@ -128,7 +128,7 @@ def test_gpt2_finetune_example_cpu(tmp_path):
            "num_workers": 0, "max_seq_length": 16, "max_target_length": 8, "max_samples": 32, "max_val_samples": 8,
            "output_dir": str(tmp_path / "ckpt"), "compute_generation_metrics": False, "vocab_size": 96,
            "mesh_dim": [1, 1, 2], "mesh_name": ["dp", "tp", "pp"], "strategy_name": "3d", "schedule": "1f1b",
-           "device_type": "cpu", "dtype": "float32",
+           "device_type": "cpu", "dtype": "float32", "log_jsonl": str(tmp_path / "train.jsonl"),
            "model_config": {"vocab_size": 96, "n_positions": 16, "n_embd": 32, "n_layer": 2, "n_head": 2}}
     path = tmp_path / "tiny_gpt2.yaml"
     path.write_text(yaml.safe_dump(cfg))
@@ -139,6 +139,10 @@ def test_gpt2_finetune_example_cpu(tmp_path):
     assert "Train Loss:" in out.stdout and "Val Loss:" in out.stdout
     files = sorted(os.listdir(tmp_path / "ckpt"))
     assert "final_model_pp0_tp0.pt" in files and "final_model_pp1_tp0.pt" in files, files
+    rows = [json.loads(l) for l in (tmp_path / "train.jsonl").read_text().splitlines()]
+    steps = [r for r in rows if "step" in r]
+    assert len(steps) == 4 and all(r["tokens_per_s"] > 0 and r["step_ms"] > 0 for r in steps)    # 32 samples / batch 8
+    assert any("val_loss" in r for r in rows)                                                    # epoch record (rank 0)
 
 
 def test_single_device_train_then_verify(tmp_path):
