@@ -18,3 +18,5 @@ echo "== tp2 SP fused, CTA-pair fused kernels"; QN_TP_2CTA=1 run 29842 --mesh 1,
 # 4. interleaved 1F1B (virtual pipeline stages) vs plain 1F1B at pp2 (CPU-validated; needs its first NCCL run)
 echo "== pp2 plain 1F1B"; run 29843 --mesh 1,1,2
 echo "== pp2 interleaved V=2"; run 29844 --mesh 1,1,2 --virtual-stages 2
+# 5. design input for the fused AG kernels: does NVLink traffic alone slow a concurrent GEMM?
+step "copy-engine overlap experiment" 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29871 scripts/exp_copy_engine_overlap.py
