@@ -121,24 +121,28 @@ def test_examples_run_on_cpu(example, nproc):
     assert "Train Loss:" in out.stdout and "Val Loss:" in out.stdout          # the reference's de-facto print interface
 
 
-def test_gpt2_finetune_example_cpu(tmp_path):
-    """examples.gpt2_finetune end to end on 2 CPU ranks (pp=2): sharded random init -> fit -> val -> shard files."""
+@pytest.mark.parametrize("virtual", [1, 2])
+def test_gpt2_finetune_example_cpu(tmp_path, virtual):
+    """examples.gpt2_finetune end to end on 2 CPU ranks (pp=2): sharded random init -> fit -> val -> shard files;
+    ``virtual=2`` runs the same through the interleaved schedule with two model chunks per rank."""
     import yaml
     cfg = {"batch_size": 8, "grad_acc_steps": 2, "num_epochs": 1, "learning_rate": 1e-3, "max_grad_norm": 1.0,
            "num_workers": 0, "max_seq_length": 16, "max_target_length": 8, "max_samples": 32, "max_val_samples": 8,
            "output_dir": str(tmp_path / "ckpt"), "compute_generation_metrics": False, "vocab_size": 96,
            "mesh_dim": [1, 1, 2], "mesh_name": ["dp", "tp", "pp"], "strategy_name": "3d", "schedule": "1f1b",
            "device_type": "cpu", "dtype": "float32", "log_jsonl": str(tmp_path / "train.jsonl"),
-           "model_config": {"vocab_size": 96, "n_positions": 16, "n_embd": 32, "n_layer": 2, "n_head": 2}}
+           "model_config": {"vocab_size": 96, "n_positions": 16, "n_embd": 32, "n_layer": 4, "n_head": 2},
+           "virtual_pipeline_stages": virtual}
     path = tmp_path / "tiny_gpt2.yaml"
     path.write_text(yaml.safe_dump(cfg))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
-           "--master-port", "29877", "-m", "examples.gpt2_finetune", "--config", str(path), "--cpu", "--synthetic"]
+           "--master-port", str(29877 + virtual), "-m", "examples.gpt2_finetune", "--config", str(path), "--cpu", "--synthetic"]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
     assert "Train Loss:" in out.stdout and "Val Loss:" in out.stdout
     files = sorted(os.listdir(tmp_path / "ckpt"))
-    assert "final_model_pp0_tp0.pt" in files and "final_model_pp1_tp0.pt" in files, files
+    for stage in range(2 * virtual):
+        assert f"final_model_pp{stage}_tp0.pt" in files, files
     rows = [json.loads(l) for l in (tmp_path / "train.jsonl").read_text().splitlines()]
     steps = [r for r in rows if "step" in r]
     assert len(steps) == 4 and all(r["tokens_per_s"] > 0 and r["step_ms"] > 0 for r in steps)    # 32 samples / batch 8
