@@ -25,6 +25,7 @@ class GPT2Config:
     sequence_parallel: bool = False   # token-sharded TP (fused AG->GEMM / GEMM->RS)
     pp_layer_counts: Optional[list] = None   # explicit layers per pipeline stage (default: even split)
     fp8_linear: bool = False          # forward projections on e4m3 operands with row-wise scales (bf16 backward)
+    activation_checkpointing: bool = False   # recompute each block in backward instead of keeping its activations
 
     def __post_init__(self):
         if self.n_inner is None:

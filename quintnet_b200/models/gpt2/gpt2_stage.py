@@ -79,8 +79,13 @@ class GPT2Stage(nn.Module):
                     position_ids = self._local_rows(position_ids)
             x = self.embedding(x, position_ids)
         pending = None                       # branch output whose dropout + residual add is still owed
+        recompute = bool(getattr(self.config, "activation_checkpointing", False)) and self.training \
+            and torch.is_grad_enabled()
         for blk in self.blocks:
-            pending, x = blk.forward_fused(pending, x)
+            if recompute:
+                pending, x = ops.checkpoint(blk.forward_fused, pending, x)
+            else:
+                pending, x = blk.forward_fused(pending, x)
         p_res = self.blocks[-1].mlp.resid_pdrop if len(self.blocks) else 0.0
         if not self.is_last_stage:
             return x if pending is None else ops.dropout_add(pending, x, p_res, self.training)

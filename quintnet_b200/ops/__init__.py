@@ -131,3 +131,48 @@ def rope(x, cos, sin):
 
 
 rope_tables = reference.rope_tables
+
+
+# ------------------------------------------------------------------ activation checkpointing
+def dropout_rng_state():
+    """(seed, offset) of the native dropout counter (the kernels regenerate their masks from it), or None."""
+    from . import native
+    if not native.available():
+        return None
+    from . import cuda_ops
+    return cuda_ops._PhiloxState.seed, cuda_ops._PhiloxState.offset
+
+
+def set_dropout_rng_state(state) -> None:
+    if state is not None:
+        from . import cuda_ops
+        cuda_ops._PhiloxState.seed, cuda_ops._PhiloxState.offset = state
+
+
+class _ReplayDropoutRng:
+    """Recomputation must draw the SAME dropout masks as the original forward: rewind the native counter to where
+    the checkpointed region started, and put it back afterwards (torch's own generators are handled by
+    ``preserve_rng_state``)."""
+
+    def __init__(self, state):
+        self.state, self.saved = state, None
+
+    def __enter__(self):
+        self.saved = dropout_rng_state()
+        set_dropout_rng_state(self.state)
+
+    def __exit__(self, *exc):
+        set_dropout_rng_state(self.saved)
+        return False
+
+
+def checkpoint(fn, *args):
+    """Run ``fn(*args)`` without keeping its intermediate activations; they are recomputed in backward."""
+    import contextlib
+    from torch.utils.checkpoint import checkpoint as _ckpt
+    state = dropout_rng_state()
+
+    def context_fn():
+        return contextlib.nullcontext(), _ReplayDropoutRng(state)
+
+    return _ckpt(fn, *args, use_reentrant=False, context_fn=context_fn, preserve_rng_state=True)

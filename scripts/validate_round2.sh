@@ -20,3 +20,5 @@ echo "== pp2 plain 1F1B"; run 29843 --mesh 1,1,2
 echo "== pp2 interleaved V=2"; run 29844 --mesh 1,1,2 --virtual-stages 2
 # 5. design input for the fused AG kernels: does NVLink traffic alone slow a concurrent GEMM?
 step "copy-engine overlap experiment" 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29871 scripts/exp_copy_engine_overlap.py
+# 6. GPU tests written without hardware access
+QN_RUN_UNVALIDATED=1 step "unvalidated GPU tests" 120 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x --timeout 90 -k "activation_checkpointing"

@@ -357,3 +357,18 @@ def test_pp2_interleaved_evaluate():
 
 def test_3d_2x2x2_interleaved_zero1_sp(tmp_path):
     run_distributed(_run_interleaved, 8, 1, True, [2, 2, 2], ["dp", "tp", "pp"], str(tmp_path), 16, timeout=600)
+
+
+def test_activation_checkpointing_matches():
+    """Recomputing the blocks in backward gives the same loss and gradients, dropout included (RNG replay)."""
+    cfg_d = dict(CFG, embd_pdrop=0.1, attn_pdrop=0.0, resid_pdrop=0.1)
+    ids = torch.randint(1, 96, (4, 16))
+    grads = []
+    for ckpt in (False, True):
+        model = GPT2Model(GPT2Config(**dict(cfg_d, activation_checkpointing=ckpt)), seed=1).train()
+        torch.manual_seed(123)
+        ls, n = model(ids, labels=ids)
+        (ls / n).backward()
+        grads.append((float(ls / n), torch.cat([p.grad.flatten() for p in model.parameters()])))
+    assert abs(grads[0][0] - grads[1][0]) < 1e-6
+    assert torch.allclose(grads[0][1], grads[1][1], atol=1e-6)
