@@ -161,3 +161,15 @@ def test_single_device_train_then_verify(tmp_path):
                          cwd=tmp_path, env=env)
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
     assert "0 missing, 0 unexpected" in out.stdout and "accuracy:" in out.stdout
+
+
+def test_launch_tool_parses_epoch_metrics():
+    """tools.launch (the reference's Modal launchers' job): run an example under torchrun, parse the printed epoch
+    lines into one JSON summary."""
+    out = subprocess.run([sys.executable, "-m", "quintnet_b200.tools.launch", "--nproc", "2", "--port", "29691", "-m",
+                          "examples.simple_dp", "--", "--cpu", "--synthetic", "--epochs", "2", "--samples", "128"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
+    summary = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert summary["exit_code"] == 0 and len(summary["epochs"]) == 2
+    assert {"train_loss", "train_acc", "val_loss", "val_acc"} <= set(summary["epochs"][0])
