@@ -68,10 +68,14 @@ struct TpComm {
   __nv_bfloat16* stage[TP_MAX];       // RS: every rank's staging buffer [world][rows_per_rank][N]
   uint32_t* rs_flags[TP_MAX];         // RS: every rank's flags [mb_per_rank][4][N/64][world]
   uint32_t comm_ctas;                 // AG: the last `comm_ctas` CTAs of the grid only push (0: two push warps per CTA)
+  uint32_t external_push;             // AG: the shard was (is being) copied by someone else — copy engine on a side
+                                      // stream — who publishes ONE flag per source rank at ag_flags[kAgDoneBase + src]
   uint32_t debug;                     // QN_TP_DEBUG timing-attribution knobs (results are WRONG when set):
                                       //   1 RS: skip the peer wait + add    2 RS: remote stores go to local memory
                                       //   4 AG: skip the flag waits         8 AG: skip the push
 };
+
+constexpr uint32_t kAgDoneBase = 200000;      // flag index of the per-source "whole shard has landed" flags (external push)
 
 QN_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
@@ -240,7 +244,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t mb128 = m_blk * kMbPerTile + cta_rank;          // this CTA's 128-row block of A
           a_remote = (mb128 / tc.mb_per_rank) != static_cast<uint32_t>(tc.rank);
           if (a_remote && !(tc.debug & 4u)) {   // the peer's pushes of these 128 rows must have landed
-            if (lane < 16) wait_flag_ge(tc.ag_flags[tc.rank] + mb128 * 16 + lane, tc.seq);  // 16 8-row units in parallel
+            if (tc.external_push) {
+              if (lane == 0) wait_flag_ge(tc.ag_flags[tc.rank] + kAgDoneBase + mb128 / tc.mb_per_rank, tc.seq);
+            } else if (lane < 16) {
+              wait_flag_ge(tc.ag_flags[tc.rank] + mb128 * 16 + lane, tc.seq);                // 16 8-row units in parallel
+            }
             __syncwarp();
             fence_proxy_async_all();      // generic-proxy (NVLink) writes -> async-proxy (TMA) reads
           }
@@ -337,7 +345,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-  } else if (FUSE == FUSE_AG && n_comm == 0 && (warp == 2 || warp == 3)) {
+  } else if (FUSE == FUSE_AG && n_comm == 0 && !tc.external_push && (warp == 2 || warp == 3)) {
     // ------------------------------------------------ all-gather push (this rank's shard -> every peer)
     const uint32_t units = tc.rows_per_rank / 32;
     const uint32_t vec_per_unit = 32 * p.K / 8;                 // 16-byte vectors per 32-row unit
@@ -902,6 +910,9 @@ static int fill_comm(TpComm& c, int rank, int world, unsigned seq, int M) {
   const char* cc = getenv("QN_TP_COMM_CTAS");
   c.comm_ctas = cc ? static_cast<uint32_t>(atoi(cc)) : kDefaultCommCtas;
   if (c.comm_ctas > 64) c.comm_ctas = 64;
+  const char* ext = getenv("QN_TP_AG_MODE");                 // "ce": the Python side copies with the copy engine
+  c.external_push = (ext && ext[0] == 'c') ? 1u : 0u;
+  if (c.external_push) c.comm_ctas = 0;
   return 0;
 }
 }  // namespace qn
@@ -1042,3 +1053,17 @@ extern "C" int qn_gemm_fp8(const void* a8, const void* b8, void* c, int M, int N
   if (block_n == 256) return launch<256, false, false>(ta, tb, tc, tz, p, 0, stream);
   return launch<128, false, false>(ta, tb, tc, tz, p, 0, stream);
 }
+
+// Publish `value` at a (peer-mapped) flag after everything earlier in `stream` — e.g. a cudaMemcpyAsync into the
+// peer's gather buffer — has completed: the external-push variant of the all-gather (QN_TP_AG_MODE=ce).
+namespace qn {
+__global__ void write_flag_kernel(uint32_t* flag, uint32_t value) {
+  __threadfence_system();
+  st_release_sys(flag, value);
+}
+}  // namespace qn
+extern "C" int qn_write_flag(void* flag_base, long long index, unsigned value, cudaStream_t stream) {
+  qn::write_flag_kernel<<<1, 1, 0, stream>>>(static_cast<uint32_t*>(flag_base) + index, value);
+  return static_cast<int>(cudaGetLastError());
+}
+extern "C" int qn_ag_done_base() { return static_cast<int>(qn::kAgDoneBase); }

@@ -16,6 +16,7 @@ GEMM then optional ``All_Gather``) and ``RowParallelLinear.forward`` (``layers.p
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Dict, Optional
 
 import torch
@@ -85,7 +86,43 @@ def can_fuse(rows_total: int, group, *dims) -> bool:
     P = dist.get_world_size(group)
     flags_needed = max(rows_total // 8, (rows_total // P // 128) * 4 * ((max(dims) + 63) // 64) * P) * 4
     return (rows_total % (128 * P) == 0 and all(int(d) % 8 == 0 for d in dims) and P <= 8
-            and flags_needed <= _FLAG_BYTES)
+            and flags_needed <= _FLAG_BYTES and rows_total // 8 < 200000)   # per-unit flags stay below kAgDoneBase
+
+
+# Experimental (QN_TP_AG_MODE=ce, round-2 validation pending): hand the all-gather to the COPY ENGINE.  Right after
+# the producer of x_local, a side stream copies the shard into every peer's gather buffer with cudaMemcpyAsync and
+# publishes one flag per destination; the AG->GEMM kernel then runs without push warps and only acquires that flag
+# before its first remote tile.  No SM, register or L1 involvement in the transfer.
+_AG_MODE_CE = os.environ.get("QN_TP_AG_MODE", "") == "ce"
+_cudart = None
+
+
+def _copy_engine_allgather(ws: "_Workspace", x_local: torch.Tensor, par: int, rows: int, K: int):
+    global _cudart
+    if _cudart is None:
+        _cudart = ctypes.CDLL("libcudart.so")
+    lib = native.require()
+    if getattr(ws, "side", None) is None:
+        ws.side = torch.cuda.Stream(device=x_local.device)
+        ws.ag_done_base = int(lib.qn_ag_done_base())
+    cur = torch.cuda.current_stream()
+    ws.side.wait_stream(cur)
+    nbytes = rows * K * 2
+    off = ws.rank * nbytes
+    with torch.cuda.stream(ws.side):
+        stream = ctypes.c_void_p(ws.side.cuda_stream)
+        for p in range(ws.world):
+            dst = ws.gather[par].peer_ptrs[p] + off
+            rc = _cudart.cudaMemcpyAsync(ctypes.c_void_p(dst), ctypes.c_void_p(x_local.data_ptr()),
+                                         ctypes.c_size_t(nbytes), 3, stream)
+            if rc != 0:
+                raise RuntimeError(f"cudaMemcpyAsync (copy-engine all-gather) failed: {rc}")
+            if p != ws.rank:
+                native.check(lib.qn_write_flag(ws.ag_flags.peer_ptrs[p], ws.ag_done_base + ws.rank, ws.seq_ag, stream),
+                             "qn_write_flag")
+        ev = ws.side.record_event()
+    x_local.record_stream(ws.side)
+    return ev
 
 
 def _ag_gemm(ws: _Workspace, x_local: torch.Tensor, b: torch.Tensor, b_mn: bool, N: int, K: int, epilogue: int,
@@ -103,6 +140,7 @@ def _ag_gemm(ws: _Workspace, x_local: torch.Tensor, b: torch.Tensor, b_mn: bool,
     ws.seq_ag += 1
     par = ws.seq_ag & 1
     y = torch.empty((M, N), dtype=torch.bfloat16, device=x_local.device)
+    ce_event = _copy_engine_allgather(ws, x_local, par, rows, K) if _AG_MODE_CE else None
     rc = native.require().qn_gemm_ag_bf16(
         x_local.data_ptr(), ws.ptrs(ws.gather[par]), ws.ptrs(ws.ag_flags), ws.rank, ws.world, ws.seq_ag,
         b.data_ptr(), y.data_ptr(), M, N, K, b.stride(0), N, int(b_mn), epilogue, native.ptr(bias), native.ptr(z),
@@ -111,6 +149,8 @@ def _ag_gemm(ws: _Workspace, x_local: torch.Tensor, b: torch.Tensor, b_mn: bool,
     native.count()
     x_full = None
     if out_full_x:
+        if ce_event is not None:               # the local rows reach the gather buffer on the side stream
+            torch.cuda.current_stream().wait_event(ce_event)
         x_full = ws.gather[par].tensor[: M * K * 2].view(torch.bfloat16).view(M, K)
         if not transient:
             x_full = x_full.clone()
