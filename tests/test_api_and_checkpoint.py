@@ -179,3 +179,40 @@ def test_bench_contract_cpu():
     assert {"model", "global_batch", "seq_len", "parallelism", "l2"} <= set(rec["config"])
     assert {"value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"} <= set(rec["e2e"])
     assert rec["value"] > 0 and rec["e2e"]["h2d_bytes_per_step"] > 0
+
+
+def _zero1_resume(rank, world, out_dir):
+    """ZeRO-1 under dp2 x pp2: every dp rank writes its optimizer shard; a fresh trainer resumes bit-exactly."""
+    from quintnet_b200 import GPT2Trainer, get_strategy, init_process_groups
+    from quintnet_b200.models.gpt2 import GPT2Config
+    from quintnet_b200.parallel.pipeline_parallel import PipelineDataLoader
+    from quintnet_b200.utils.data import SyntheticTokens, make_loader
+    cfg = dict(_train_cfg(out_dir, zero=1), mesh_dim=[2, 1, 2])
+    pg = init_process_groups("cpu", cfg["mesh_dim"], cfg["mesh_name"])
+    model = get_strategy("3d", pg, cfg, None, is_staged=True).apply(None)
+    loader = make_loader(SyntheticTokens(32, 16, 96, seed=2, pad_id=0, min_fill=1.0), 2, pg, shuffle=False)
+    tr = GPT2Trainer(model, loader, None, cfg, pg, GPT2Config(**CFG))
+    for _ in range(2):
+        tr.train_step()
+    tr._save_checkpoint("z1.pt")
+    dist.barrier()
+    if dist.get_rank() == 0:
+        names = sorted(os.listdir(out_dir))
+        assert sum(n.endswith(".opt.pt") for n in names) == 4, names          # one optimizer shard per (pp, dp) rank
+    model2 = get_strategy("3d", pg, dict(cfg, seed=7), None, is_staged=True).apply(None)
+    tr2 = GPT2Trainer(model2, loader, None, cfg, pg, GPT2Config(**CFG))
+    tr2.resume(os.path.join(out_dir, "z1.pt"))
+    for (n1, p1), (n2, p2) in zip(tr.gpt2_stage.named_parameters(), tr2.gpt2_stage.named_parameters()):
+        assert torch.equal(p1, p2), n1
+    tr.micro_loader = PipelineDataLoader(loader, 2, "clm")
+    tr2.micro_loader = PipelineDataLoader(loader, 2, "clm")
+    l1, l2 = tr.train_step(), tr2.train_step()
+    if l1[0] is not None:
+        assert abs(l1[0] - l2[0]) < 1e-5
+    for (n1, p1), (n2, p2) in zip(tr.gpt2_stage.named_parameters(), tr2.gpt2_stage.named_parameters()):
+        assert torch.allclose(p1, p2, atol=1e-6), n1                           # optimizer state came back too
+
+
+def test_zero1_checkpoint_resume():
+    with tempfile.TemporaryDirectory() as d:
+        run_distributed(_zero1_resume, 4, d)
