@@ -173,3 +173,22 @@ def test_launch_tool_parses_epoch_metrics():
     summary = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert summary["exit_code"] == 0 and len(summary["epochs"]) == 2
     assert {"train_loss", "train_acc", "val_loss", "val_acc"} <= set(summary["epochs"][0])
+
+
+def test_custom_dataset_from_disk(tmp_path):
+    """CustomDataset over an on-disk HuggingFace dataset with PIL images (the MNIST path of the reference)."""
+    datasets = pytest.importorskip("datasets")
+    import numpy as np
+    from PIL import Image
+    from quintnet_b200.utils.data import CustomDataset, mnist_transform
+    rng = np.random.default_rng(0)
+    imgs = [Image.fromarray(rng.integers(0, 255, (28, 28), dtype=np.uint8)) for _ in range(6)]
+    ds = datasets.DatasetDict({"train": datasets.Dataset.from_dict({"image": imgs[:4], "label": [0, 1, 2, 3]}),
+                               "test": datasets.Dataset.from_dict({"image": imgs[4:], "label": [4, 5]})})
+    ds.save_to_disk(str(tmp_path / "mnist"))
+    train = CustomDataset(str(tmp_path / "mnist"), "train", mnist_transform)
+    test = CustomDataset(str(tmp_path / "mnist"), "test", mnist_transform)
+    assert len(train) == 4 and len(test) == 2
+    s = train[2]
+    assert s["image"].shape == (1, 28, 28) and s["image"].dtype == torch.float32 and int(s["label"]) == 2
+    assert abs(float(s["image"].mean()) - (np.array(imgs[2], dtype="float32").mean() / 255 - 0.1307) / 0.3081) < 1e-4
