@@ -192,3 +192,31 @@ def test_custom_dataset_from_disk(tmp_path):
     s = train[2]
     assert s["image"].shape == (1, 28, 28) and s["image"].dtype == torch.float32 and int(s["label"]) == 2
     assert abs(float(s["image"].mean()) - (np.array(imgs[2], dtype="float32").mean() / 255 - 0.1307) / 0.3081) < 1e-4
+
+
+def test_greedy_generation_and_metrics():
+    """generate_summary / evaluate_generation (greedy, full re-forward per token as in the reference) on a tiny
+    random GPT-2 with a toy tokenizer."""
+    from quintnet_b200.models.gpt2 import GPT2Config, GPT2Model
+    from quintnet_b200.utils.metrics import evaluate_generation, generate_summary
+
+    class Tok(_WordTokenizer):
+        eos_token_id = 0
+
+        def __call__(self, texts, **kw):
+            kw.pop("return_tensors", None)
+            return super().__call__([texts] if isinstance(texts, str) else texts, return_tensors="pt", **kw)
+
+        def decode(self, ids, skip_special_tokens=True):
+            inv = {v: k for k, v in self.vocab.items()}
+            return " ".join(inv.get(int(i), "?") for i in ids if not (skip_special_tokens and int(i) == 0))
+
+    tok = Tok()
+    for w in "the cat sat on the mat a dog ran TL;DR:".split():
+        tok._ids(w)
+    model = GPT2Model(GPT2Config(vocab_size=32, n_positions=32, n_embd=32, n_layer=1, n_head=2), seed=0).eval()
+    text = generate_summary(model, tok, "the cat sat", torch.device("cpu"), max_new_tokens=5)
+    assert isinstance(text, str) and len(text.split()) <= 5
+    scores = evaluate_generation(model, tok, [{"article": "the cat sat on the mat", "highlights": "cat sat"}],
+                                 torch.device("cpu"), num_samples=1, max_new_tokens=4)
+    assert {"rouge1", "rouge2", "rougeL", "bleu"} <= set(scores)
