@@ -216,3 +216,19 @@ def _zero1_resume(rank, world, out_dir):
 def test_zero1_checkpoint_resume():
     with tempfile.TemporaryDirectory() as d:
         run_distributed(_zero1_resume, 4, d)
+
+
+def test_bench_reference_arm_reports_unavailable_without_gpu():
+    """`bench.py --impl reference` must never crash the driver: where the reference cannot run (no CUDA here) it
+    prints {"impl": "reference", "unavailable": ...} and exits 0."""
+    import json
+    import subprocess
+    import sys
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: the reference arm actually runs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-1500:]
+    rec = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert rec["impl"] == "reference" and "unavailable" in rec
