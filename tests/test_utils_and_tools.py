@@ -143,6 +143,14 @@ def test_gpt2_finetune_example_cpu(tmp_path, virtual):
     files = sorted(os.listdir(tmp_path / "ckpt"))
     for stage in range(2 * virtual):
         assert f"final_model_pp{stage}_tp0.pt" in files, files
+    # the merge CLI turns the shards into one HF-layout file (any number of stages, incl. virtual ones)
+    merged = tmp_path / "merged.pt"
+    cli = subprocess.run([sys.executable, "-m", "quintnet_b200.tools.merge_checkpoints", "--input_dir",
+                          str(tmp_path / "ckpt"), "--output", str(merged), "--prefix", "final_model"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert cli.returncode == 0 and merged.exists(), cli.stderr[-1000:]
+    hf = torch.load(merged, weights_only=False)["model_state_dict"]
+    assert "transformer.h.3.mlp.c_proj.weight" in hf and "lm_head.weight" in hf
     rows = [json.loads(l) for l in (tmp_path / "train.jsonl").read_text().splitlines()]
     steps = [r for r in rows if "step" in r]
     assert len(steps) == 4 and all(r["tokens_per_s"] > 0 and r["step_ms"] > 0 for r in steps)    # 32 samples / batch 8
