@@ -228,3 +228,22 @@ def test_greedy_generation_and_metrics():
     scores = evaluate_generation(model, tok, [{"article": "the cat sat on the mat", "highlights": "cat sat"}],
                                  torch.device("cpu"), num_samples=1, max_new_tokens=4)
     assert {"rouge1", "rouge2", "rougeL", "bleu"} <= set(scores)
+
+
+def test_full_3d_staged_build_from_safetensors(tmp_path):
+    """examples.full_3d --staged --checkpoint: every rank loads only its shard of an HF-layout safetensors file
+    (tp2 x pp2 here) and reports its stage."""
+    import yaml
+    from quintnet_b200.core.distributed_loading import save_random_hf_checkpoint
+    from quintnet_b200.models.gpt2 import GPT2Config
+    mc = {"vocab_size": 96, "n_positions": 16, "n_embd": 32, "n_layer": 4, "n_head": 4}
+    ck = save_random_hf_checkpoint(str(tmp_path / "tiny.safetensors"), GPT2Config(**mc), seed=5, prefix="transformer.")
+    cfg = {"mesh_dim": [1, 2, 2], "mesh_name": ["dp", "tp", "pp"], "device_type": "cpu", "dtype": "float32",
+           "strategy_name": "3d", "model_config": mc, "max_seq_length": 16, "batch_size": 4, "grad_acc_steps": 2}
+    (tmp_path / "g.yaml").write_text(yaml.safe_dump(cfg))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr", "127.0.0.1",
+           "--master-port", "29733", "-m", "examples.full_3d", "--staged", "--config", str(tmp_path / "g.yaml"), "--cpu",
+           "--checkpoint", ck]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
+    assert out.stdout.count("stage built:") == 4
