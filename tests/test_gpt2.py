@@ -3,6 +3,8 @@ single process (loss AND post-step parameters), 3-D 2x2x2 parity."""
 import copy
 import os
 
+import pytest
+
 import torch
 import torch.distributed as dist
 import torch.nn as nn
@@ -82,8 +84,9 @@ def _tp_equals_single(rank, world):
                               ref.blocks[1].attn.c_attn.proj.weight.grad[cols], atol=1e-4), sp
 
 
-def test_tp_equals_single():
-    run_distributed(_tp_equals_single, 2)
+@pytest.mark.parametrize("world", [2, 4])
+def test_tp_equals_single(world):
+    run_distributed(_tp_equals_single, world)
 
 
 def _train_cfg(mesh_dim, mesh_name, schedule="1f1b", zero=0, sp=False, M=4, batch=8):
