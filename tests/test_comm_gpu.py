@@ -227,3 +227,18 @@ def test_flag_watchdog_fires_on_dropped_collective(tmp_path):
         outcome = f.read()
     print(outcome)
     assert outcome.startswith("fired"), outcome
+
+
+# --------------------------------------------------------------------------------------------------------
+# 4-rank variants of the in-kernel collectives (group sizes beyond the 2-rank axes of the 2x2x2 mesh).  Written
+# without hardware access in round 1 -> opt-in until they have run once (QN_RUN_UNVALIDATED=1).
+# --------------------------------------------------------------------------------------------------------
+_unvalidated = pytest.mark.skipif(__import__("os").environ.get("QN_RUN_UNVALIDATED") != "1",
+                                  reason="first hardware run pending (QN_RUN_UNVALIDATED=1)")
+
+
+@_unvalidated
+@pytest.mark.multigpu(4)
+@pytest.mark.parametrize("fn", ["_allreduce", "_zero1_native", "_tp_fused", "_sp_mlp"])
+def test_in_kernel_collectives_world4(fn):
+    run_distributed(globals()[fn], 4, backend="nccl")
