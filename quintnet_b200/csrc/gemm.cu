@@ -104,7 +104,7 @@ QN_DEVICE void tile_coords(uint32_t tile, uint32_t tiles_m, uint32_t tiles_n, ui
   n_blk = in_group / gsize;
 }
 
-template <uint32_t BLOCK_N, bool A_MN, bool B_MN, int FUSE, bool CTA2 = false>
+template <uint32_t BLOCK_N, bool A_MN, bool B_MN, int FUSE, bool CTA2 = false, bool ACCUM = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_z,
@@ -514,6 +514,39 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
           continue;
         }
+        if constexpr (ACCUM) {
+          // C += A·B (weight-gradient accumulation over micro-batches straight into the gradient buffer): the old
+          // C tile is bulk-loaded by TMA into the staging buffer, the accumulator is added and the tile stored back
+          uint64_t* ab = &aux_bar[warp - kEpiWarp0];
+          if (lane == 0) {
+            mbar_arrive_expect_tx(ab, 4096);
+            tma_load_2d(sbuf, &tmap_c, ab, static_cast<int32_t>(nc), static_cast<int32_t>(m0));
+          }
+          uint32_t acc[64];
+          tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
+          tmem_ld_32x32b_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
+          tmem_ld_wait();
+          mbar_wait(ab, aux_phase);
+          aux_phase ^= 1;
+          const float* f = reinterpret_cast<const float*>(acc);
+#pragma unroll
+          for (uint32_t v = 0; v < 8; ++v) {
+            uint4* sp = reinterpret_cast<uint4*>(srow + ((v ^ (lane & 7)) << 4));
+            const uint4 a4 = *sp;
+            const float2 a0 = unpack_bf16(a4.x), a1 = unpack_bf16(a4.y), a2 = unpack_bf16(a4.z), a3 = unpack_bf16(a4.w);
+            uint4 pk;
+            pk.x = pack_bf16(f[v * 8 + 0] + a0.x, f[v * 8 + 1] + a0.y); pk.y = pack_bf16(f[v * 8 + 2] + a1.x, f[v * 8 + 3] + a1.y);
+            pk.z = pack_bf16(f[v * 8 + 4] + a2.x, f[v * 8 + 5] + a2.y); pk.w = pack_bf16(f[v * 8 + 6] + a3.x, f[v * 8 + 7] + a3.y);
+            *sp = pk;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmap_c, sbuf, static_cast<int32_t>(nc), static_cast<int32_t>(m0));
+            tma_store_commit();
+          }
+          continue;
+        }
         if (p.epilogue == EPI_MUL_AUX) {
           // out = acc ⊙ aux : the aux tile (e.g. gelu'(z)) is bulk-loaded by TMA into the staging buffer,
           // multiplied in place and stored back by TMA — no strided per-thread global loads
@@ -696,12 +729,12 @@ static bool use_cta_pairs(int M, int N, int block_n, int splits, int max_ctas) {
 }
 
 // CTA-pair (cta_group::2) launch: clusters of 2 CTAs, one 256 x 256 tile per cluster and step
-template <bool A_MN, bool B_MN, int FUSE = FUSE_NONE>
+template <bool A_MN, bool B_MN, int FUSE = FUSE_NONE, bool ACCUM = false>
 static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tz,
                        const GemmParams& p, cudaStream_t stream, const CUtensorMap* tx = nullptr,
                        const TpComm* comm = nullptr) {
   using C = Cfg<256, true>;
-  auto kern = gemm_bf16_kernel<256, A_MN, B_MN, FUSE, true>;
+  auto kern = gemm_bf16_kernel<256, A_MN, B_MN, FUSE, true, ACCUM>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -731,12 +764,12 @@ static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
 }
 
-template <uint32_t BLOCK_N, bool A_MN, bool B_MN, int FUSE = FUSE_NONE>
+template <uint32_t BLOCK_N, bool A_MN, bool B_MN, int FUSE = FUSE_NONE, bool ACCUM = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tz,
                   const GemmParams& p, int max_ctas, cudaStream_t stream, const CUtensorMap* tx = nullptr,
                   const TpComm* comm = nullptr) {
   using C = Cfg<BLOCK_N>;
-  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, FUSE>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, FUSE, false, ACCUM>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -836,6 +869,20 @@ f32_to_bf16_2d_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ 
     const int r = static_cast<int>(i / (cols / 4)), c = static_cast<int>(i % (cols / 4)) * 4;
     const float4 v = *reinterpret_cast<const float4*>(in + r * ld_in + c);
     *reinterpret_cast<uint2*>(out + r * ld_out + c) = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+__global__ void __launch_bounds__(256)
+f32_to_bf16_2d_accum_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, int rows, int cols,
+                            long long ld_in, long long ld_out) {        // out += in   (bf16 += fp32)
+  const long long n4 = static_cast<long long>(rows) * (cols / 4);
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / (cols / 4)), c = static_cast<int>(i % (cols / 4)) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(in + r * ld_in + c);
+    uint2* op = reinterpret_cast<uint2*>(out + r * ld_out + c);
+    const uint2 o = *op;
+    const float2 o0 = unpack_bf16(o.x), o1 = unpack_bf16(o.y);
+    *op = make_uint2(pack_bf16(v.x + o0.x, v.y + o0.y), pack_bf16(v.z + o1.x, v.w + o1.y));
   }
 }
 }  // namespace qn
@@ -1067,3 +1114,46 @@ extern "C" int qn_write_flag(void* flag_base, long long index, unsigned value, c
   return static_cast<int>(cudaGetLastError());
 }
 extern "C" int qn_ag_done_base() { return static_cast<int>(qn::kAgDoneBase); }
+
+// Weight-gradient accumulation:  C[M, N] += Aᵀ-stored · B-stored  (a: [K, M], b: [K, N], both MN-major — the wgrad
+// layout dW += dYᵀ · X).  The epilogue reloads the old C tile by TMA, so micro-batch gradients accumulate straight into
+// the gradient buffer without a separate elementwise pass.  splits > 1: split-K into the zeroed fp32 workspace
+// `acc32`, then one pass adds it into c.
+extern "C" int qn_gemm_bf16_wgrad_accum(const void* a, const void* b, void* c, float* acc32, int M, int N, int K,
+                                        long long lda, long long ldb, long long ldc, int splits, int block_n,
+                                        cudaStream_t stream) {
+  using namespace qn;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda % 8) || (ldb % 8) || (ldc % 8) || (N % 4) || (reinterpret_cast<uintptr_t>(c) & 15)) return 910;
+  if (block_n == 0) block_n = N > 128 ? 256 : 128;
+  const int num_kb = (K + 63) / 64;
+  if (splits > num_kb) splits = num_kb;
+  if (splits < 1 || acc32 == nullptr) splits = 1;
+  if (splits > 1) {
+    const int per = (num_kb + splits - 1) / splits;
+    splits = (num_kb + per - 1) / per;
+  }
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.epilogue = EPI_NONE;
+  p.splits = splits; p.acc32 = acc32; p.ld32 = N;
+  CUtensorMap ta, tb, tcm;
+  int rc;
+  if ((rc = make_tmap(&ta, a, K, M, lda, 64, BLOCK_K))) return rc;
+  if ((rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K))) return rc;
+  if ((rc = make_tmap(&tcm, c, M, N, ldc, 64, 32))) return rc;
+  const bool two_cta = use_cta_pairs(M, N, block_n, splits, 0);
+  if (splits > 1) {                 // partial sums go to acc32 (the ACCUM epilogue is not used on this path)
+    if (two_cta) rc = launch_2cta<true, true>(ta, tb, tcm, tcm, p, stream);
+    else if (block_n == 256) rc = launch<256, true, true>(ta, tb, tcm, tcm, p, 0, stream);
+    else rc = launch<128, true, true>(ta, tb, tcm, tcm, p, 0, stream);
+    if (rc) return rc;
+    long long n4 = static_cast<long long>(M) * (N / 4);
+    int grid = static_cast<int>((n4 + 255) / 256 > 148 * 8 ? 148 * 8 : (n4 + 255) / 256);
+    f32_to_bf16_2d_accum_kernel<<<grid, 256, 0, stream>>>(acc32, static_cast<__nv_bfloat16*>(c), M, N, N, ldc);
+    return static_cast<int>(cudaGetLastError());
+  }
+  if (two_cta) return launch_2cta<true, true, FUSE_NONE, true>(ta, tb, tcm, tcm, p, stream);
+  if (block_n == 256) return launch<256, true, true, FUSE_NONE, true>(ta, tb, tcm, tcm, p, 0, stream);
+  return launch<128, true, true, FUSE_NONE, true>(ta, tb, tcm, tcm, p, 0, stream);
+}

@@ -9,6 +9,7 @@ is missing the op raises, unless ``QUINTNET_ALLOW_FALLBACK=1`` is set
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -176,3 +177,26 @@ def checkpoint(fn, *args):
         return contextlib.nullcontext(), _ReplayDropoutRng(state)
 
     return _ckpt(fn, *args, use_reentrant=False, context_fn=context_fn, preserve_rng_state=True)
+
+
+# ------------------------------------------------------------------ fused weight-gradient accumulation
+_FUSE_WGRAD_ACCUM = os.environ.get("QUINTNET_FUSE_WGRAD_ACCUM", "0") == "1"
+
+
+def set_fused_wgrad_accumulation(on: bool) -> None:
+    """When on, linear layers whose weight already has a ``.grad`` buffer ADD their weight gradient into it from
+    inside the backward op (on B200: in the wgrad GEMM's epilogue) and hand autograd no gradient for the weight —
+    one pass over the gradient instead of GEMM-store + elementwise accumulate.  Off by default."""
+    global _FUSE_WGRAD_ACCUM
+    _FUSE_WGRAD_ACCUM = bool(on)
+
+
+def fused_wgrad_accumulation() -> bool:
+    return _FUSE_WGRAD_ACCUM
+
+
+def wgrad_done(w) -> None:
+    """Nothing to do: autograd still runs the weight's AccumulateGrad node (with an undefined gradient) after an op
+    that returned ``None`` for it, and fires the post-accumulate hooks the data-parallel buckets count on — after the
+    op's backward, i.e. after the in-place accumulation.  (``tests/test_gpt2.py`` runs the 3-D suites with the switch on.)"""
+    return None

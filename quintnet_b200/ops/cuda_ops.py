@@ -78,6 +78,26 @@ def _auto_splits(M: int, N: int, K: int) -> int:
     return s if s >= 2 else 1
 
 
+def wgrad(w_param, dy2: torch.Tensor, x2: torch.Tensor, N: int, K: int, M: int):
+    """dW[N, K] = dYᵀ[N, M] · X[M, K] (both operands stored [M, ·] -> MN-major).  Returns the gradient for autograd —
+    or ``None`` after ADDING it into ``w_param.grad`` inside the GEMM epilogue when fused weight-gradient
+    accumulation is on and the gradient buffer exists (micro-batches after the first)."""
+    from . import fused_wgrad_accumulation, wgrad_done
+    g = getattr(w_param, "grad", None) if w_param is not None else None
+    if (fused_wgrad_accumulation() and g is not None and g.dtype == torch.bfloat16 and g.dim() == 2
+            and tuple(g.shape) == (N, K) and g.stride(1) == 1 and g.stride(0) % 8 == 0 and K % 4 == 0
+            and g.data_ptr() % 16 == 0):
+        splits = _auto_splits(N, K, M)
+        acc32 = torch.zeros((N, K), dtype=torch.float32, device=g.device) if splits > 1 else None
+        rc = _lib().qn_gemm_bf16_wgrad_accum(dy2.data_ptr(), x2.data_ptr(), g.data_ptr(), native.ptr(acc32), N, K, M,
+                                             dy2.stride(0), x2.stride(0), g.stride(0), splits, 0, native.stream())
+        native.check(rc, f"qn_gemm_bf16_wgrad_accum(N={N},K={K},M={M})")
+        native.count(3 if splits > 1 else 1)
+        wgrad_done(w_param)
+        return None
+    return gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True)
+
+
 class _Linear(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, act):
@@ -100,6 +120,7 @@ class _Linear(torch.autograd.Function):
         ctx.save_for_backward(x2, wq, z)
         ctx.act, ctx.has_bias, ctx.xshape = act, b is not None, x.shape
         ctx.wdtype = w.dtype
+        ctx.w_param = w if w.dtype == torch.bfloat16 else None      # target of fused gradient accumulation
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
@@ -118,8 +139,8 @@ class _Linear(torch.autograd.Function):
             dx = gemm(dy2, w, M, K, N, b_mn=True).view(ctx.xshape)
         if ctx.needs_input_grad[1]:
             # dW[N,K] = dYᵀ[N,M] · X[M,K]       (both operands stored [K_red=M, ·] -> MN-major)
-            dw = gemm(dy2, x2, N, K, M, a_mn=True, b_mn=True)
-            if ctx.wdtype != torch.bfloat16:
+            dw = wgrad(getattr(ctx, "w_param", None), dy2, x2, N, K, M)
+            if dw is not None and ctx.wdtype != torch.bfloat16:
                 dw = dw.to(ctx.wdtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy2)
@@ -182,6 +203,7 @@ class _LinearFP8(torch.autograd.Function):
             raise ValueError(f"native fp8 linear: unsupported activation {act}")
         ctx.save_for_backward(x2, wq, z)
         ctx.act, ctx.has_bias, ctx.xshape, ctx.wdtype = act, b is not None, x.shape, w.dtype
+        ctx.w_param = w if w.dtype == torch.bfloat16 else None
         return y.view(*x.shape[:-1], N)
 
     backward = _Linear.backward
@@ -218,10 +240,10 @@ class _FusedMLP(torch.autograd.Function):
         if not dy2.is_contiguous():
             dy2 = dy2.contiguous()
         dz = gemm(dy2, w2, M, I, O, b_mn=True, epilogue=EPI_MUL_AUX, z=z)      # (dY·W2) ⊙ gelu'(z), z := gelu'
-        dw2 = gemm(dy2, a, O, I, M, a_mn=True, b_mn=True) if ctx.needs_input_grad[3] else None
+        dw2 = wgrad(w2, dy2, a, O, I, M) if ctx.needs_input_grad[3] else None
         db2 = colsum(dy2) if (ctx.has_b2 and ctx.needs_input_grad[4]) else None
         dx = gemm(dz, w1, M, E, I, b_mn=True).view(ctx.xshape) if ctx.needs_input_grad[0] else None
-        dw1 = gemm(dz, x2, I, E, M, a_mn=True, b_mn=True) if ctx.needs_input_grad[1] else None
+        dw1 = wgrad(w1, dz, x2, I, E, M) if ctx.needs_input_grad[1] else None
         db1 = colsum(dz) if (ctx.has_b1 and ctx.needs_input_grad[2]) else None
         return dx, dw1, db1, dw2, db2
 

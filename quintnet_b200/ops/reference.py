@@ -12,8 +12,40 @@ import torch
 import torch.nn.functional as F
 
 
+class _LinearAccumRef(torch.autograd.Function):
+    """CPU twin of the fused weight-gradient accumulation: the backward ADDS dW into ``w.grad`` itself (when the
+    buffer exists), reports it to the data-parallel bucket bookkeeping and returns no gradient for the weight."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        ctx.w_param, ctx.has_bias = w, b is not None
+        return F.linear(x, w, b)
+
+    @staticmethod
+    def backward(ctx, dy):
+        from . import wgrad_done
+        x, w = ctx.saved_tensors
+        dy2, x2 = dy.reshape(-1, dy.shape[-1]), x.reshape(-1, x.shape[-1])
+        dx = (dy2 @ w).view(x.shape) if ctx.needs_input_grad[0] else None
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dw = dy2.t() @ x2
+            wp = ctx.w_param
+            if wp.grad is not None:
+                wp.grad.add_(dw.to(wp.grad.dtype))
+                wgrad_done(wp)
+                dw = None
+        db = dy2.sum(0) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        return dx, dw, db
+
+
 def linear(x, w, b=None, act: Optional[str] = None):
-    y = F.linear(x, w, b)
+    from . import fused_wgrad_accumulation
+    if fused_wgrad_accumulation() and isinstance(w, torch.nn.Parameter) and torch.is_grad_enabled():
+        y = _LinearAccumRef.apply(x, w, b)
+    else:
+        y = F.linear(x, w, b)
     if act == "gelu":
         y = F.gelu(y)
     elif act == "relu":

@@ -23,7 +23,7 @@ import torch
 import torch.distributed as dist
 
 from . import native, symm
-from .cuda_ops import EPI_BIAS, EPI_BIAS_GELU, EPI_MUL_AUX, EPI_NONE, colsum, gemm
+from .cuda_ops import EPI_BIAS, EPI_BIAS_GELU, EPI_MUL_AUX, EPI_NONE, colsum, gemm, wgrad
 
 _P, _I, _L, _U32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_uint
 native.declare("qn_gemm_ag_bf16", [_P, _P, _P, _I, _I, _U32, _P, _P, _I, _I, _I, _L, _L, _I, _I, _P, _P, _L, _I, _I, _P])
@@ -204,7 +204,7 @@ class _AllGatherLinear(torch.autograd.Function):
         if ctx.needs_input_grad[0]:                        # dX_local = RS(dY · W)
             dx = _gemm_rs(ws, dy2, w, True, K, N, None).view(ctx.xshape)
         if ctx.needs_input_grad[1]:
-            dw = gemm(dy2, x_full, N, K, M, a_mn=True, b_mn=True)
+            dw = wgrad(w, dy2, x_full, N, K, M)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = colsum(dy2)
         return dx, dw, db, None, None
@@ -235,7 +235,7 @@ class _LinearReduceScatter(torch.autograd.Function):
         need_full = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
         # dX = AG(dY_local) · W   (W [N, K] stored [K_red = N, N_out = K] -> MN-major B)
         dx, dy_full = _ag_gemm(ws, dy2, w, True, K, N, EPI_NONE, None, None, need_full, transient=True)
-        dw = gemm(dy_full, x2, N, K, M, a_mn=True, b_mn=True) if ctx.needs_input_grad[1] else None
+        dw = wgrad(w, dy_full, x2, N, K, M) if ctx.needs_input_grad[1] else None
         db = colsum(dy_full) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx.view(ctx.xshape), dw, db, None
 
@@ -271,10 +271,10 @@ class _SequenceParallelMLP(torch.autograd.Function):
         M = x_full.shape[0]
         # dZ = (AG(dY_local) · W2) ⊙ gelu'(z)   — gelu' applied in the fused kernel's epilogue
         dz, dy_full = _ag_gemm(ws, dy2, w2, True, I, O, EPI_MUL_AUX, None, g, True, transient=True)
-        dw2 = gemm(dy_full, a, O, I, M, a_mn=True, b_mn=True)
+        dw2 = wgrad(w2, dy_full, a, O, I, M)
         db2 = colsum(dy_full) if ctx.has_b2 else None
         dx = _gemm_rs(ws, dz, w1, True, E, I, None).view(ctx.xshape)             # dX_local = RS(dZ · W1)
-        dw1 = gemm(dz, x_full, I, E, M, a_mn=True, b_mn=True)
+        dw1 = wgrad(w1, dz, x_full, I, E, M)
         db1 = colsum(dz) if ctx.has_b1 else None
         return dx, dw1, db1, dw2, db2, None
 

@@ -68,6 +68,9 @@ class _TrainerBase:
         self.grad_acc_steps = int(config.get("grad_acc_steps", 1))
         self.max_grad_norm = float(config.get("max_grad_norm", 0.0))
         self.logger = StepLogger(config.get("log_jsonl"), self.global_rank)
+        if config.get("fuse_wgrad_accumulation") is not None:
+            from . import ops
+            ops.set_fused_wgrad_accumulation(bool(config["fuse_wgrad_accumulation"]))
         self.start_epoch = 0
         self.global_step = 0
 

@@ -21,7 +21,9 @@ echo "== pp2 interleaved V=2"; run 29844 --mesh 1,1,2 --virtual-stages 2
 # 5. design input for the fused AG kernels: does NVLink traffic alone slow a concurrent GEMM?
 step "copy-engine overlap experiment" 120 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29871 scripts/exp_copy_engine_overlap.py
 # 6. GPU tests written without hardware access
-QN_RUN_UNVALIDATED=1 step "unvalidated GPU tests" 120 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x --timeout 90 -k "activation_checkpointing"
+QN_RUN_UNVALIDATED=1 step "unvalidated GPU tests" 120 python -m pytest tests/test_kernels_gpu.py -q -m gpu -x --timeout 90 -k "activation_checkpointing or wgrad_accumulate"
 # 7. all-gather by the copy engine instead of push warps (decides NEXT.md section 2, option 1)
 QN_TP_AG_MODE=ce step "tp fused tests, copy-engine AG" 120 python -m pytest tests/test_comm_gpu.py -q -m gpu -x --timeout 90 -k "tp_fused or sequence_parallel"
 echo "== tp2 SP fused, copy-engine AG"; QN_TP_AG_MODE=ce run 29845 --mesh 1,2,1
+# 8. fused weight-gradient accumulation end to end (N = 1 bench with and without)
+echo "== N=1 bench, fused wgrad accumulation"; QUINTNET_FUSE_WGRAD_ACCUM=1 timeout --signal=KILL 240 python bench.py --steps 3 --warmup 3 --no-e2e 2>&1 | grep '^{"metric' | cut -c1-330

@@ -375,3 +375,11 @@ def test_activation_checkpointing_matches():
         grads.append((float(ls / n), torch.cat([p.grad.flatten() for p in model.parameters()])))
     assert abs(grads[0][0] - grads[1][0]) < 1e-6
     assert torch.allclose(grads[0][1], grads[1][1], atol=1e-6)
+
+
+def test_3d_2x2x2_fused_wgrad_accumulation(monkeypatch):
+    """Weight gradients added into the gradient buffers by the backward ops themselves (no AccumulateGrad add): same
+    losses and parameters as the single-process loop under dp2 x tp2 x pp2 + ZeRO-1 + sequence parallelism."""
+    monkeypatch.setenv("QUINTNET_FUSE_WGRAD_ACCUM", "1")
+    run_distributed(_run_parallel, 8, [2, 2, 2], ["dp", "tp", "pp"], "1f1b", 1, True, 16, timeout=600)
+    run_distributed(_run_parallel, 8, [2, 2, 2], ["dp", "tp", "pp"], "1f1b", 0, False, timeout=600)

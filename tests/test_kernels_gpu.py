@@ -369,3 +369,25 @@ def test_activation_checkpointing_replays_native_dropout():
         outs.append((float((ls / n).detach()), torch.cat([p.grad.float().flatten() for p in model.parameters()])))
     assert abs(outs[0][0] - outs[1][0]) < 1e-3
     assert _rel(outs[1][1], outs[0][1]) < 2e-2      # attention bwd accumulates dQ with atomics: not bitwise
+
+
+@pytest.mark.skipif(__import__("os").environ.get("QN_RUN_UNVALIDATED") != "1",
+                    reason="written without GPU access in round 1; enable with QN_RUN_UNVALIDATED=1")
+@pytest.mark.parametrize("N,K,M", [(1024, 1024, 4096), (4096, 1024, 16384), (768, 3072, 2048)])
+def test_wgrad_accumulate_epilogue(N, K, M):
+    """dW += dYᵀ·X inside the GEMM epilogue (ACCUM kernels, CTA pairs / single CTA / split-K) vs fp32."""
+    from quintnet_b200 import ops
+    from quintnet_b200.ops import cuda_ops
+    torch.manual_seed(31)
+    dy = (torch.randn(M, N, device="cuda") * 0.1).to(torch.bfloat16)
+    x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    w = torch.nn.Parameter(torch.zeros(N, K, device="cuda", dtype=torch.bfloat16))
+    w.grad = (torch.randn(N, K, device="cuda") * 3.0).to(torch.bfloat16)
+    ref = w.grad.float() + dy.float().t() @ x.float()
+    ops.set_fused_wgrad_accumulation(True)
+    try:
+        out = cuda_ops.wgrad(w, dy, x, N, K, M)
+    finally:
+        ops.set_fused_wgrad_accumulation(False)
+    assert out is None
+    assert _rel(w.grad, ref) < 1e-2, _rel(w.grad, ref)
