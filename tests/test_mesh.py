@@ -64,3 +64,23 @@ def test_bad_args():
         init_process_groups("tpu", [1], ["dp"])
     with pytest.raises(ValueError):
         init_process_groups("cpu", [1, 1], ["dp"])
+
+
+def _mesh_4d_with_cp(rank, world):
+    """A fourth, arbitrarily named axis (e.g. a context-parallel 'cp' axis reserved for ring attention) composes
+    with dp / tp / pp: fibres, coordinates and missing-axis defaults all keep working."""
+    pg = init_process_groups("cpu", [2, 1, 2, 2], ["dp", "tp", "pp", "cp"])
+    assert pg.axis_size("cp") == 2 and pg.axis_size("tp") == 1 and pg.axis_size("ep") == 1
+    coords = pg.get_coordinates_tensor_search(rank)
+    assert len(coords) == 4 and coords[3] == pg.axis_rank("cp") == rank % 2
+    g = pg.get_group("cp")
+    t = torch.tensor([float(rank)])
+    dist.all_reduce(t, group=g)
+    partner = rank ^ 1
+    assert t.item() == rank + partner
+    fibres = pg.device_mesh.get_all_fibres("cp")
+    assert sorted(map(tuple, fibres)) == [(0, 1), (2, 3), (4, 5), (6, 7)]
+
+
+def test_mesh_4d_named_axis():
+    run_distributed(_mesh_4d_with_cp, 8)
