@@ -22,6 +22,8 @@ class BucketConfig:
     # grads are ALWAYS views into the flat bucket buffer in this implementation;
     # the flag is kept for API compatibility
     gradient_as_bucket_view: bool = True
+    # parameters that receive no gradient in a step are ALWAYS tolerated: their bucket slots stay zero and the
+    # end-of-backward callback reduces buckets whose ready-count never completed (API-compatibility flag)
     find_unused_parameters: bool = False
     # also make parameters views of a flat per-bucket buffer (needed by ZeRO-1)
     flatten_parameters: bool = False
