@@ -40,7 +40,6 @@ _PREFIXES = {
 _EXACT = {
     "utils.model": "quintnet_b200.models.vit",
     "utils.Dataloader": "quintnet_b200.utils.data",
-    "utils.utils": "quintnet_b200.utils.checkpoint",            # save_checkpoint / load_checkpoint
     "utils.logging": "quintnet_b200.utils.logger",              # setup_logger / log_rank_0
     "optimizers.zero": "quintnet_b200.optim.zero",
     "optimizers.distributed_adamw": "quintnet_b200.optim.distributed_adamw",

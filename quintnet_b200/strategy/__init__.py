@@ -4,6 +4,7 @@ from __future__ import annotations
 
 from typing import Optional
 
+from ..core.process_groups import ProcessGroupManager  # noqa: F401  (re-exported like the reference)
 from .base_strategy import BaseStrategy
 from .strategies import (DataParallelStrategy, TensorParallelStrategy, PipelineParallelStrategy,
                          DataTensorParallelStrategy, DataPipelineParallelStrategy,

@@ -284,3 +284,33 @@ def test_every_reference_module_path_imports():
                     if mod and mod != "__init__":
                         have.add(mod.lstrip("."))
         assert have <= set(_REFERENCE_MODULES), sorted(have - set(_REFERENCE_MODULES))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not mounted")
+def test_every_public_symbol_of_the_reference_exists():
+    """Symbol-level parity, derived from the reference sources with ``ast`` only (nothing of the reference is
+    imported or executed): every public top-level class / function of every module — and every name its
+    ``__init__`` files re-export — exists on the module that ``QuintNet.<same path>`` resolves to."""
+    import ast
+    import importlib
+    missing = []
+    for root, _, files in os.walk("/root/reference"):
+        rel = os.path.relpath(root, "/root/reference")
+        if rel.split(os.sep)[0] in ("tests", "examples", ".git"):
+            continue
+        for f in files:
+            if not f.endswith(".py") or f in ("setup.py", "test.py", "test_weight_shapes.py") or "modal_run" in f:
+                continue
+            mod = os.path.join(rel, f[:-3]).replace(os.sep, ".").lstrip(".")
+            mod = mod[:-9] if mod.endswith(".__init__") else mod
+            mod = "" if mod in ("__init__", "") else mod
+            tree = ast.parse(open(os.path.join(root, f)).read())
+            names = [n.name for n in tree.body if isinstance(n, (ast.ClassDef, ast.FunctionDef)) and not n.name.startswith("_")]
+            if f == "__init__.py":
+                for n in tree.body:
+                    if isinstance(n, ast.ImportFrom):
+                        names += [a.asname or a.name for a in n.names if a.name != "*"]
+            target = importlib.import_module("QuintNet" + ("." + mod if mod else ""))
+            missing += [(mod, nm) for nm in names
+                        if not hasattr(target, nm) and nm not in ("Dict", "Any", "Optional", "List", "Tuple", "Union")]
+    assert not missing, missing
