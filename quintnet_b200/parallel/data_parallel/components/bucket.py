@@ -109,6 +109,25 @@ class GradientBucket:
         if flat.data_ptr() != self.flat_grad.data_ptr():
             self.flat_grad.copy_(flat)
 
+    # ---- reference API (``components/bucket.py:94-180``) ----------------------------------------------------
+    def has_gradients(self) -> bool:
+        """True if at least one parameter of the bucket currently holds a gradient."""
+        return any(p.grad is not None for p in self.parameters if p.requires_grad)
+
+    def register_hooks(self, hook_fn) -> None:
+        """Call ``hook_fn(param)`` after each parameter's gradient has been accumulated (post-accumulate hooks: the
+        reference's tensor hooks fire BEFORE ``.grad`` is written — SURVEY §8-D1b)."""
+        if not hasattr(self, "_hook_handles"):
+            self._hook_handles = []
+        for p in self.parameters:
+            if p.requires_grad:
+                self._hook_handles.append(p.register_post_accumulate_grad_hook(hook_fn))
+
+    def remove_hooks(self) -> None:
+        for h in getattr(self, "_hook_handles", []):
+            h.remove()
+        self._hook_handles = []
+
     def __repr__(self) -> str:
         return (f"GradientBucket(id={self.bucket_id}, params={len(self.parameters)}, "
                 f"{self.size_mb:.2f} MB, {self.grad_dtype})")

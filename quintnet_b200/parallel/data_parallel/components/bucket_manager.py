@@ -66,6 +66,18 @@ class BucketManager:
             h.remove()
         self._hooks = []
 
+    # ---- reference API names (``components/bucket_manager.py:117-170``) ------------------------------------
+    def register_hooks(self, bucket_ready_callback: Callable[[int], None]) -> None:
+        """``bucket_ready_callback(bucket_id)`` fires when every gradient of a bucket has been accumulated."""
+        def on_grad(bucket, param, idx):
+            bucket.absorb(param, idx)
+            if bucket.increment_gradient_count():
+                bucket_ready_callback(bucket.bucket_id)
+        self.register_gradient_hooks(on_grad)
+
+    def remove_all_hooks(self) -> None:
+        self.remove_hooks()
+
     def reset_buckets(self) -> None:
         for b in self.buckets.values():
             b.reset()

@@ -314,3 +314,28 @@ def test_every_public_symbol_of_the_reference_exists():
             missing += [(mod, nm) for nm in names
                         if not hasattr(target, nm) and nm not in ("Dict", "Any", "Optional", "List", "Tuple", "Union")]
     assert not missing, missing
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not mounted")
+def test_every_public_method_of_the_reference_classes_exists():
+    """Method-level parity (ast only): every public method of every public reference class exists on our class."""
+    import ast
+    import importlib
+    missing = []
+    for root, _, files in os.walk("/root/reference"):
+        rel = os.path.relpath(root, "/root/reference")
+        if rel.split(os.sep)[0] in ("tests", "examples", ".git"):
+            continue
+        for f in files:
+            if not f.endswith(".py") or f in ("setup.py", "test.py", "test_weight_shapes.py") or "modal_run" in f:
+                continue
+            mod = os.path.join(rel, f[:-3]).replace(os.sep, ".").lstrip(".")
+            mod = mod[:-9] if mod.endswith(".__init__") else mod
+            mod = "" if mod in ("__init__", "") else mod
+            target = importlib.import_module("QuintNet" + ("." + mod if mod else ""))
+            for n in ast.parse(open(os.path.join(root, f)).read()).body:
+                if isinstance(n, ast.ClassDef) and not n.name.startswith("_"):
+                    cls = getattr(target, n.name)
+                    missing += [(mod, n.name, b.name) for b in n.body
+                                if isinstance(b, ast.FunctionDef) and not b.name.startswith("_") and not hasattr(cls, b.name)]
+    assert not missing, missing

@@ -108,3 +108,27 @@ def test_local_ddp_and_bucket_api():
         assert p.grad.data_ptr() == v.data_ptr()
     ddp.remove_hooks()
     assert ReductionStrategy.MEAN.value == "mean"
+
+
+def test_reference_hook_api_names():
+    """BucketManager.register_hooks / remove_all_hooks and GradientBucket.has_gradients / register_hooks / remove_hooks
+    (the reference's method names) on top of the post-accumulate machinery."""
+    import torch.nn as nn
+    from quintnet_b200.parallel.data_parallel import BucketConfig, BucketManager
+    torch.manual_seed(0)
+    model = nn.Sequential(nn.Linear(8, 16), nn.ReLU(), nn.Linear(16, 4))
+    bm = BucketManager(BucketConfig(capacity_mb=1))
+    buckets = bm.create_buckets(model)
+    ready, seen = [], []
+    bm.register_hooks(ready.append)
+    b0 = next(iter(buckets.values()))
+    b0.register_hooks(lambda p: seen.append(tuple(p.shape)))
+    model(torch.randn(3, 8)).sum().backward()
+    assert sorted(ready) == sorted(buckets) and b0.has_gradients()
+    assert len(seen) == len([p for p in b0.parameters if p.requires_grad])
+    bm.remove_all_hooks()
+    b0.remove_hooks()
+    bm.reset_buckets()
+    ready.clear(); seen.clear()
+    model(torch.randn(3, 8)).sum().backward()
+    assert not ready and not seen
