@@ -57,18 +57,18 @@ def _coerce_numbers(obj):
     return obj
 
 
-def load_config(path: str) -> Dict[str, Any]:
-    if not os.path.exists(path):
-        raise FileNotFoundError(f"config file not found: {path}")
+def load_config(config_path: str) -> Dict[str, Any]:
+    if not os.path.exists(config_path):
+        raise FileNotFoundError(f"config file not found: {config_path}")
     try:
-        with open(path, "r") as f:
+        with open(config_path, "r") as f:
             cfg = yaml.safe_load(f)
     except yaml.YAMLError as e:
-        raise RuntimeError(f"failed to parse config {path}: {e}") from e
+        raise RuntimeError(f"failed to parse config {config_path}: {e}") from e
     if cfg is None:
         cfg = {}
     if not isinstance(cfg, dict):
-        raise RuntimeError(f"config {path} must be a mapping at top level")
+        raise RuntimeError(f"config {config_path} must be a mapping at top level")
     return _coerce_numbers(cfg)
 
 

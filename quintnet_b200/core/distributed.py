@@ -11,8 +11,10 @@ import torch
 import torch.distributed as dist
 
 
-def setup_distributed(backend: Optional[str] = None, device_type: Optional[str] = None,
-                      timeout_seconds: int = 1800) -> torch.device:
+def setup_distributed(backend: Optional[str] = None, init_method: Optional[str] = None,
+                      timeout_seconds: int = 1800, device_type: Optional[str] = None) -> torch.device:
+    """Reference signature ``(backend, init_method, timeout_seconds)`` (``core/distributed.py:16-31``, a stub there)
+    plus ``device_type``; ``init_method`` defaults to the torchrun environment."""
     if device_type is None:
         device_type = "cuda" if torch.cuda.is_available() else "cpu"
     backend = backend or ("nccl" if device_type == "cuda" else "gloo")
@@ -25,6 +27,8 @@ def setup_distributed(backend: Optional[str] = None, device_type: Optional[str] 
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ.setdefault("MASTER_PORT", "29500")
         kwargs = {"device_id": device} if device_type == "cuda" else {}
+        if init_method:
+            kwargs["init_method"] = init_method
         dist.init_process_group(backend=backend,
                                 timeout=datetime.timedelta(seconds=timeout_seconds), **kwargs)
     return device

@@ -39,12 +39,15 @@ class DeviceMesh:
     def __init__(
         self,
         mesh: Optional[torch.Tensor] = None,
+        device_type: str = "cuda",
         mesh_dim: Optional[Sequence[int]] = None,
         mesh_name: Sequence[str] = ("dp", "tp", "pp"),
-        device_type: str = "cuda",
+        is_backend_initialised: bool = False,
         backend: Optional[str] = None,
         timeout_seconds: int = 1800,
     ):
+        # positional order and ``is_backend_initialised`` as in the reference (``core/mesh.py:132``); the flag is
+        # informational here — the default process group is created only if it does not exist yet
         if mesh is None:
             if mesh_dim is None:
                 raise ValueError("either mesh or mesh_dim must be given")
@@ -119,7 +122,8 @@ class DeviceMesh:
             return 0
         return self.get_coordinates(rank)[self.mesh_name.index(name)]
 
-    def get_group(self, name: str) -> Optional[dist.ProcessGroup]:
+    def get_group(self, dim_name: str) -> Optional[dist.ProcessGroup]:
+        name = dim_name
         if name not in self.mesh_name:
             if name in _KNOWN_AXES:
                 return None

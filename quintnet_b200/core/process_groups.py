@@ -38,8 +38,8 @@ class ProcessGroupManager:
         self.mesh = self.device_mesh.mesh
 
     # -- reference-compatible accessors
-    def get_group(self, name: str):
-        return self.device_mesh.get_group(name)
+    def get_group(self, dim_name: str):
+        return self.device_mesh.get_group(dim_name)
 
     def get_all_groups(self) -> Dict[str, Optional[dist.ProcessGroup]]:
         return self.device_mesh.get_all_groups()

@@ -25,8 +25,9 @@ class GPT2Block(nn.Module):
         self.attn = GPT2Attention(config, tp_rank, tp_size, tp_group, device, attn_c_attn_weight,
                                   attn_c_attn_bias, attn_c_proj_weight, attn_c_proj_bias, dtype=dtype)
         self.ln_2 = nn.LayerNorm(E, eps=eps, device=device, dtype=dtype)
-        self.mlp = GPT2MLP(config, tp_rank, tp_size, tp_group, device, mlp_c_fc_weight, mlp_c_fc_bias,
-                           mlp_c_proj_weight, mlp_c_proj_bias, dtype=dtype)
+        self.mlp = GPT2MLP(config=config, tp_rank=tp_rank, tp_size=tp_size, tp_group=tp_group, device=device,
+                           c_fc_weight=mlp_c_fc_weight, c_fc_bias=mlp_c_fc_bias, c_proj_weight=mlp_c_proj_weight,
+                           c_proj_bias=mlp_c_proj_bias, dtype=dtype)
         with torch.no_grad():
             for ln, w, b in ((self.ln_1, ln_1_weight, ln_1_bias), (self.ln_2, ln_2_weight, ln_2_bias)):
                 if w is not None:

@@ -14,11 +14,21 @@ from ...parallel.tensor_parallel.layers import ColumnParallelLinear, RowParallel
 
 
 class GPT2MLP(nn.Module):
-    def __init__(self, config, tp_rank: int, tp_size: int, tp_group, device,
+    def __init__(self, embed_dim=None, hidden_dim: Optional[int] = None, tp_rank: int = 0, tp_size: int = 1,
+                 tp_group=None, device=None,
                  c_fc_weight: Optional[torch.Tensor] = None, c_fc_bias: Optional[torch.Tensor] = None,
                  c_proj_weight: Optional[torch.Tensor] = None, c_proj_bias: Optional[torch.Tensor] = None,
-                 dtype=None):
+                 dropout_prob: float = 0.1, dtype=None, config=None):
+        """Reference signature (``utils/GPT2/gpt2_mlp.py:69-82``): ``embed_dim, hidden_dim, tp_rank, tp_size, tp_group,
+        device, c_fc_weight, c_fc_bias, c_proj_weight, c_proj_bias=None, dropout_prob=0.1``.  Alternatively pass
+        ``config=GPT2Config`` (or a config as the first argument) to take the sizes and options from it."""
         super().__init__()
+        if config is None and hasattr(embed_dim, "n_embd"):
+            config, embed_dim = embed_dim, None
+        if config is None:
+            from .gpt2_config import GPT2Config
+            config = GPT2Config(n_embd=int(embed_dim), n_inner=int(hidden_dim) if hidden_dim else None,
+                                n_head=max(int(embed_dim) // 64, 1), resid_pdrop=float(dropout_prob))
         self.embed_dim = config.n_embd
         self.inner_dim = config.n_inner if config.n_inner is not None else 4 * config.n_embd
         if self.inner_dim % tp_size:

@@ -21,8 +21,10 @@ def _round_up(x: int, m: int) -> int:
 
 
 class GradientBucket:
-    def __init__(self, bucket_id: int, params: List[nn.Parameter], grad_dtype: torch.dtype,
+    def __init__(self, bucket_id: int, parameters: List[nn.Parameter], grad_dtype: Optional[torch.dtype] = None,
                  pad_to: int = 1, flatten_parameters: bool = False, allocator=None):
+        params = list(parameters)
+        grad_dtype = grad_dtype or params[0].dtype
         self.bucket_id = bucket_id
         self.parameters: List[nn.Parameter] = list(params)
         self.device = params[0].device
@@ -105,9 +107,9 @@ class GradientBucket:
     def flatten_gradients(self) -> torch.Tensor:
         return self.flat_grad
 
-    def unflatten_gradients(self, flat: torch.Tensor) -> None:
-        if flat.data_ptr() != self.flat_grad.data_ptr():
-            self.flat_grad.copy_(flat)
+    def unflatten_gradients(self, flattened_tensor: torch.Tensor) -> None:
+        if flattened_tensor.data_ptr() != self.flat_grad.data_ptr():
+            self.flat_grad.copy_(flattened_tensor)
 
     # ---- reference API (``components/bucket.py:94-180``) ----------------------------------------------------
     def has_gradients(self) -> bool:

@@ -9,9 +9,10 @@ from .bucket import GradientBucket
 
 
 class GradientReducer:
-    def __init__(self, backend: DistributedBackend, config: DistributedConfig,
+    def __init__(self, backend: DistributedBackend, distributed_config: DistributedConfig,
                  reduction_strategy: ReductionStrategy = ReductionStrategy.MEAN):
-        self.backend, self.config, self.reduction_strategy = backend, config, reduction_strategy
+        self.backend, self.config, self.reduction_strategy = backend, distributed_config, reduction_strategy
+        self.distributed_config = distributed_config
 
     @property
     def scale(self) -> float:

@@ -14,8 +14,9 @@ from ..core.config import DistributedConfig
 
 
 class ParameterBroadcaster:
-    def __init__(self, backend: DistributedBackend, config: DistributedConfig):
-        self.backend, self.config = backend, config
+    def __init__(self, backend: DistributedBackend, distributed_config: DistributedConfig):
+        self.backend, self.config = backend, distributed_config
+        self.distributed_config = distributed_config
 
     def _src(self) -> int:
         g = self.config.process_group

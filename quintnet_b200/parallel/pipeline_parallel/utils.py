@@ -6,19 +6,19 @@ from typing import List
 from typing import Optional, Sequence
 
 
-def distribute_layers(num_layers: int, num_stages: int,
+def distribute_layers(total_layers: int, num_stages: int,
                       counts: Optional[Sequence[int]] = None) -> List[List[int]]:
-    """Split ``num_layers`` layer indices over ``num_stages`` stages.  Default: as evenly as possible,
+    """Split ``total_layers`` layer indices over ``num_stages`` stages.  Default: as evenly as possible,
     remainder to the earliest stages (the reference's rule).  ``counts`` gives an explicit number of
     layers per stage (e.g. ``[13, 11]`` to offset the lm_head + loss work of the last GPT-2 stage)."""
     if num_stages < 1:
         raise ValueError("num_stages must be >= 1")
     if counts is not None:
         counts = [int(c) for c in counts]
-        if len(counts) != num_stages or sum(counts) != num_layers or min(counts) < 0:
-            raise ValueError(f"pp layer split {counts} does not cover {num_layers} layers over {num_stages} stages")
+        if len(counts) != num_stages or sum(counts) != total_layers or min(counts) < 0:
+            raise ValueError(f"pp layer split {counts} does not cover {total_layers} layers over {num_stages} stages")
     else:
-        base, rem = divmod(num_layers, num_stages)
+        base, rem = divmod(total_layers, num_stages)
         counts = [base + (1 if s < rem else 0) for s in range(num_stages)]
     out, start = [], 0
     for n in counts:

@@ -158,7 +158,8 @@ class VocabParallelEmbedding(nn.Module):
                 nn.init.normal_(self.weight, std=0.02)
         self.weight._qn_tp_sharded = True
 
-    def forward(self, ids: torch.Tensor) -> torch.Tensor:
+    def forward(self, input_ids: torch.Tensor) -> torch.Tensor:
+        ids = input_ids
         in_range = (ids >= self.vocab_start_idx) & (ids < self.vocab_end_idx)
         local = (ids - self.vocab_start_idx).clamp(0, self.weight.shape[0] - 1)
         out = torch.nn.functional.embedding(local, self.weight)

@@ -16,7 +16,7 @@ from __future__ import annotations
 import argparse
 import os
 import re
-from typing import Dict, Tuple
+from typing import Dict, Optional, Tuple
 
 import torch
 
@@ -40,8 +40,12 @@ def load_shards(input_dir: str, prefix: str) -> Dict[Tuple[int, int], dict]:
     return shards
 
 
-def merge_tp_shards(tp_states: Dict[int, dict], legacy_qkv: bool = False) -> dict:
-    """Merge the TP ranks of ONE pipeline stage."""
+def merge_tp_shards(tp_shards: Dict[int, dict], pp_rank: Optional[int] = None, legacy_qkv: bool = False) -> dict:
+    """Merge the TP ranks of ONE pipeline stage (reference signature ``(tp_shards, pp_rank)``,
+    ``merge_checkpoints.py:59``).  ``tp_shards[t]`` is a stage state dict or a whole shard payload holding one under
+    ``'model_state_dict'``; ``pp_rank`` is informational."""
+    tp_states = {t: (s["model_state_dict"] if isinstance(s, dict) and "model_state_dict" in s else s)
+                 for t, s in tp_shards.items()}
     tp = len(tp_states)
     s0 = tp_states[0]
     if tp == 1:
@@ -64,7 +68,14 @@ def merge_tp_shards(tp_states: Dict[int, dict], legacy_qkv: bool = False) -> dic
     return out
 
 
-def merge_pp_stages(stage_states: Dict[int, dict], n_layer: int, counts=None) -> dict:
+def merge_pp_stages(pp_stages: Dict[int, dict], config=None, counts=None, n_layer: Optional[int] = None) -> dict:
+    """Reference signature ``(pp_stages, config)`` (``merge_checkpoints.py:100``): ``config`` is the model config dict
+    (``n_layer``); an int is taken as the layer count directly.  ``counts`` = explicit layers per stage."""
+    stage_states = pp_stages
+    if n_layer is None:
+        n_layer = config if isinstance(config, int) else int((config or {}).get("n_layer", 0))
+    if not n_layer:
+        n_layer = sum(len({k.split(".")[1] for k in s if k.startswith("blocks.")}) for s in stage_states.values())
     pp = len(stage_states)
     layer_map = distribute_layers(n_layer, pp, counts)
     out = {}
@@ -80,7 +91,8 @@ def merge_pp_stages(stage_states: Dict[int, dict], n_layer: int, counts=None) ->
     return out
 
 
-def convert_to_hf_format(merged: dict) -> dict:
+def convert_to_hf_format(merged_state: dict) -> dict:
+    merged = merged_state
     hf = {}
     for key, v in merged.items():
         if key == "lm_head_weight":
@@ -98,8 +110,9 @@ def convert_to_hf_format(merged: dict) -> dict:
     return hf
 
 
-def merge_checkpoints(input_dir: str, output: str, prefix: str = "final_model",
+def merge_checkpoints(input_dir: str, output_path: str, prefix: str = "final_model",
                       legacy_qkv: bool = False) -> dict:
+    output = output_path
     shards = load_shards(input_dir, prefix)
     pps = sorted({p for p, _ in shards})
     tps = sorted({t for _, t in shards})
@@ -108,7 +121,7 @@ def merge_checkpoints(input_dir: str, output: str, prefix: str = "final_model",
     mc = (any_shard.get("extra") or {}).get("model_config") or config.get("model_config") or {}
     stage_states = {}
     for p in pps:
-        stage_states[p] = merge_tp_shards({t: shards[(p, t)]["model_state_dict"] for t in tps}, legacy_qkv)
+        stage_states[p] = merge_tp_shards({t: shards[(p, t)] for t in tps}, p, legacy_qkv)
     n_layer = int(mc.get("n_layer", 0)) or sum(
         len({k.split(".")[1] for k in s if k.startswith("blocks.")}) for s in stage_states.values())
     counts = (any_shard.get("parallelism_info") or {}).get("pp_layer_counts")

@@ -138,17 +138,28 @@ def _plain(obj):
     return obj
 
 
-# ---- single-process helpers (reference utils/utils.py:58-96) ----------------
-def save_checkpoint(model, optimizer, epoch: int, loss: float, path: str) -> None:
-    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
-    torch.save({"epoch": epoch, "model_state_dict": model.state_dict(),
-                "optimizer_state_dict": None if optimizer is None else optimizer.state_dict(),
-                "loss": loss}, path)
+# ---- single-process helpers with the signatures of the reference's ``utils/checkpoint.py:10-38`` (TODO stubs there) ----
+def save_checkpoint(model, optimizer, epoch: int, checkpoint_dir, is_best: bool = False, **kwargs) -> str:
+    """Write ``{checkpoint_dir}/checkpoint_epoch_{epoch}.pt`` (``epoch``, ``model_state_dict``,
+    ``optimizer_state_dict`` + any extra ``kwargs`` such as ``loss=``) and, with ``is_best``, a copy as
+    ``best_model.pt``.  Returns the path.  (The ``(model, optimizer, epoch, loss, path)`` variant of the reference's
+    ``utils/utils.py`` lives in :mod:`quintnet_b200.utils.utils`.)"""
+    checkpoint_dir = str(checkpoint_dir)
+    os.makedirs(checkpoint_dir, exist_ok=True)
+    payload = {"epoch": epoch, "model_state_dict": model.state_dict(),
+               "optimizer_state_dict": None if optimizer is None else optimizer.state_dict(), **kwargs}
+    path = os.path.join(checkpoint_dir, f"checkpoint_epoch_{epoch}.pt")
+    torch.save(payload, path)
+    if is_best:
+        torch.save(payload, os.path.join(checkpoint_dir, "best_model.pt"))
+    return path
 
 
-def load_checkpoint(model, optimizer, path: str, map_location="cpu"):
-    ck = torch.load(path, map_location=map_location, weights_only=False)
-    model.load_state_dict(ck["model_state_dict"])
+def load_checkpoint(checkpoint_path, model, optimizer=None, strict: bool = True, map_location="cpu") -> dict:
+    """Load a file written by :func:`save_checkpoint` (or any ``{'model_state_dict': …}`` file) into ``model`` /
+    ``optimizer``; returns the remaining entries (``epoch``, ``loss``, …)."""
+    ck = torch.load(str(checkpoint_path), map_location=map_location, weights_only=False)
+    model.load_state_dict(ck["model_state_dict"], strict=strict)
     if optimizer is not None and ck.get("optimizer_state_dict") is not None:
         optimizer.load_state_dict(ck["optimizer_state_dict"])
-    return ck.get("epoch", 0), ck.get("loss", None)
+    return {k: v for k, v in ck.items() if k not in ("model_state_dict", "optimizer_state_dict")}

@@ -108,12 +108,23 @@ class SummarizationCollator:
 
 
 class SummarizationDataLoader(DataLoader):
-    def __init__(self, dataset, tokenizer, batch_size: int = 8, max_length: int = 512,
-                 max_target_length: int = 128, shuffle: bool = True, num_workers: int = 0,
-                 sampler=None, **kw):
+    """Reference signature ``(dataset, batch_size, collator, shuffle=True, num_workers=0)``
+    (``utils/Dataloader.py:334-341``); without a ``collator`` one is built from ``tokenizer`` / ``max_length`` /
+    ``max_target_length``."""
+
+    def __init__(self, dataset, batch_size: int = 8, collator=None, shuffle: bool = True, num_workers: int = 0,
+                 tokenizer=None, max_length: int = 512, max_target_length: int = 128, sampler=None, **kw):
+        if collator is None:
+            if tokenizer is None:
+                raise ValueError("SummarizationDataLoader needs a collator or a tokenizer")
+            collator = SummarizationCollator(tokenizer, max_length, max_target_length)
+        self.collator = collator
         super().__init__(dataset, batch_size=batch_size, shuffle=shuffle if sampler is None else False,
-                         sampler=sampler, num_workers=num_workers,
-                         collate_fn=SummarizationCollator(tokenizer, max_length, max_target_length), **kw)
+                         sampler=sampler, num_workers=num_workers, collate_fn=collator, **kw)
+
+    @property
+    def data_loader(self):          # the reference wraps a DataLoader in this attribute
+        return self
 
 
 # ------------------------------------------------------------------- synthetic

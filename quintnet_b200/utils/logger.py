@@ -9,15 +9,15 @@ from typing import Optional
 
 
 class Logger:
-    """Tee a stream into a file."""
+    """Tee a stream into a file (reference signature ``Logger(filename, stream)``, ``utils/logger.py:5-21``)."""
 
-    def __init__(self, stream, path: str):
-        self.stream = stream
-        self.file = open(path, "a", buffering=1)
+    def __init__(self, filename: str, stream=None):
+        self.stream = self.terminal = stream if stream is not None else sys.stdout
+        self.file = self.log = open(filename, "a", buffering=1)
 
-    def write(self, data):
-        self.stream.write(data)
-        self.file.write(data)
+    def write(self, message):
+        self.stream.write(message)
+        self.file.write(message)
 
     def flush(self):
         self.stream.flush()
@@ -28,8 +28,8 @@ def setup_rank_logging(log_dir: str = "logs") -> str:
     rank = int(os.environ.get("RANK", 0))
     os.makedirs(log_dir, exist_ok=True)
     path = os.path.join(log_dir, f"rank_{rank}.log")
-    sys.stdout = Logger(sys.stdout, path)
-    sys.stderr = Logger(sys.stderr, path)
+    sys.stdout = Logger(path, sys.stdout)
+    sys.stderr = Logger(path, sys.stderr)
     return path
 
 
@@ -48,17 +48,33 @@ class StepLogger:
             self.f.write(json.dumps(kw) + "\n")
 
 
-def setup_logger(name: str = "quintnet", level: str = "INFO"):
+def setup_logger(name: str = "quintnet", level="INFO", log_file: Optional[str] = None):
+    """Rank-tagged ``logging.Logger`` (reference signature ``(name, level, log_file)``, ``utils/logging.py:9`` — a stub
+    there).  ``level`` is a ``logging`` int or its name; ``log_file`` adds a file handler."""
     import logging
     lg = logging.getLogger(name)
+    fmt = logging.Formatter(f"%(asctime)s [rank {os.environ.get('RANK', 0)}] [%(levelname)s] %(message)s")
     if not lg.handlers:
         h = logging.StreamHandler()
-        h.setFormatter(logging.Formatter("%(asctime)s [%(levelname)s] %(message)s"))
+        h.setFormatter(fmt)
         lg.addHandler(h)
-    lg.setLevel(getattr(logging, level.upper(), logging.INFO))
+    if log_file and not any(getattr(h, "baseFilename", None) == os.path.abspath(log_file) for h in lg.handlers):
+        os.makedirs(os.path.dirname(os.path.abspath(log_file)), exist_ok=True)
+        fh = logging.FileHandler(log_file)
+        fh.setFormatter(fmt)
+        lg.addHandler(fh)
+    lg.setLevel(level if isinstance(level, int) else getattr(logging, str(level).upper(), logging.INFO))
     return lg
 
 
-def log_rank_0(msg: str, logger=None) -> None:
-    if int(os.environ.get("RANK", 0)) == 0:
-        (logger.info if logger is not None else print)(msg)
+def log_rank_0(message: str, level=None, logger=None) -> None:
+    """Emit ``message`` on global rank 0 only (reference signature ``(message, level)``, ``utils/logging.py:22``)."""
+    import logging
+    if int(os.environ.get("RANK", 0)) != 0:
+        return
+    if isinstance(level, logging.Logger):          # older call style: log_rank_0(msg, logger)
+        logger, level = level, None
+    if logger is None:
+        print(message)
+    else:
+        logger.log(level if isinstance(level, int) else logging.INFO, message)

@@ -81,9 +81,12 @@ def compute_rouge_bleu(predictions: List[str], references: List[str]) -> Dict[st
 
 
 @torch.no_grad()
-def generate_summary(model, tokenizer, article: str, device, max_new_tokens: int = 128,
+def generate_summary(model, tokenizer, input_text: str, max_new_tokens: int = 128, device=None,
                      max_input_length: int = 384) -> str:
-    prompt = f"{article}\n\nTL;DR: "
+    """Greedy summary of ``input_text`` (reference signature ``utils/metrics.py:74-80``)."""
+    if device is None:
+        device = next(model.parameters()).device
+    prompt = f"{input_text}\n\nTL;DR: "
     ids = tokenizer(prompt, return_tensors="pt", truncation=True, max_length=max_input_length)["input_ids"].to(device)
     model.eval()
     out = ids
@@ -97,11 +100,12 @@ def generate_summary(model, tokenizer, article: str, device, max_new_tokens: int
     return tokenizer.decode(out[0, ids.shape[1]:], skip_special_tokens=True)
 
 
-def evaluate_generation(model, tokenizer, dataset, device, num_samples: int = 50,
+def evaluate_generation(model, tokenizer, val_dataset, device, num_samples: int = 50,
                         max_new_tokens: int = 128) -> Dict[str, float]:
+    dataset = val_dataset
     preds, refs = [], []
     for i in range(min(num_samples, len(dataset))):
         item = dataset[i]
-        preds.append(generate_summary(model, tokenizer, item["article"], device, max_new_tokens))
+        preds.append(generate_summary(model, tokenizer, item["article"], max_new_tokens, device))
         refs.append(item["highlights"])
     return compute_rouge_bleu(preds, refs)

@@ -4,6 +4,7 @@ numbers are reduced with MAX (the slowest rank defines the step)."""
 from __future__ import annotations
 
 import contextlib
+import os
 import time
 from collections import defaultdict
 from typing import Dict, Optional
@@ -65,8 +66,9 @@ class DeviceTimer:
 
 
 @contextlib.contextmanager
-def profile_time(name: str = "block", sink: Optional[dict] = None, verbose: bool = False):
-    """Wall-time (device-synchronised) of a block in milliseconds."""
+def profile_time(name: str = "Operation", rank: int = 0, sink: Optional[dict] = None, verbose: bool = False):
+    """Wall-time (device-synchronised) of a block in milliseconds; printed (``verbose``) only on ``rank``
+    (reference signature ``(name, rank)``, ``utils/profiling.py:12`` — a stub there)."""
     if torch.cuda.is_available():
         torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -78,25 +80,27 @@ def profile_time(name: str = "block", sink: Optional[dict] = None, verbose: bool
         ms = (time.perf_counter() - t0) * 1e3
         if sink is not None:
             sink[name] = ms
-        if verbose:
+        if verbose and int(os.environ.get("RANK", 0)) == int(rank):
             print(f"[profile_time] {name}: {ms:.3f} ms")
 
 
 @contextlib.contextmanager
-def profile_memory(name: str = "block", sink: Optional[dict] = None, verbose: bool = False):
-    """Peak CUDA memory delta of a block in MiB (0 on CPU)."""
-    cuda = torch.cuda.is_available()
+def profile_memory(device: Optional[torch.device] = None, name: str = "block", sink: Optional[dict] = None,
+                   verbose: bool = False):
+    """Peak CUDA memory delta of a block in MiB on ``device`` (current device by default; 0 on CPU).  Reference
+    signature ``(device)``, ``utils/profiling.py:21`` — a stub there."""
+    cuda = torch.cuda.is_available() and (device is None or torch.device(device).type == "cuda")
     if cuda:
-        torch.cuda.synchronize()
-        torch.cuda.reset_peak_memory_stats()
-        base = torch.cuda.memory_allocated()
+        torch.cuda.synchronize(device)
+        torch.cuda.reset_peak_memory_stats(device)
+        base = torch.cuda.memory_allocated(device)
     try:
         yield
     finally:
         peak = 0.0
         if cuda:
-            torch.cuda.synchronize()
-            peak = (torch.cuda.max_memory_allocated() - base) / 2 ** 20
+            torch.cuda.synchronize(device)
+            peak = (torch.cuda.max_memory_allocated(device) - base) / 2 ** 20
         if sink is not None:
             sink[name] = peak
         if verbose:

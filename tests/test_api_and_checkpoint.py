@@ -339,3 +339,100 @@ def test_every_public_method_of_the_reference_classes_exists():
                     missing += [(mod, n.name, b.name) for b in n.body
                                 if isinstance(b, ast.FunctionDef) and not b.name.startswith("_") and not hasattr(cls, b.name)]
     assert not missing, missing
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference tree not mounted")
+def test_every_reference_signature_is_accepted():
+    """Signature-level parity (ast vs inspect): for every public function, method and constructor of the reference, our
+    callable accepts all of its parameter names, in the same positional order (extra parameters of ours come after
+    or are keyword-only in practice)."""
+    import ast
+    import importlib
+    import inspect
+    issues = []
+
+    def check(label, fnode, obj):
+        try:
+            sig = inspect.signature(obj)
+        except (TypeError, ValueError):
+            return
+        names = [x.arg for x in fnode.args.posonlyargs + fnode.args.args]
+        kwonly = [x.arg for x in fnode.args.kwonlyargs]
+        ours = list(sig.parameters.values())
+        our_names = [p.name for p in ours]
+        has_kwargs = any(p.kind == p.VAR_KEYWORD for p in ours)
+        has_var = any(p.kind == p.VAR_POSITIONAL for p in ours)
+        if names and names[0] in ("self", "cls"):
+            names = names[1:]
+        miss = [n for n in names + kwonly if n not in our_names and not has_kwargs]
+        pos = [p.name for p in ours if p.kind in (p.POSITIONAL_ONLY, p.POSITIONAL_OR_KEYWORD) and p.name not in ("self", "cls")]
+        order_bad = (not has_var) and any(i >= len(pos) or pos[i] != n for i, n in enumerate(names) if n in our_names)
+        if miss or order_bad:
+            issues.append((label, miss, names, pos))
+
+    for root, _, files in os.walk("/root/reference"):
+        rel = os.path.relpath(root, "/root/reference")
+        if rel.split(os.sep)[0] in ("tests", "examples", ".git"):
+            continue
+        for f in files:
+            if not f.endswith(".py") or f in ("setup.py", "test.py", "test_weight_shapes.py") or "modal_run" in f:
+                continue
+            mod = os.path.join(rel, f[:-3]).replace(os.sep, ".").lstrip(".")
+            mod = mod[:-9] if mod.endswith(".__init__") else mod
+            mod = "" if mod in ("__init__", "") else mod
+            target = importlib.import_module("QuintNet" + ("." + mod if mod else ""))
+            for n in ast.parse(open(os.path.join(root, f)).read()).body:
+                if isinstance(n, ast.FunctionDef) and not n.name.startswith("_"):
+                    check(f"{mod}.{n.name}", n, getattr(target, n.name))
+                if isinstance(n, ast.ClassDef) and not n.name.startswith("_"):
+                    cls = getattr(target, n.name)
+                    for b in n.body:
+                        if isinstance(b, ast.FunctionDef) and (not b.name.startswith("_") or b.name == "__init__"):
+                            if b.name in ("forward", "backward") and any(
+                                    isinstance(d, ast.Name) and d.id == "staticmethod" for d in b.decorator_list):
+                                continue                      # autograd.Function statics: ctx-based, not a user API
+                            obj = getattr(cls, b.name, None)
+                            if obj is not None:
+                                check(f"{mod}.{n.name}.{b.name}", b, obj)
+    assert not issues, issues
+
+
+def test_reference_style_helper_calls(tmp_path):
+    """The helpers whose signatures were aligned with the reference behave: utils.utils / utils.checkpoint save+load,
+    Logger(filename, stream), setup_logger(log_file=…), merge helpers with payload dicts, distribute_layers(total_layers=…)."""
+    import io
+    import torch.nn as nn
+    from QuintNet.parallelism.pipeline_parallel.utils import distribute_layers
+    from QuintNet.utils import checkpoint as ck
+    from QuintNet.utils import utils as uu
+    from QuintNet.utils.logger import Logger
+    from QuintNet.utils.logging import log_rank_0, setup_logger
+    from QuintNet.merge_checkpoints import convert_to_hf_format, merge_pp_stages, merge_tp_shards
+    m, opt = nn.Linear(4, 3), None
+    opt = torch.optim.SGD(m.parameters(), lr=0.1)
+    uu.save_checkpoint(m, opt, 3, 0.5, str(tmp_path / "a.pt"))
+    m2 = nn.Linear(4, 3)
+    _, _, epoch, loss = uu.load_checkpoint(m2, torch.optim.SGD(m2.parameters(), lr=0.1), str(tmp_path / "a.pt"))
+    assert epoch == 3 and loss == 0.5 and torch.equal(m.weight, m2.weight) and uu.count_parameters(m) == 15
+    path = ck.save_checkpoint(m, opt, epoch=4, checkpoint_dir=tmp_path / "d", is_best=True, loss=0.25)
+    assert os.path.exists(path) and os.path.exists(tmp_path / "d" / "best_model.pt")
+    m3 = nn.Linear(4, 3)
+    meta = ck.load_checkpoint(checkpoint_path=path, model=m3, optimizer=None, strict=True)
+    assert meta["epoch"] == 4 and meta["loss"] == 0.25 and torch.equal(m.weight, m3.weight)
+    buf = io.StringIO()
+    lg = Logger(str(tmp_path / "tee.log"), buf)
+    lg.write("hello"); lg.flush()
+    assert buf.getvalue() == "hello" and open(tmp_path / "tee.log").read() == "hello"
+    logger = setup_logger(name="qn_test", level="INFO", log_file=str(tmp_path / "log" / "x.log"))
+    log_rank_0("visible", logger=logger)
+    for h in logger.handlers:
+        h.flush()
+    assert "visible" in open(tmp_path / "log" / "x.log").read()
+    assert distribute_layers(total_layers=5, num_stages=2) == [[0, 1, 2], [3, 4]]
+    tp = {t: {"model_state_dict": {"blocks.0.mlp.c_fc.proj.weight": torch.full((2, 3), float(t)),
+                                     "blocks.0.ln_1.weight": torch.ones(3)}} for t in range(2)}
+    stage = merge_tp_shards(tp_shards=tp, pp_rank=0)
+    assert stage["blocks.0.mlp.c_fc.proj.weight"].shape == (4, 3)
+    merged = merge_pp_stages(pp_stages={0: stage, 1: dict(stage)}, config={"n_layer": 2})
+    assert {"blocks.0.ln_1.weight", "blocks.1.ln_1.weight"} <= set(merged)
+    assert "transformer.h.1.mlp.c_fc.weight" in convert_to_hf_format(merged_state=merged)

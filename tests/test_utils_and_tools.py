@@ -82,7 +82,7 @@ def test_profiling_and_memory():
     from quintnet_b200.utils.memory import clear_cache, get_memory_usage
     from quintnet_b200.utils.profiling import DeviceTimer, nvtx_range, profile_memory, profile_time
     sink = {}
-    with profile_time("mm", sink), profile_memory("mm_mem", sink), nvtx_range("mm"):
+    with profile_time("mm", sink=sink), profile_memory(name="mm_mem", sink=sink), nvtx_range("mm"):
         torch.randn(64, 64) @ torch.randn(64, 64)
     assert sink["mm"] > 0 and sink["mm_mem"] >= 0
     t = DeviceTimer()
@@ -223,7 +223,7 @@ def test_greedy_generation_and_metrics():
     for w in "the cat sat on the mat a dog ran TL;DR:".split():
         tok._ids(w)
     model = GPT2Model(GPT2Config(vocab_size=32, n_positions=32, n_embd=32, n_layer=1, n_head=2), seed=0).eval()
-    text = generate_summary(model, tok, "the cat sat", torch.device("cpu"), max_new_tokens=5)
+    text = generate_summary(model, tok, "the cat sat", max_new_tokens=5, device=torch.device("cpu"))
     assert isinstance(text, str) and len(text.split()) <= 5
     scores = evaluate_generation(model, tok, [{"article": "the cat sat on the mat", "highlights": "cat sat"}],
                                  torch.device("cpu"), num_samples=1, max_new_tokens=4)
