@@ -15,8 +15,13 @@ def main():
     ap = base_parser("gpt2_config.yaml")
     ap.add_argument("--staged", action="store_true")
     ap.add_argument("--checkpoint", default=None)
+    ap.add_argument("--model_config", default=None, help="JSON file with the GPT-2 model config (overrides the YAML's)")
     args = ap.parse_args()
     config = load_config(args.config)
+    if args.model_config:
+        import json
+        with open(args.model_config) as f:
+            config["model_config"] = json.load(f)
     if args.cpu:
         config["device_type"] = "cpu"
     setup_distributed(device_type=config.get("device_type", "cuda"))
