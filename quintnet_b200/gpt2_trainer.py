@@ -144,6 +144,14 @@ class GPT2Trainer(_TrainerBase):
             si = int(self.config.get("save_interval", 0) or 0)
             if si and self.global_step % si == 0:
                 self._save_checkpoint(f"step{self.global_step}.pt")
+            ei = int(self.config.get("eval_interval", 0) or 0)       # mid-epoch validation every `eval_interval` steps
+            if ei and self.val_loader is not None and self.global_step % ei == 0:
+                v_loss, v_ppl = self._validate_epoch(epoch)
+                self.model.train()
+                if v_loss is not None and reporter:
+                    print(f"  step {self.global_step} Val Loss: {v_loss:.4f} | Val PPL: {_finite(v_ppl):.2f}", flush=True)
+                    if self.step_logger is not None:
+                        self.step_logger.log(step=self.global_step, val_loss=v_loss, val_ppl=_finite(v_ppl))
         if n == 0:
             return None, None
         avg = tot / n

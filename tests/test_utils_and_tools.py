@@ -130,7 +130,7 @@ def test_gpt2_finetune_example_cpu(tmp_path, virtual):
            "num_workers": 0, "max_seq_length": 16, "max_target_length": 8, "max_samples": 32, "max_val_samples": 8,
            "output_dir": str(tmp_path / "ckpt"), "compute_generation_metrics": False, "vocab_size": 96,
            "mesh_dim": [1, 1, 2], "mesh_name": ["dp", "tp", "pp"], "strategy_name": "3d", "schedule": "1f1b",
-           "device_type": "cpu", "dtype": "float32", "log_jsonl": str(tmp_path / "train.jsonl"),
+           "device_type": "cpu", "dtype": "float32", "log_jsonl": str(tmp_path / "train.jsonl"), "eval_interval": 2,
            "model_config": {"vocab_size": 96, "n_positions": 16, "n_embd": 32, "n_layer": 4, "n_head": 2},
            "virtual_pipeline_stages": virtual}
     path = tmp_path / "tiny_gpt2.yaml"
@@ -152,8 +152,9 @@ def test_gpt2_finetune_example_cpu(tmp_path, virtual):
     hf = torch.load(merged, weights_only=False)["model_state_dict"]
     assert "transformer.h.3.mlp.c_proj.weight" in hf and "lm_head.weight" in hf
     rows = [json.loads(l) for l in (tmp_path / "train.jsonl").read_text().splitlines()]
-    steps = [r for r in rows if "step" in r]
+    steps = [r for r in rows if "step" in r and "loss" in r]
     assert len(steps) == 4 and all(r["tokens_per_s"] > 0 and r["step_ms"] > 0 for r in steps)    # 32 samples / batch 8
+    assert [r["step"] for r in rows if "step" in r and "val_loss" in r] == [2, 4]                # eval_interval = 2
     assert any("val_loss" in r for r in rows)                                                    # epoch record (rank 0)
 
 
