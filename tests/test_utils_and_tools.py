@@ -248,3 +248,17 @@ def test_full_3d_staged_build_from_safetensors(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
     assert out.stdout.count("stage built:") == 4
+
+
+def test_check_weight_shapes_tool(tmp_path, capsys):
+    """tools.check_weight_shapes (the reference's test_weight_shapes.py role) on random weights and on a safetensors file."""
+    from quintnet_b200.core.distributed_loading import save_random_hf_checkpoint
+    from quintnet_b200.models.gpt2 import GPT2Config
+    from quintnet_b200.tools import check_weight_shapes as cws
+    cfg = GPT2Config(vocab_size=96, n_positions=16, n_embd=32, n_layer=4, n_head=4)
+    from quintnet_b200.core.distributed_loading import hf_shapes, random_hf_tensor
+    shapes = hf_shapes(cfg)
+    n = cws.check(cfg, lambda name: random_hf_tensor(name, shapes[name], cfg, 0, torch.device("cpu")), tp=2, pp=2, verbose=False)
+    assert n > 40
+    cws.main(["--model", "gpt2_base", "--tp", "4", "--pp", "2"])
+    assert "shard shapes match" in capsys.readouterr().out
