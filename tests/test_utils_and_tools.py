@@ -262,3 +262,14 @@ def test_check_weight_shapes_tool(tmp_path, capsys):
     assert n > 40
     cws.main(["--model", "gpt2_base", "--tp", "4", "--pp", "2"])
     assert "shard shapes match" in capsys.readouterr().out
+
+
+def test_reference_readme_launch_lines_work():
+    """The reference README's launch line, verbatim apart from the CPU flags: ``-m QuintNet.examples.simple_dp`` with
+    ``--config QuintNet/examples/dp_config.yaml``."""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29612", "-m", "QuintNet.examples.simple_dp", "--config", "QuintNet/examples/dp_config.yaml",
+           "--cpu", "--synthetic", "--epochs", "1", "--samples", "64"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
+    assert "Train Loss:" in out.stdout
