@@ -298,8 +298,8 @@ def pipeline_communicate(
     pp_rank: int,
     device,
     dtype,
-    is_first_stage: bool,
-    is_last_stage: bool,
+    is_first_stage: bool = False,
+    is_last_stage: bool = False,
     tensor: Optional[torch.Tensor] = None,
     shapes: Optional[Sequence[int]] = None,
 ):
@@ -355,8 +355,8 @@ def bidirectional_pipeline_communicate(
     recv_shapes: Sequence[int],
     device,
     dtype,
-    is_first_stage: bool,
-    is_last_stage: bool,
+    is_first_stage: bool = False,
+    is_last_stage: bool = False,
 ):
     """Batched send+recv with the same neighbour (1F1B steady state).
 

@@ -41,7 +41,7 @@ class DeviceMesh:
         mesh: Optional[torch.Tensor] = None,
         device_type: str = "cuda",
         mesh_dim: Optional[Sequence[int]] = None,
-        mesh_name: Sequence[str] = ("dp", "tp", "pp"),
+        mesh_name: Sequence[str] = ("dp", "pp", "tp"),        # the reference's default axis order
         is_backend_initialised: bool = False,
         backend: Optional[str] = None,
         timeout_seconds: int = 1800,

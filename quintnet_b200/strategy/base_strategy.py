@@ -20,7 +20,7 @@ class BaseStrategy(ABC):
     def coordinator_kwargs(self) -> dict:
         return {}
 
-    def apply(self, model: Optional[nn.Module]) -> nn.Module:
+    def apply(self, model: Optional[nn.Module] = None) -> nn.Module:
         coord = self.coordinator_cls(model, pg_manager=self.pg_manager, config=self.config,
                                      device=self.device, **self.coordinator_kwargs())
         out = coord.parallelize()

@@ -25,7 +25,7 @@ from ..parallel.pipeline_parallel.utils import distribute_layers
 _SHARD_RE = re.compile(r"_pp(\d+)_tp(\d+)\.pt$")
 
 
-def load_shards(input_dir: str, prefix: str) -> Dict[Tuple[int, int], dict]:
+def load_shards(input_dir: str, prefix: str = "final_model") -> Dict[Tuple[int, int], dict]:
     shards = {}
     for fn in sorted(os.listdir(input_dir)):
         if not fn.startswith(prefix + "_pp"):
