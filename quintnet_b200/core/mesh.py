@@ -122,6 +122,11 @@ class DeviceMesh:
             return 0
         return self.get_coordinates(rank)[self.mesh_name.index(name)]
 
+    @property
+    def groups(self) -> Dict[str, Optional[dist.ProcessGroup]]:
+        """axis name -> this rank's process group (the reference's ``self.groups`` dict)."""
+        return dict(self._groups)
+
     def get_group(self, dim_name: str) -> Optional[dist.ProcessGroup]:
         name = dim_name
         if name not in self.mesh_name:

@@ -24,6 +24,7 @@ class GPT2Attention(nn.Module):
         super().__init__()
         self.embed_dim, self.num_heads = config.n_embd, config.n_head
         self.head_dim = self.embed_dim // self.num_heads
+        self.scale = self.head_dim ** -0.5
         if self.num_heads % tp_size:
             raise ValueError(f"n_head={self.num_heads} not divisible by tp={tp_size}")
         self.tp_rank, self.tp_size, self.tp_group, self.device = tp_rank, tp_size, tp_group, device

@@ -15,6 +15,7 @@ class GPT2Embedding(nn.Module):
                  wte_weights: Optional[torch.Tensor] = None, wpe_weights: Optional[torch.Tensor] = None,
                  dropout_prob: float = 0.1, device=None, dtype=None, use_wpe: bool = True):
         super().__init__()
+        self.vocab_size, self.max_position_embeddings, self.embed_dim = vocab_size, max_position_embeddings, embed_dim
         self.wte = nn.Embedding(vocab_size, embed_dim, device=device, dtype=dtype)
         self.wpe = nn.Embedding(max_position_embeddings, embed_dim, device=device, dtype=dtype) \
             if use_wpe else None

@@ -34,6 +34,7 @@ class GPT2MLP(nn.Module):
         if self.inner_dim % tp_size:
             raise ValueError(f"n_inner={self.inner_dim} not divisible by tp={tp_size}")
         self.inner_dim_local = self.inner_dim // tp_size
+        self.hidden_dim, self.hidden_dim_local = self.inner_dim, self.inner_dim_local      # reference attribute names
         self.tp_rank, self.tp_size, self.tp_group, self.device = tp_rank, tp_size, tp_group, device
         sp = bool(getattr(config, "sequence_parallel", False)) and tp_size > 1
         fp8 = self.fp8 = bool(getattr(config, "fp8_linear", False))

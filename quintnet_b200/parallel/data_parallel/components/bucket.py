@@ -111,6 +111,10 @@ class GradientBucket:
         if flattened_tensor.data_ptr() != self.flat_grad.data_ptr():
             self.flat_grad.copy_(flattened_tensor)
 
+    @property
+    def is_ready(self) -> bool:       # reference attribute: every gradient of the bucket has arrived
+        return self.are_all_gradients_ready()
+
     # ---- reference API (``components/bucket.py:94-180``) ----------------------------------------------------
     def has_gradients(self) -> bool:
         """True if at least one parameter of the bucket currently holds a gradient."""

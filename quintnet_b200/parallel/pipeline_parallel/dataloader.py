@@ -12,6 +12,10 @@ class PipelineDataLoader:
         self.data_iter = iter(dataloader)
         self.epoch = 0
 
+    @property
+    def iterator(self):               # the reference's attribute name for the live iterator
+        return self.data_iter
+
     def __iter__(self):
         return self
 

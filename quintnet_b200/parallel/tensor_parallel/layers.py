@@ -150,13 +150,18 @@ class VocabParallelEmbedding(nn.Module):
         self.num_embeddings, self.embedding_dim = num_embeddings, embedding_dim
         self.vocab_start_idx, self.vocab_end_idx = vocab_start_idx, vocab_end_idx
         n_local = vocab_end_idx - vocab_start_idx
-        self.weight = nn.Parameter(torch.empty(n_local, embedding_dim, device=local_device, dtype=dtype))
+        # the table lives in ``self.embedding`` (state-dict key ``embedding.weight``) as in the reference
+        self.embedding = nn.Embedding(n_local, embedding_dim, device=local_device, dtype=dtype)
         with torch.no_grad():
             if weight_slice is not None:
-                self.weight.copy_(weight_slice)
+                self.embedding.weight.copy_(weight_slice)
             else:
-                nn.init.normal_(self.weight, std=0.02)
-        self.weight._qn_tp_sharded = True
+                nn.init.normal_(self.embedding.weight, std=0.02)
+        self.embedding.weight._qn_tp_sharded = True
+
+    @property
+    def weight(self) -> nn.Parameter:
+        return self.embedding.weight
 
     def forward(self, input_ids: torch.Tensor) -> torch.Tensor:
         ids = input_ids

@@ -28,6 +28,7 @@ class CustomDataset(Dataset):
             raise ImportError("CustomDataset needs the HuggingFace `datasets` package") from e
         from datasets import Dataset as HFDataset, load_from_disk
         self.transform = transform
+        self.dataset_path, self.split = dataset_path, split
         if os.path.isdir(dataset_path):
             ds = load_from_disk(dataset_path)
             self.data = ds[split] if hasattr(ds, "keys") and split in ds else ds
@@ -35,6 +36,10 @@ class CustomDataset(Dataset):
             self.data = HFDataset.from_file(dataset_path)
         else:
             raise ValueError(f"unsupported dataset path {dataset_path}")
+
+    @property
+    def dataset(self):                # reference attribute name
+        return self.data
 
     def __len__(self):
         return len(self.data)
@@ -70,6 +75,7 @@ class SummarizationDataset(Dataset):
         df = pd.read_csv(path)
         if max_samples:
             df = df.iloc[:max_samples]
+        self.dataset_path, self.split, self.data = dataset_path, split, df
         self.articles: List[str] = df["article"].astype(str).tolist()
         self.highlights: List[str] = df["highlights"].astype(str).tolist()
 
