@@ -50,6 +50,10 @@ def run_vit(strategy_name: str, default_config: str):
     if args.epochs:
         config["num_epochs"] = args.epochs
     setup_distributed(device_type=config.get("device_type", "cuda"))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if len(config["mesh_dim"]) == 1 and int(config["mesh_dim"][0]) != world:
+        print(f"[examples] 1-D mesh {config['mesh_dim']} resized to the launch size [{world}]")
+        config["mesh_dim"] = [world]
     pg = init_process_groups(config.get("device_type", "cuda"), config["mesh_dim"], config["mesh_name"])
     pg.print_mesh_info()
     train_loader, val_loader = vit_loaders(config, pg, args.synthetic, args.samples)
