@@ -35,6 +35,7 @@ class PipelineTrainer:
         self.task_type, self.vocab_size = task_type, vocab_size
         self.loss_scale, self.shift_labels = loss_scale, shift_labels
         self.pg_manager = pg_manager
+        self.batch_labels, self.batch_predictions = [], []     # reference attributes (never filled there either)
         self.compute_dtype = compute_dtype
         stage = unwrap_stage(model)
         self.stage = stage
