@@ -111,7 +111,7 @@ def _torch_symm_alloc(nbytes: int, device, group):
     mc = 0
     try:
         mc = int(h.multicast_ptr or 0)
-    except (AttributeError, RuntimeError):       # no NVLS multicast on this fabric / torch build
+    except Exception:  # noqa: BLE001 — hardware/driver probe: any failure just means no NVLS multicast here
         mc = 0
     return t, peer, sig, mc, h
 
