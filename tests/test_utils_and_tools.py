@@ -110,7 +110,7 @@ def test_eval_checkpoint_tool(tmp_path, capsys):
     assert 3.0 < loss < 7.0                                     # ~ln(128) = 4.85 for a random model
 
 
-@pytest.mark.parametrize("example,nproc", [("examples.simple_dp", 2), ("examples.simple_pp", 2), ("examples.simple_tp", 2),
+@pytest.mark.parametrize("example,nproc", [("examples.simple_pp", 2), ("examples.simple_tp", 2),   # simple_dp: README-line test below
                                            ("examples.full_3d", 8)])
 def test_examples_run_on_cpu(example, nproc):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
