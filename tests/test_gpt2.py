@@ -382,3 +382,6 @@ def test_3d_2x2x2_fused_wgrad_accumulation(monkeypatch):
     losses and parameters as the single-process loop under dp2 x tp2 x pp2 + ZeRO-1 + sequence parallelism."""
     monkeypatch.setenv("QUINTNET_FUSE_WGRAD_ACCUM", "1")
     run_distributed(_run_parallel, 8, [2, 2, 2], ["dp", "tp", "pp"], "1f1b", 1, True, 16, timeout=600)
+    # plain DDP (per-bucket all-reduce driven by the post-accumulate hooks): the mode in which calling the hook by hand
+    # would double-count and reduce buckets before their last gradient has arrived
+    run_distributed(_run_parallel, 8, [2, 2, 2], ["dp", "tp", "pp"], "1f1b", 0, False, timeout=600)
