@@ -59,6 +59,11 @@ class Hybrid3DCoordinator(BaseCoordinator):
         model_config = mc if isinstance(mc, GPT2Config) else GPT2Config.from_dict(dict(mc))
         if cfg.get("sequence_parallel") is not None:
             model_config.sequence_parallel = bool(cfg["sequence_parallel"])
+        elif pg.axis_size("tp") > 1 and "batch_size" in cfg:
+            # not specified: token-sharded TP (the fused AG->GEMM / GEMM->RS kernels need it) whenever the micro-batch
+            # splits evenly over the tp ranks
+            mb = int(cfg["batch_size"]) // max(int(cfg.get("grad_acc_steps", 1)) * pg.axis_size("dp"), 1)
+            model_config.sequence_parallel = mb >= pg.axis_size("tp") and mb % pg.axis_size("tp") == 0
         pp = pg.axis_size("pp")
         V = int(cfg.get("virtual_pipeline_stages", 1) or 1) if pp > 1 else 1
         n_stages = pp * V                     # virtual stage v * pp + rank lives on this rank (interleaved 1F1B)
