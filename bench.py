@@ -61,6 +61,16 @@ def parse_args():
     ap.add_argument("--sequence-parallel", type=int, default=None)
     ap.add_argument("--cpu", action="store_true", help="gloo/CPU plumbing run (tiny model)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-precision", default="both", choices=["fp32", "tf32", "bf16", "both"],
+                    help="reference arm: fp32 = as shipped; tf32 / bf16 = the UNMODIFIED reference step wrapped from "
+                         "outside in allow_tf32 / torch.autocast(bfloat16); both = fp32 line first, bf16 line last")
+    ap.add_argument("--dropout", type=float, default=0.1)
+    ap.add_argument("--parity-steps", type=int, default=0,
+                    help="parity mode: dropout 0, mesh-independent data order; run this many optimizer steps and "
+                         "write the per-step losses to --parity-out (compare two runs with --check-parity A B)")
+    ap.add_argument("--parity-out", default=None)
+    ap.add_argument("--check-parity", nargs=2, default=None, metavar=("A.json", "B.json"))
+    ap.add_argument("--parity-tol", type=float, default=2e-2)
     ap.add_argument("--workload", default="gpt2", choices=["gpt2", "vit"],
                     help="gpt2 = headline metric; vit = the reference's ViT-MNIST 3-D example config (secondary)")
     return ap.parse_args()
@@ -194,8 +204,8 @@ def build_config(args, mesh, impl):
     dp, tp, pp = mesh
     M = args.global_batch // (args.micro_batch * dp)
     assert M >= 1 and M * args.micro_batch * dp == args.global_batch
-    mc = dict(vocab_size=args.vocab, n_positions=1024, n_inner=None, attn_pdrop=0.1, embd_pdrop=0.1,
-              resid_pdrop=0.1, layer_norm_epsilon=1e-5, **MODELS[args.model])
+    mc = dict(vocab_size=args.vocab, n_positions=1024, n_inner=None, attn_pdrop=args.dropout, embd_pdrop=args.dropout,
+              resid_pdrop=args.dropout, layer_norm_epsilon=1e-5, **MODELS[args.model])
     mc["n_inner"] = 4 * mc["n_embd"]
     cfg = {
         "batch_size": args.global_batch, "learning_rate": 5e-5, "num_epochs": 1, "grad_acc_steps": M,
@@ -254,6 +264,17 @@ def sum_over_ranks(x: float, device):
     return float(t.item())
 
 
+def global_loss(loss, device):
+    """Mean of the step loss over the ranks that hold one (last pipeline stage of every dp replica), on every rank —
+    so rank 0 can report it at any mesh."""
+    import torch
+    import torch.distributed as dist
+    has = loss is not None
+    t = torch.tensor([float(loss) if has else 0.0, 1.0 if has else 0.0], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t[0].item() / t[1].item()) if t[1].item() > 0 else None
+
+
 def emit(args, mesh, M, ms_total, e2e, clocks, launches, impl, dtype, extra=None):
     dp, tp, pp = mesh
     tokens = args.global_batch * args.seq_len
@@ -292,13 +313,38 @@ def run_ours(args):
     model_config = GPT2Config.from_dict(cfg["model_config"])
     dp_rank = pg.axis_rank("dp")
     n_micro = M * 2
-    dev_batches = make_micro_batches(n_micro, args.micro_batch, args.seq_len, args.vocab, 1000 + dp_rank, False, device)
+    if args.parity_steps > 0:
+        # mesh-independent data: ONE seeded global batch of global_batch/micro_batch micro-batches; dp replica r takes
+        # micro-batches [r*M, (r+1)*M) — the union over replicas is the same set of tokens at every mesh
+        allb = make_micro_batches(M * mesh[0], args.micro_batch, args.seq_len, args.vocab, 4242, False, None)
+        dev_batches = [{k: v.to(device) for k, v in b.items()} for b in allb[dp_rank * M:(dp_rank + 1) * M]]
+    else:
+        dev_batches = make_micro_batches(n_micro, args.micro_batch, args.seq_len, args.vocab, 1000 + dp_rank, False, device)
     trainer = GPT2Trainer(model, ListLoader(dev_batches, args.micro_batch), None, cfg, pg, model_config)
 
     last = {}
 
     def step():
         last["loss"] = trainer.train_step()
+
+    if args.parity_steps > 0:
+        losses = []
+        for _ in range(args.parity_steps):
+            step()
+            lv = last["loss"][0] if last["loss"] is not None else None
+            losses.append(global_loss(lv, device))
+        if rank == 0:
+            rec = {"impl": "ours", "parity": True, "n_gpus": args.gpus, "mesh": list(mesh), "model": args.model,
+                   "steps": args.parity_steps, "losses": losses,
+                   "native_ops": sorted(native._enabled_set()) if native.available() else []}
+            print(json.dumps(rec), flush=True)
+            if args.parity_out:
+                os.makedirs(os.path.dirname(os.path.abspath(args.parity_out)), exist_ok=True)
+                with open(args.parity_out, "w") as f:
+                    json.dump(rec, f)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
 
     for _ in range(args.warmup):
         step()
@@ -329,10 +375,12 @@ def run_ours(args):
         tokens = args.global_batch * args.seq_len
         e2e = {"value": tokens / (ms_e / args.steps / 1e3), "unit": "tokens/s", "ms_per_step": ms_e / args.steps,
                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}
+    lv = last.get("loss")
+    last_loss = global_loss(lv[0] if lv is not None else None, device)
     if rank == 0:
         extra = {"zero_stage": cfg["zero_stage"], "sequence_parallel": cfg["sequence_parallel"],
                  "native_ops": sorted(native._enabled_set()) if native.available() else [],
-                 "last_loss": last.get("loss", (None, None))[0],
+                 "last_loss": last_loss,
                  "virtual_pipeline_stages": cfg.get("virtual_pipeline_stages", 1)}
         emit(args, mesh, M, ms, e2e, clocks, launches, "ours", "fp32" if args.cpu else "bf16", extra)
     dist.barrier()
@@ -411,22 +459,58 @@ def _run_reference(args, ref_root):
             trainer.train_loader = one_step
             trainer._train_epoch_standard(0)
 
-    for _ in range(args.warmup):
-        step()
-    sampler = ClockSampler(rank == 0, args.gpus)
-    sampler.start()
-    ms = timed_region(step, args.steps, device, False)
-    clocks = sampler.stop() if rank == 0 else None
-    ms = max_over_ranks(ms, device)
+    import contextlib
     tokens = args.global_batch * args.seq_len
     per_mb = args.micro_batch * args.seq_len * 8
-    if rank == 0:
-        # the reference's loop already copies every micro-batch from (pinned) host memory and reads the loss
-        # back with .item(): its device-timed number IS its end-to-end number
-        e2e = {"value": tokens / (ms / args.steps / 1e3), "unit": "tokens/s", "ms_per_step": ms / args.steps,
-               "h2d_bytes_per_step": int(per_mb * 3 * M * world), "d2h_bytes_per_step": int(8 * M * world)}
-        emit(args, mesh, M, ms, e2e, clocks, 0, "reference", "fp32",
-             {"note": "reference as shipped: fp32, torch ops (cuBLAS/SDPA) + NCCL; no DP gradient sync (its default)"})
+
+    def measure(precision):
+        """The SAME unmodified reference step, wrapped from outside: fp32 = as shipped; tf32 = allow_tf32; bf16 =
+        torch.autocast(bfloat16) around the reference's own forward/backward (no file under baseline/_ref is edited;
+        inter-stage tensors stay fp32 because residual adds / LayerNorm promote back to fp32 under autocast)."""
+        torch.backends.cuda.matmul.allow_tf32 = precision == "tf32"
+        torch.backends.cudnn.allow_tf32 = precision == "tf32"
+        ctx = (lambda: torch.autocast("cuda", dtype=torch.bfloat16)) if precision == "bf16" else contextlib.nullcontext
+
+        def pstep():
+            with ctx():
+                step()
+        for _ in range(args.warmup):
+            pstep()
+        sampler = ClockSampler(rank == 0, args.gpus)
+        sampler.start()
+        ms = timed_region(pstep, args.steps, device, False)
+        clocks = sampler.stop() if rank == 0 else None
+        return max_over_ranks(ms, device), clocks
+
+    precisions = ["fp32", "bf16"] if args.ref_precision == "both" else [args.ref_precision]
+    results, errors = {}, {}
+    for prec in precisions:
+        try:
+            results[prec] = measure(prec)
+        except Exception as e:  # noqa: BLE001 — the wrapped precision may be unsupported by the reference's own code
+            if prec == "fp32":
+                raise
+            errors[prec] = f"{type(e).__name__}: {str(e)[:160]}"
+    precisions = [q for q in precisions if q in results]
+    for i, prec in enumerate(precisions):
+        ms, clocks = results[prec]
+        if rank == 0:
+            # the reference's loop already copies every micro-batch from (pinned) host memory and reads the loss
+            # back with .item(): its device-timed number IS its end-to-end number
+            e2e = {"value": tokens / (ms / args.steps / 1e3), "unit": "tokens/s", "ms_per_step": ms / args.steps,
+                   "h2d_bytes_per_step": int(per_mb * 3 * M * world), "d2h_bytes_per_step": int(8 * M * world)}
+            note = {"fp32": "reference as shipped: fp32, torch ops (cuBLAS/SDPA) + NCCL; no DP gradient sync (its default)",
+                    "tf32": "unmodified reference, torch.backends.cuda.matmul.allow_tf32=True set by the harness",
+                    "bf16": "unmodified reference step wrapped by the harness in torch.autocast(cuda, bfloat16): "
+                            "cuBLAS bf16 GEMMs + SDPA, fp32 weights/optimizer; no DP gradient sync (its default)"}[prec]
+            others = {q: {"tokens_per_s": tokens / (results[q][0] / args.steps / 1e3),
+                          "ms_per_step": results[q][0] / args.steps} for q in precisions if q != prec}
+            extra = {"note": note, "ref_precision": prec}
+            if others:
+                extra["other_precisions"] = others
+            if errors:
+                extra["precision_errors"] = errors
+            emit(args, mesh, M, ms, e2e, clocks, 0, "reference", prec, extra)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -515,8 +599,23 @@ def run_vit(args):
     dist.destroy_process_group()
 
 
+def check_parity(a_path, b_path, tol):
+    a, b = json.load(open(a_path)), json.load(open(b_path))
+    la, lb = a["losses"], b["losses"]
+    n = min(len(la), len(lb))
+    diffs = [abs(x - y) for x, y in zip(la[:n], lb[:n])]
+    ok = n > 0 and all(d < tol for d in diffs)
+    print(json.dumps({"parity": "ok" if ok else "FAIL", "tol": tol, "max_abs_diff": max(diffs) if diffs else None,
+                      "a": {"mesh": a["mesh"], "losses": la}, "b": {"mesh": b["mesh"], "losses": lb}}), flush=True)
+    return 0 if ok else 1
+
+
 def main():
     args = parse_args()
+    if args.check_parity:
+        sys.exit(check_parity(args.check_parity[0], args.check_parity[1], args.parity_tol))
+    if args.parity_steps > 0:
+        args.dropout = 0.0
     if args.workload == "vit":
         return run_vit(args)
     if args.cpu and args.model != "gpt2-tiny":
