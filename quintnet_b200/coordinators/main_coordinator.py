@@ -29,6 +29,19 @@ def resolve_dtype(config: dict) -> torch.dtype:
     return v if isinstance(v, torch.dtype) else _DTYPES[str(v).lower()]
 
 
+def resolve_main_grad_dtype(config: dict) -> Optional[torch.dtype]:
+    """dtype of the gradient buckets when it differs from the parameter dtype.  Low-precision training (bf16 / fp16
+    parameters) accumulates micro-batch gradients and reduces them over DP in fp32 main-grad buckets by default
+    (``main_grad_dtype: float32``; set ``main_grad_dtype: param`` to accumulate in the parameter dtype)."""
+    if resolve_dtype(config) == torch.float32:
+        return None
+    v = config.get("main_grad_dtype", "float32")
+    if v is None or str(v).lower() in ("param", "none", "same"):
+        return None
+    dt = v if isinstance(v, torch.dtype) else _DTYPES[str(v).lower()]
+    return None if dt == resolve_dtype(config) else dt
+
+
 def resolve_device(pg_manager, config: Optional[dict] = None) -> torch.device:
     dt = (config or {}).get("device_type", getattr(pg_manager, "device_type", "cuda"))
     if dt == "cuda" and torch.cuda.is_available():
@@ -44,7 +57,8 @@ def wrap_data_parallel(model: nn.Module, pg_manager, config: dict) -> nn.Module:
     dist_cfg = DistributedConfig(rank=pg_manager.axis_rank("dp"), world_size=dp_size,
                                  process_group=pg_manager.get_group("dp"))
     bcfg = BucketConfig(capacity_mb=int(config.get("bucket_cap_mb", 25)),
-                        flatten_parameters=zero >= 1 or bool(config.get("flatten_parameters", False)))
+                        flatten_parameters=zero >= 1 or bool(config.get("flatten_parameters", False)),
+                        grad_dtype=resolve_main_grad_dtype(config))
     return DataParallel(model, dist_cfg, bcfg, reduce_mode="defer" if zero >= 1 else "all_reduce")
 
 

@@ -36,9 +36,12 @@ struct GemmParams {
   const __nv_bfloat16* bias;   // [N] or null
   int epilogue;
   int has_z;                   // EPI_BIAS_GELU: also store gelu'(z) through tmap_z (consumed by EPI_MUL_AUX)
+  uint32_t group_m;            // tile rasterisation: m-blocks per L2-reuse group (0 = kGroupM)
   uint32_t splits;             // split-K factor (>1: fp32 partials are atomically added into acc32)
   float* acc32;                // [M, ld32] fp32, zero-initialised by the caller
   uint32_t ld32;
+  int acc_f32;                 // the fp32 buffer IS the result (C += A·B in fp32, e.g. main-grad accumulation): every
+                               // work unit adds its accumulator with vector red.add, also when splits == 1
   // FP8 (e4m3) operands with row-wise scaling: A and B hold fp8 bytes (K counts byte PAIRS here, so every tile,
   // descriptor and TMA box is byte-identical to the bf16 path); C = (A8 · B8ᵀ) * scale_a[row] * scale_b[col]
   int fp8;
@@ -46,40 +49,50 @@ struct GemmParams {
   const float* scale_b;        // [N] dequantisation scale of each B row (= output column)
 };
 
-// Fused tensor-parallel collectives (FUSE template parameter of the kernel):
+// Fused tensor-parallel collectives (FUSE template parameter of the kernel).  Every byte that crosses NVLink is moved
+// by the TMA engine from inside the GEMM kernel (1-D bulk async copies on peer-mapped addresses), so no LSU
+// instruction, register or per-thread fence of the compute pipeline is spent on the transfer:
 //   FUSE_AG (K3): the A operand is the all-gather of every rank's row shard.  Local rows are read straight from
-//     x_local; warps 2-3 of every CTA PUSH this rank's shard into the peers' symmetric gather buffers over
-//     NVLink (plain 16-byte stores) and publish a per-32-row release flag; the TMA producer acquires the flags
-//     of a remote 128-row block before its first load.  Tiles are ordered local-rows-first, so the transfer
-//     hides behind the local half of the GEMM.
-//   FUSE_RS (K4): the output is reduce-scattered by rows.  Partial tiles whose rows belong to a peer are
-//     written from the epilogue into that peer's symmetric staging buffer (coalesced 16-byte NVLink stores) and
-//     flagged; tiles owned by this rank are processed LAST and their epilogue adds the peers' partials (TMA
-//     load from the local staging buffer after acquiring the flag) before the bias / store.
+//     x_local.  ONE thread per CTA (warp 3) is a copy pump: it bulk-loads 8-row units of this rank's shard into a
+//     small shared-memory ring and bulk-stores each unit into every peer's (and the local) symmetric gather
+//     buffer, publishing the unit's flag once its store group has completed.  148 pumps x 2 slots x 16 KB keep
+//     ~4.7 MB in flight — far more than the NVLink bandwidth-delay product — while each pump handles only ~7 units.
+//     The TMA producer acquires the 16 flags of a remote 128-row block before its first load; tiles are ordered
+//     local-rows-first, so the transfer hides behind the local half of the GEMM.
+//   FUSE_RS (K4): the output is reduce-scattered by rows.  Partial [32 x 64] slabs whose rows belong to a peer are
+//     staged in shared memory (the same swizzled image a TMA tile store would read) and bulk-stored as one 4 KB
+//     block into that peer's symmetric staging buffer; their flags are published lazily (two store groups behind)
+//     so the epilogue never waits for an NVLink round trip.  Tiles owned by this rank are processed LAST; their
+//     epilogue bulk-loads the peers' staged slabs (flag acquire -> 4 KB bulk load) while the accumulator is read
+//     from TMEM, adds them in fp32 and stores the tile.  Two staging buffers per epilogue warp.
 enum Fuse : int { FUSE_NONE = 0, FUSE_AG = 1, FUSE_RS = 2 };
 constexpr int TP_MAX = 8;
+enum AgMode : uint32_t { AG_PUMP = 0, AG_LSU = 1, AG_EXTERNAL = 2 };
 struct TpComm {
   int rank, world;
   uint32_t seq;                       // launch sequence number of this workspace (flags hold seq values)
   uint32_t rows_per_rank, mb_per_rank;
   const __nv_bfloat16* x_local;       // AG: [rows_per_rank, K] contiguous
   __nv_bfloat16* gather[TP_MAX];      // AG: every rank's gather buffer [M, K] (peer mappings)
-  uint32_t* ag_flags[TP_MAX];         // AG: every rank's per-32-row flags [M / 32]
-  __nv_bfloat16* stage[TP_MAX];       // RS: every rank's staging buffer [world][rows_per_rank][N]
-  uint32_t* rs_flags[TP_MAX];         // RS: every rank's flags [mb_per_rank][4][N/64][world]
-  uint32_t comm_ctas;                 // AG: the last `comm_ctas` CTAs of the grid only push (0: two push warps per CTA)
-  uint32_t external_push;             // AG: the shard was (is being) copied by someone else — copy engine on a side
-                                      // stream — who publishes ONE flag per source rank at ag_flags[kAgDoneBase + src]
+  uint32_t* ag_flags[TP_MAX];         // AG: every rank's per-8-row flags [M / 8]
+  __nv_bfloat16* stage[TP_MAX];       // RS: every rank's staging buffer [world][slabs_per_rank] x 4 KB slab images
+  uint32_t* rs_flags[TP_MAX];         // RS: every rank's flags [slabs_per_rank][world]
+  uint32_t ag_mode;                   // AG_PUMP: one bulk-copy pump thread per CTA (default); AG_LSU: two push warps
+                                      // per CTA with 16-byte stores (round-1 kernel, kept for A/B timing);
+                                      // AG_EXTERNAL: the shard is copied by someone else (copy engine on a side
+                                      // stream) who publishes ONE flag per source rank at ag_flags[kAgDoneBase + src]
   uint32_t debug;                     // QN_TP_DEBUG timing-attribution knobs (results are WRONG when set):
-                                      //   1 RS: skip the peer wait + add    2 RS: remote stores go to local memory
-                                      //   4 AG: skip the flag waits         8 AG: skip the push
+                                      //   1 RS: skip the peer wait + add    4 AG: skip the flag waits    8 AG: skip the push
 };
 
 constexpr uint32_t kAgDoneBase = 200000;      // flag index of the per-source "whole shard has landed" flags (external push)
+constexpr uint32_t kPumpSlot = 16384;         // AG pump: bytes per ring slot (one 8-row unit at K <= 1024)
+constexpr uint32_t kPumpRing = 2;
+constexpr uint32_t kSmemLimit = 232448;       // 227 KB per CTA on sm_100a
 
 QN_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <uint32_t BLOCK_N, bool CTA2 = false>
+template <uint32_t BLOCK_N, bool CTA2 = false, int FUSE = FUSE_NONE>
 struct Cfg {
   // CTA2: a pair of CTAs (cta_group::2) owns a 256 x BLOCK_N tile; each CTA stages its own 128 rows of A and HALF of
   // the B rows, so a pipeline stage is 32 KB instead of 48 KB per SM (a third less L2 -> SM traffic per flop).
@@ -87,18 +100,34 @@ struct Cfg {
   static constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;        // 16 KB
   static constexpr uint32_t B_BYTES = B_ROWS * BLOCK_K * 2;         // 16/32 KB
   static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr uint32_t EPI_BYTES = 8 * 4096;                   // 8 epilogue warps x (32 rows x 128 B)
-  static constexpr uint32_t kStages = (BLOCK_N == 256 && !CTA2) ? 4 : 6;
-  static constexpr uint32_t BAR_BYTES = 256;
-  static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + EPI_BYTES + BAR_BYTES + 1024;  // +align slack
+  static constexpr uint32_t EPI_PER_WARP = FUSE == FUSE_RS ? 8192 : 4096;   // RS: two (32 rows x 128 B) staging buffers
+  static constexpr uint32_t EPI_BYTES = 8 * EPI_PER_WARP;
+  static constexpr uint32_t RING_BYTES = FUSE == FUSE_AG ? kPumpRing * kPumpSlot : 0;
+  static constexpr uint32_t BAR_BYTES = 512;
+  static constexpr uint32_t FIXED_BYTES = EPI_BYTES + RING_BYTES + BAR_BYTES + 1024;   // +align slack
+  static constexpr uint32_t kStagesFit = (kSmemLimit - FIXED_BYTES) / STAGE_BYTES;
+  static constexpr uint32_t kStages = kStagesFit < 6 ? kStagesFit : 6;      // plain: 4 (256 x 1 CTA) / 6; fused: 3 / 5
+  static constexpr uint32_t SMEM_BYTES = kStages * STAGE_BYTES + FIXED_BYTES;
   static constexpr uint32_t TMEM_COLS = 2 * BLOCK_N;                // 256 / 512
+  static_assert(kStages >= 3, "pipeline too shallow");
 };
 
-QN_DEVICE void tile_coords(uint32_t tile, uint32_t tiles_m, uint32_t tiles_n, uint32_t& m_blk, uint32_t& n_blk) {
-  const uint32_t per_group = kGroupM * tiles_n;
+// Exit handshake of a CTA pair with a deadline: each CTA arrives on BOTH CTAs' exit barrier and waits on its own
+// (mbar_wait carries the cycle-counter watchdog), instead of an untimed barrier.cluster at the end of the kernel —
+// a CTA that left early (the round-1 hang) now traps its partner instead of hanging the GPU.
+QN_DEVICE void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+
+QN_DEVICE void tile_coords(uint32_t tile, uint32_t tiles_m, uint32_t tiles_n, uint32_t group_m, uint32_t& m_blk,
+                           uint32_t& n_blk) {
+  const uint32_t gm = group_m ? group_m : kGroupM;
+  const uint32_t per_group = gm * tiles_n;
   const uint32_t group = tile / per_group;
-  const uint32_t first_m = group * kGroupM;
-  const uint32_t gsize = min(tiles_m - first_m, kGroupM);
+  const uint32_t first_m = group * gm;
+  const uint32_t gsize = min(tiles_m - first_m, gm);
   const uint32_t in_group = tile - group * per_group;
   m_blk = first_m + in_group % gsize;
   n_blk = in_group / gsize;
@@ -109,86 +138,29 @@ __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_z,
                  const __grid_constant__ CUtensorMap tmap_x, const GemmParams p, const TpComm tc) {
-  using C = Cfg<BLOCK_N, CTA2>;
+  using C = Cfg<BLOCK_N, CTA2, FUSE>;
   constexpr uint32_t kStages = C::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_epi = smem + kStages * C::STAGE_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_epi + C::EPI_BYTES);
+  uint8_t* smem_ring = smem_epi + C::EPI_BYTES;                       // FUSE_AG: copy-pump ring
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_ring + C::RING_BYTES);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* aux_bar = tmem_empty + 2;          // [8] one per epilogue warp (EPI_MUL_AUX tile loads)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(aux_bar + 8);
+  uint64_t* aux_bar = tmem_empty + 2;          // [8] one per epilogue warp (aux / old-C / staged-partial tile loads)
+  uint64_t* pump_bar = aux_bar + 8;            // [kPumpRing] FUSE_AG copy pump
+  uint64_t* exit_bar = pump_bar + kPumpRing;   // CTA pair: exit handshake
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(exit_bar + 1);
+  static_assert((2 * 6 + 4 + 8 + kPumpRing + 1) * 8 + 4 <= C::BAR_BYTES, "barrier area too small");
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
-  // FUSE_AG with dedicated communication CTAs: the last `comm_ctas` CTAs never touch the tensor cores.  One
-  // thread per CTA pumps this rank's shard through a shared-memory ring with 1-D bulk async copies: load an
-  // 8-row unit, bulk-store it into every peer's gather buffer over NVLink and into the local one, and publish
-  // the unit's flag once its store group has completed.  Units are dealt round-robin over the comm CTAs, so the
-  // rows arrive in order and the consumers' remote tiles become ready progressively; no per-thread fences or
-  // register staging, and the compute CTAs' TMA / MMA pipelines do not share an SM with NVLink-bound stores.
-  const uint32_t n_comm = (FUSE == FUSE_AG) ? tc.comm_ctas : 0u;
   const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;               // 0 = leader of the CTA pair
-  const uint32_t n_cta = CTA2 ? gridDim.x / 2 : gridDim.x - n_comm;      // persistent workers (CTAs or CTA pairs)
+  const uint32_t n_cta = CTA2 ? gridDim.x / 2 : gridDim.x;               // persistent workers (CTAs or CTA pairs)
   const uint32_t worker = CTA2 ? blockIdx.x / 2 : blockIdx.x;
   constexpr uint32_t TILE_M = CTA2 ? 2 * BLOCK_M : BLOCK_M;
-  if constexpr (FUSE == FUSE_AG) {
-    if (n_comm > 0 && blockIdx.x >= n_cta) {            // (n_cta counts CTA PAIRS when CTA2: never take this path then)
-      // two pump threads per CTA (lane 0 of warps 0 and 1), each with its own ring
-      constexpr uint32_t kPumps = 2, kRing = 6, kAhead = 3, kLag = 12;
-      __shared__ uint64_t comm_full[kPumps][kRing];
-      if (threadIdx.x == 0) {
-        for (uint32_t i = 0; i < kPumps * kRing; ++i) mbar_init(&comm_full[0][0] + i, 1);
-        fence_barrier_init();
-      }
-      __syncthreads();
-      if (warp >= kPumps || lane != 0 || (tc.debug & 8u)) return;
-      const uint32_t units = tc.rows_per_rank / 8;
-      const uint32_t unit_bytes = 16u * p.K;                     // 8 rows x K bf16
-      const uint32_t g = (blockIdx.x - n_cta) * kPumps + warp, G = n_comm * kPumps;
-      const uint32_t mine = (units > g) ? (units - g + G - 1) / G : 0u;
-      const uint8_t* src = reinterpret_cast<const uint8_t*>(tc.x_local);
-      uint8_t* ring = smem + warp * kRing * unit_bytes;
-      uint64_t* full = comm_full[warp];
-      const size_t shard_off = static_cast<size_t>(tc.rank) * tc.rows_per_rank * p.K * 2;
-      uint32_t published = 0;
-      auto publish = [&](uint32_t upto) {                        // flags of units [published, upto)
-        fence_proxy_async_all();
-        __threadfence_system();
-        for (uint32_t k = published; k < upto; ++k)
-          for (int pr = 1; pr < tc.world; ++pr)
-            st_relaxed_sys(tc.ag_flags[(tc.rank + pr) % tc.world] + tc.rank * units + g + k * G, tc.seq);
-        published = upto;
-      };
-      for (uint32_t it = 0; it < mine + kAhead; ++it) {
-        if (it < mine) {                                         // load unit `it` into its ring slot
-          const uint32_t st = it % kRing;
-          tma_store_wait_read<kRing - kAhead - 1>();             // the stores that read this slot have drained it
-          mbar_arrive_expect_tx(&full[st], unit_bytes);
-          bulk_load_1d(ring + st * unit_bytes, src + static_cast<size_t>(g + it * G) * unit_bytes, unit_bytes, &full[st]);
-        }
-        if (it >= kAhead) {                                      // store unit j to every gather buffer
-          const uint32_t j = it - kAhead, st = j % kRing;
-          mbar_wait(&full[st], (j / kRing) & 1);
-          const size_t off = shard_off + static_cast<size_t>(g + j * G) * unit_bytes;
-          for (int pr = 0; pr < tc.world; ++pr)
-            bulk_store_1d(reinterpret_cast<uint8_t*>(tc.gather[(tc.rank + pr) % tc.world]) + off, ring + st * unit_bytes,
-                          unit_bytes);
-          tma_store_commit();
-          if ((j & 3u) == 3u && j >= kLag) {                     // every 4th unit: publish what has surely landed
-            tma_store_wait_all<kLag>();                          // groups <= j - kLag are complete (acked by the peer)
-            publish(j - kLag + 1);
-          }
-        }
-      }
-      tma_store_wait_all<0>();
-      publish(mine);
-      return;
-    }
-  }
   const uint32_t tiles_m = (p.M + TILE_M - 1) / TILE_M;
   const uint32_t tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const uint32_t num_tiles = tiles_m * tiles_n;
@@ -217,6 +189,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       mbar_init(&tmem_empty[i], CTA2 ? 16 : 8);        // CTA pair: the epilogue warps of BOTH CTAs release the leader
     }
     for (uint32_t i = 0; i < 8; ++i) mbar_init(&aux_bar[i], 1);
+    for (uint32_t i = 0; i < kPumpRing; ++i) mbar_init(&pump_bar[i], 1);
+    mbar_init(exit_bar, 2);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -235,7 +209,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t tile = work / splits, split = work - tile * splits;
         const uint32_t kb_begin = split * kb_per_split, kb_end = min(num_kb_total, kb_begin + kb_per_split);
         uint32_t m_blk, n_blk;
-        tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
+        tile_coords(tile, tiles_m, tiles_n, p.group_m, m_blk, n_blk);
         m_blk = (m_blk + m_shift) % tiles_m;
         // CTA pair: this CTA stages rows [rank*128, +128) of the 256-row A tile and B rows [rank*B_ROWS, +B_ROWS)
         const int32_t m0 = m_blk * TILE_M + cta_rank * BLOCK_M, n0 = n_blk * BLOCK_N + cta_rank * (CTA2 ? C::B_ROWS : 0u);
@@ -244,7 +218,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t mb128 = m_blk * kMbPerTile + cta_rank;          // this CTA's 128-row block of A
           a_remote = (mb128 / tc.mb_per_rank) != static_cast<uint32_t>(tc.rank);
           if (a_remote && !(tc.debug & 4u)) {   // the peer's pushes of these 128 rows must have landed
-            if (tc.external_push) {
+            if (tc.ag_mode == AG_EXTERNAL) {
               if (lane == 0) wait_flag_ge(tc.ag_flags[tc.rank] + kAgDoneBase + mb128 / tc.mb_per_rank, tc.seq);
             } else if (lane < 16) {
               wait_flag_ge(tc.ag_flags[tc.rank] + mb128 * 16 + lane, tc.seq);                // 16 8-row units in parallel
@@ -345,20 +319,71 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
-  } else if (FUSE == FUSE_AG && n_comm == 0 && !tc.external_push && (warp == 2 || warp == 3)) {
-    // ------------------------------------------------ all-gather push (this rank's shard -> every peer)
+  } else if (FUSE == FUSE_AG && warp == 3 && tc.ag_mode == AG_PUMP) {
+    // ------------------------------------------------ all-gather copy pump (this rank's shard -> every rank)
+    // One thread.  Units of 8 rows (16*K bytes, contiguous in x_local and in every gather buffer) are dealt
+    // round-robin over the CTAs; a unit moves in pieces of <= kPumpSlot bytes: bulk load -> ring slot -> one bulk
+    // store per destination (peers over NVLink + the local gather buffer, which then holds the complete gathered
+    // operand for the weight-gradient GEMM).  A unit's flag is published when its store groups have COMPLETED
+    // (cp.async.bulk.wait_group without .read: the writes are performed), two groups behind the pump head.
+    if (lane == 0 && !(tc.debug & 8u)) {
+      const uint32_t units = tc.rows_per_rank / 8;
+      const uint32_t unit_bytes = 16u * p.K;
+      const uint32_t npiece = (unit_bytes + kPumpSlot - 1) / kPumpSlot;
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(tc.x_local);
+      const size_t shard_off = static_cast<size_t>(tc.rank) * tc.rows_per_rank * p.K * 2;
+      uint32_t cnt = 0;                              // pieces issued (= store groups committed)
+      uint32_t pend_u[3] = {0, 0, 0}, pend_g[3] = {0, 0, 0}, npend = 0;   // units whose last group is not yet known complete
+      auto publish = [&](uint32_t u) {
+        for (int pr = 1; pr < tc.world; ++pr)
+          st_relaxed_sys(tc.ag_flags[(tc.rank + pr) % tc.world] + tc.rank * units + u, tc.seq);
+      };
+      for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+        for (uint32_t pc = 0; pc < npiece; ++pc) {
+          const uint32_t off_in_unit = pc * kPumpSlot;
+          const uint32_t bytes = min(kPumpSlot, unit_bytes - off_in_unit);
+          const size_t off = static_cast<size_t>(u) * unit_bytes + off_in_unit;
+          const uint32_t slot = cnt % kPumpRing;
+          uint8_t* buf = smem_ring + slot * kPumpSlot;
+          tma_store_wait_read<kPumpRing - 1>();      // the stores that last read this slot have drained it
+          mbar_arrive_expect_tx(&pump_bar[slot], bytes);
+          bulk_load_1d(buf, src + off, bytes, &pump_bar[slot]);
+          mbar_wait(&pump_bar[slot], (cnt / kPumpRing) & 1);
+          for (int pr = 1; pr <= tc.world; ++pr)     // peers first, the local copy last
+            bulk_store_1d(reinterpret_cast<uint8_t*>(tc.gather[(tc.rank + pr) % tc.world]) + shard_off + off, buf, bytes);
+          tma_store_commit();
+          ++cnt;
+        }
+        // lazily publish: keep up to 3 units pending; the oldest one's groups are complete once at most 2 newer
+        // groups are outstanding
+        if (npend == 3) {
+          tma_store_wait_all<2>();                   // groups <= cnt - 3 complete; pend_g[0] <= cnt - 3 by construction
+          fence_proxy_async_all();
+          __threadfence_system();
+          publish(pend_u[0]);
+          pend_u[0] = pend_u[1]; pend_g[0] = pend_g[1]; pend_u[1] = pend_u[2]; pend_g[1] = pend_g[2];
+          npend = 2;
+        }
+        pend_u[npend] = u; pend_g[npend] = cnt; ++npend;
+      }
+      if (npend) {
+        tma_store_wait_all<0>();
+        fence_proxy_async_all();
+        __threadfence_system();
+        for (uint32_t i = 0; i < npend; ++i) publish(pend_u[i]);
+      }
+    }
+  } else if (FUSE == FUSE_AG && tc.ag_mode == AG_LSU && (warp == 2 || warp == 3)) {
+    // ------------------------------------------------ round-1 all-gather push with 16-byte LSU stores (A/B timing only)
     const uint32_t units = tc.rows_per_rank / 32;
     const uint32_t vec_per_unit = 32 * p.K / 8;                 // 16-byte vectors per 32-row unit
     for (uint32_t u = blockIdx.x * 2 + (warp - 2); u < units && !(tc.debug & 8u); u += gridDim.x * 2) {
       const uint4* src = reinterpret_cast<const uint4*>(tc.x_local + static_cast<size_t>(u) * 32 * p.K);
       const size_t dst_off = (static_cast<size_t>(tc.rank) * tc.rows_per_rank + u * 32) * p.K;
-      // 16 x 16 B in flight per lane: the copy is latency-bound per warp, so depth is what shortens it
       for (uint32_t i = lane; i < vec_per_unit; i += 32 * 16) {
         uint4 v[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) if (i + j * 32 < vec_per_unit) v[j] = ld_nc_v4(src + i + j * 32);
-        // pr = 0 is this rank's own gather buffer: after the kernel it holds the complete gathered operand,
-        // which the weight-gradient GEMM reads in place (no host-side reassembly copies)
         for (int pr = 0; pr < tc.world; ++pr) {
           uint4* dst = reinterpret_cast<uint4*>(tc.gather[(tc.rank + pr) % tc.world] + dst_off);
 #pragma unroll
@@ -378,28 +403,33 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const uint32_t q = (warp - kEpiWarp0) & 3;
     const uint32_t half = (warp - kEpiWarp0) >> 2;
     constexpr uint32_t kChunks = BLOCK_N / 64;
-    uint8_t* sbuf = smem_epi + (warp - kEpiWarp0) * 4096;
+    uint8_t* sbuf = smem_epi + (warp - kEpiWarp0) * C::EPI_PER_WARP;
     uint8_t* srow = sbuf + lane * 128;
     uint32_t as = 0, aphase = 0, aux_phase = 0;
-    // FUSE_RS: flags of slabs already stored to a peer but not yet published (one system fence per 4 slabs)
+    // FUSE_RS: slab counter (staging buffer = slab & 1; every slab commits exactly one bulk group) and the flags of
+    // remote slabs whose store group is not yet known to be complete (published two groups behind, one fence per pair)
+    uint32_t rs_slab = 0;
     uint32_t* pend0 = nullptr; uint32_t* pend1 = nullptr; uint32_t* pend2 = nullptr; uint32_t* pend3 = nullptr;
     uint32_t npend = 0;
-    auto flush_pending = [&]() {
+    auto publish_pending = [&](bool all) {     // lane 0 only
       if (npend == 0) return;
+      if (all) tma_store_wait_all<0>(); else tma_store_wait_all<2>();   // !all: called with 4 pending -> the oldest 2 are complete
+      fence_proxy_async_all();
       __threadfence_system();
-      __syncwarp();
-      if (lane == 0) {                       // one fence above covers all four flags
-        st_relaxed_sys(pend0, tc.seq);
-        if (npend > 1) st_relaxed_sys(pend1, tc.seq);
+      st_relaxed_sys(pend0, tc.seq);
+      if (npend > 1) st_relaxed_sys(pend1, tc.seq);
+      if (all) {
         if (npend > 2) st_relaxed_sys(pend2, tc.seq);
         if (npend > 3) st_relaxed_sys(pend3, tc.seq);
+        npend = 0;
+      } else {
+        pend0 = pend2; pend1 = pend3; npend -= 2;
       }
-      npend = 0;
     };
     for (uint32_t work = worker; work < num_work; work += n_cta) {
       const uint32_t tile = work / splits;
       uint32_t m_blk, n_blk;
-      tile_coords(tile, tiles_m, tiles_n, m_blk, n_blk);
+      tile_coords(tile, tiles_m, tiles_n, p.group_m, m_blk, n_blk);
       m_blk = (m_blk + m_shift) % tiles_m;
       const uint32_t m0 = m_blk * TILE_M + cta_rank * BLOCK_M + q * 32, n0 = n_blk * BLOCK_N;
       mbar_wait(&tmem_full[as], aphase);
@@ -410,11 +440,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t nc = n0 + chunk * 64;
         if (nc >= p.N) break;                          // warp-uniform
         const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BLOCK_N + chunk * 64;
-        // the TMA store that last read this staging buffer must have finished reading it
-        if (lane == 0) tma_store_wait_read<0>();
-        __syncwarp();
-        if (p.splits > 1) {
-          // split-K: fp32 partial of this K-slice -> vectorised atomics into the fp32 accumulator
+        // the TMA store that last read this staging buffer must have finished reading it (FUSE_RS double-buffers
+        // its staging and waits inside its own branch)
+        if constexpr (FUSE != FUSE_RS) {
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+        if (p.splits > 1 || p.acc_f32) {
+          // split-K / fp32 accumulation: fp32 partial of this K-slice -> vectorised atomics into the fp32 buffer
           const uint32_t row = m0 + lane;
 #pragma unroll
           for (uint32_t hcol = 0; hcol < 2; ++hcol) {
@@ -440,13 +473,35 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t owner = mb128 / tc.mb_per_rank;
           const uint32_t m_loc = m0 - owner * tc.rows_per_rank;          // first row of this warp's slab in the owner's shard
           const uint32_t n_chunks = (p.N + 63) / 64;
-          const uint32_t fidx = (((mb128 % tc.mb_per_rank) * 4 + q) * n_chunks + (nc >> 6)) * tc.world;
+          const uint32_t slab_id = ((mb128 % tc.mb_per_rank) * 4 + q) * n_chunks + (nc >> 6);
+          const uint32_t slabs_per_rank = tc.mb_per_rank * 4 * n_chunks;
+          const bool mine = owner == static_cast<uint32_t>(tc.rank);
+          uint8_t* obuf = sbuf + (rs_slab & 1u) * 4096;                  // output staging of this slab
+          uint8_t* pbuf = sbuf + ((rs_slab & 1u) ^ 1u) * 4096;           // landing zone of the peers' staged partials
+          uint8_t* orow = obuf + lane * 128;
+          uint64_t* ab = &aux_bar[warp - kEpiWarp0];
+          ++rs_slab;
+          if (lane == 0) {
+            if (mine && !(tc.debug & 1u)) {
+              publish_pending(true);               // everything this warp sent is visible before it starts waiting
+              tma_store_wait_read<0>();            // both staging buffers are free
+              const uint32_t src = (tc.rank + 1) % tc.world;       // first peer's partial: load overlaps the TMEM read
+              wait_flag_ge(tc.rs_flags[tc.rank] + slab_id * tc.world + src, tc.seq);
+              fence_proxy_async_all();
+              mbar_arrive_expect_tx(ab, 4096);
+              bulk_load_1d(pbuf, reinterpret_cast<const uint8_t*>(tc.stage[tc.rank]) +
+                                     (static_cast<size_t>(src) * slabs_per_rank + slab_id) * 4096, 4096, ab);
+            } else {
+              tma_store_wait_read<1>();            // the group that last read obuf (two slabs ago) has drained it
+            }
+          }
+          __syncwarp();
           uint32_t acc[64];
           tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&acc[0]));
           tmem_ld_32x32b_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&acc[32]));
           tmem_ld_wait();
           float* f = reinterpret_cast<float*>(acc);
-          if (p.bias != nullptr) {                                     // bias rides on the partial of the rank that owns it
+          if (p.bias != nullptr) {       // the bias lives on ONE rank (tp-rank 0) and rides on every partial slab of that rank
 #pragma unroll
             for (uint32_t v = 0; v < 8; ++v) {
               if (nc + v * 8 < p.N) {
@@ -457,28 +512,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               }
             }
           }
-          if (owner == static_cast<uint32_t>(tc.rank) && !(tc.debug & 1u)) {
-            flush_pending();     // everything this warp sent must be visible before it starts waiting
-            // reduce: add every peer's partial of this [32 x 64] slab (flag acquire -> TMA load -> smem)
-            uint64_t* ab = &aux_bar[warp - kEpiWarp0];
+          if (mine && !(tc.debug & 1u)) {
+            // reduce: add every peer's staged partial of this [32 x 64] slab (same swizzled image the sender staged)
+            const uint8_t* prow = pbuf + lane * 128;
             for (int pr = 1; pr < tc.world; ++pr) {
-              const uint32_t src = (tc.rank + pr) % tc.world;
-              if (lane == 0) {
-                wait_flag_ge(tc.rs_flags[tc.rank] + fidx + src, tc.seq);
-                fence_proxy_async_all();
-                mbar_arrive_expect_tx(ab, 4096);
-                tma_load_2d(sbuf, &tmap_x, ab, static_cast<int32_t>(nc), static_cast<int32_t>(src * tc.rows_per_rank + m_loc));
-              }
               mbar_wait(ab, aux_phase);
               aux_phase ^= 1;
 #pragma unroll
               for (uint32_t v = 0; v < 8; ++v) {
-                const uint4 a4 = *reinterpret_cast<const uint4*>(srow + ((v ^ (lane & 7)) << 4));
+                const uint4 a4 = *reinterpret_cast<const uint4*>(prow + ((v ^ (lane & 7)) << 4));
                 const float2 a0 = unpack_bf16(a4.x), a1 = unpack_bf16(a4.y), a2 = unpack_bf16(a4.z), a3 = unpack_bf16(a4.w);
                 f[v * 8 + 0] += a0.x; f[v * 8 + 1] += a0.y; f[v * 8 + 2] += a1.x; f[v * 8 + 3] += a1.y;
                 f[v * 8 + 4] += a2.x; f[v * 8 + 5] += a2.y; f[v * 8 + 6] += a3.x; f[v * 8 + 7] += a3.y;
               }
               __syncwarp();
+              if (pr + 1 < tc.world && lane == 0) {                 // next peer's partial into the same landing zone
+                const uint32_t src = (tc.rank + pr + 1) % tc.world;
+                wait_flag_ge(tc.rs_flags[tc.rank] + slab_id * tc.world + src, tc.seq);
+                fence_proxy_async_all();
+                mbar_arrive_expect_tx(ab, 4096);
+                bulk_load_1d(pbuf, reinterpret_cast<const uint8_t*>(tc.stage[tc.rank]) +
+                                       (static_cast<size_t>(src) * slabs_per_rank + slab_id) * 4096, 4096, ab);
+              }
             }
           }
 #pragma unroll
@@ -486,31 +541,23 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             uint4 pk;
             pk.x = pack_bf16(f[v * 8 + 0], f[v * 8 + 1]); pk.y = pack_bf16(f[v * 8 + 2], f[v * 8 + 3]);
             pk.z = pack_bf16(f[v * 8 + 4], f[v * 8 + 5]); pk.w = pack_bf16(f[v * 8 + 6], f[v * 8 + 7]);
-            *reinterpret_cast<uint4*>(srow + ((v ^ (lane & 7)) << 4)) = pk;
+            *reinterpret_cast<uint4*>(orow + ((v ^ (lane & 7)) << 4)) = pk;
           }
-          if (owner == static_cast<uint32_t>(tc.rank)) {
-            fence_proxy_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              tma_store_2d(&tmap_c, sbuf, static_cast<int32_t>(nc), static_cast<int32_t>(m_loc));
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            if (mine) {
+              tma_store_2d(&tmap_c, obuf, static_cast<int32_t>(nc), static_cast<int32_t>(m_loc));
               tma_store_commit();
+            } else {
+              // scatter: ONE 4 KB bulk store of the slab image into the owner's staging buffer over NVLink
+              bulk_store_1d(reinterpret_cast<uint8_t*>(tc.stage[owner]) +
+                                (static_cast<size_t>(tc.rank) * slabs_per_rank + slab_id) * 4096, obuf, 4096);
+              tma_store_commit();
+              uint32_t* fl = tc.rs_flags[owner] + slab_id * tc.world + tc.rank;
+              if (npend == 0) pend0 = fl; else if (npend == 1) pend1 = fl; else if (npend == 2) pend2 = fl; else pend3 = fl;
+              if (++npend == 4) publish_pending(false);
             }
-          } else {
-            // scatter: coalesced 16-byte NVLink stores of the bf16 partial slab into the owner's staging buffer
-            __syncwarp();
-            const uint32_t tgt = (tc.debug & 2u) ? static_cast<uint32_t>(tc.rank) : owner;
-            __nv_bfloat16* dst = tc.stage[tgt] + (static_cast<size_t>(tc.rank) * tc.rows_per_rank + m_loc) * p.N + nc;
-#pragma unroll
-            for (uint32_t i = 0; i < 8; ++i) {
-              const uint32_t r = i * 4 + (lane >> 3), c = lane & 7;
-              if (nc + c * 8 < p.N) {
-                const uint4 v = *reinterpret_cast<const uint4*>(sbuf + r * 128 + ((c ^ (r & 7)) << 4));
-                st_v4(dst + static_cast<size_t>(r) * p.N + c * 8, v);
-              }
-            }
-            uint32_t* fl = tc.rs_flags[tgt] + fidx + tc.rank;
-            if (npend == 0) pend0 = fl; else if (npend == 1) pend1 = fl; else if (npend == 2) pend2 = fl; else pend3 = fl;
-            if (++npend == 4) flush_pending();
           }
           continue;
         }
@@ -658,12 +705,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if constexpr (FUSE == FUSE_RS) flush_pending();
+    if constexpr (FUSE == FUSE_RS) { if (lane == 0) publish_pending(true); }
     if (lane == 0) tma_store_wait_all<0>();
   }
 
   tcgen05_fence_before();
-  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // the peer may still read this CTA's smem / signal its barriers
+  __syncthreads();
+  if constexpr (CTA2) {     // the partner may still read this CTA's smem / signal its barriers: leave together (timed)
+    if (threadIdx.x == 0) {
+      mbar_arrive_cluster(exit_bar, 0);
+      mbar_arrive_cluster(exit_bar, 1);
+      mbar_wait(exit_bar, 0);
+    }
+    __syncthreads();
+  }
   if (warp == 2) {
     tcgen05_fence_after();
     if constexpr (CTA2) tmem_dealloc_2cta<C::TMEM_COLS>(tmem_base); else tmem_dealloc<C::TMEM_COLS>(tmem_base);
@@ -732,8 +787,8 @@ static bool use_cta_pairs(int M, int N, int block_n, int splits, int max_ctas) {
 template <bool A_MN, bool B_MN, int FUSE = FUSE_NONE, bool ACCUM = false>
 static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tz,
                        const GemmParams& p, cudaStream_t stream, const CUtensorMap* tx = nullptr,
-                       const TpComm* comm = nullptr) {
-  using C = Cfg<256, true>;
+                       const TpComm* comm = nullptr, int max_ctas = 0) {
+  using C = Cfg<256, true, FUSE>;
   auto kern = gemm_bf16_kernel<256, A_MN, B_MN, FUSE, true, ACCUM>;
   static bool configured = false;
   if (!configured) {
@@ -747,7 +802,8 @@ static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
   }
   const uint32_t tiles = ((p.M + 255) / 256) * ((p.N + 255) / 256) * (p.splits > 1 ? p.splits : 1);
-  const uint32_t pairs = static_cast<uint32_t>(g_num_sms / 2);
+  uint32_t pairs = static_cast<uint32_t>(g_num_sms / 2);
+  if (max_ctas > 1 && static_cast<uint32_t>(max_ctas / 2) < pairs) pairs = static_cast<uint32_t>(max_ctas / 2);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(2 * (tiles < pairs ? tiles : pairs), 1, 1);
   cfg.blockDim = dim3(kNumThreads, 1, 1);
@@ -768,7 +824,7 @@ template <uint32_t BLOCK_N, bool A_MN, bool B_MN, int FUSE = FUSE_NONE, bool ACC
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tz,
                   const GemmParams& p, int max_ctas, cudaStream_t stream, const CUtensorMap* tx = nullptr,
                   const TpComm* comm = nullptr) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, false, FUSE>;
   auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, FUSE, false, ACCUM>;
   static bool configured = false;
   if (!configured) {
@@ -786,12 +842,6 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMa
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   TpComm c0{};
   if (FUSE != FUSE_NONE && comm == nullptr) return 914;
-  if (FUSE == FUSE_AG && comm->comm_ctas > 0) {              // compute CTAs + dedicated communication CTAs
-    const int ncomm = static_cast<int>(comm->comm_ctas);
-    const int avail = (max_ctas > 0 && max_ctas < g_num_sms ? max_ctas : g_num_sms) - ncomm;
-    if (avail < 1) return 917;
-    grid = (static_cast<int>(tiles) < avail ? static_cast<int>(tiles) : avail) + ncomm;
-  }
   kern<<<grid, kNumThreads, C::SMEM_BYTES, stream>>>(ta, tb, tc, tz, tx ? *tx : tc, p, comm ? *comm : c0);
   return static_cast<int>(cudaGetLastError());
 }
@@ -941,12 +991,10 @@ extern "C" int qn_gemm_bf16_splitk(const void* a, const void* b, void* c, float*
 
 // ------------------------------------------------------------------------------- fused TP entry points
 namespace qn {
-constexpr uint32_t kDefaultCommCtas = 0;
-// CTA pairs inside the fused AG / RS kernels: implemented but NOT yet validated on hardware (the first attempt
-// hung on a since-fixed early-return bug and exhausted the round's GPU budget) -> opt-in only, QN_TP_2CTA=1.
+// CTA pairs inside the fused AG / RS kernels: default on (QN_TP_2CTA=0 falls back to single-CTA tiles)
 static bool tp_cta_pairs() {
-  static const bool on = [] { const char* e = getenv("QN_TP_2CTA"); return e && atoi(e) != 0; }();
-  return on;
+  const char* e = getenv("QN_TP_2CTA");
+  return e ? atoi(e) != 0 : true;
 }
 static int fill_comm(TpComm& c, int rank, int world, unsigned seq, int M) {
   if (world < 2 || world > TP_MAX || M % (128 * world)) return 915;
@@ -954,13 +1002,16 @@ static int fill_comm(TpComm& c, int rank, int world, unsigned seq, int M) {
   c.rows_per_rank = M / world; c.mb_per_rank = c.rows_per_rank / 128;
   const char* dbg = getenv("QN_TP_DEBUG");
   c.debug = dbg ? static_cast<uint32_t>(atoi(dbg)) : 0u;
-  const char* cc = getenv("QN_TP_COMM_CTAS");
-  c.comm_ctas = cc ? static_cast<uint32_t>(atoi(cc)) : kDefaultCommCtas;
-  if (c.comm_ctas > 64) c.comm_ctas = 64;
-  const char* ext = getenv("QN_TP_AG_MODE");                 // "ce": the Python side copies with the copy engine
-  c.external_push = (ext && ext[0] == 'c') ? 1u : 0u;
-  if (c.external_push) c.comm_ctas = 0;
+  const char* mode = getenv("QN_TP_AG_MODE");                // "pump" (default) | "lsu" | "ce" (copy engine, Python side)
+  c.ag_mode = (mode && mode[0] == 'c') ? AG_EXTERNAL : (mode && mode[0] == 'l') ? AG_LSU : AG_PUMP;
   return 0;
+}
+// m-blocks per rasterisation group: the largest of 8/4/2/1 that divides the tile rows of one rank, so that no group
+// straddles an ownership boundary (remote-before-own ordering of FUSE_RS / own-before-remote of FUSE_AG stays strict
+// for every persistent worker — a straddling group could interleave waits and sends of two ranks into a cycle)
+static uint32_t fused_group_m(uint32_t tile_rows_per_rank) {
+  for (uint32_t g = 8; g > 1; g >>= 1) if (tile_rows_per_rank % g == 0) return g;
+  return 1;
 }
 }  // namespace qn
 
@@ -976,8 +1027,7 @@ extern "C" int qn_gemm_ag_bf16(const void* x_local, void* const* gather, void* c
   if (int rc = fill_comm(comm, rank, world, seq, M)) return rc;
   if ((K % 8) || (ldb % 8) || (ldc % 8)) return 910;
   comm.x_local = static_cast<const __nv_bfloat16*>(x_local);
-  if (comm.comm_ctas && (12ll * 16 * K > 192 * 1024 || (reinterpret_cast<uintptr_t>(x_local) & 15)))
-    comm.comm_ctas = 0;                                        // ring slot = 8 rows x K must fit 8-deep in smem
+  if (reinterpret_cast<uintptr_t>(x_local) & 15) return 910;
   for (int r = 0; r < world; ++r) {
     comm.gather[r] = static_cast<__nv_bfloat16*>(gather[r]);
     comm.ag_flags[r] = static_cast<uint32_t*>(ag_flags[r]);
@@ -993,15 +1043,15 @@ extern "C" int qn_gemm_ag_bf16(const void* x_local, void* const* gather, void* c
   int rc;
   if ((rc = make_tmap(&ta, x_local, comm.rows_per_rank, K, K, 64, BLOCK_M))) return rc;
   if ((rc = make_tmap(&tx, gather[rank], M, K, K, 64, BLOCK_M))) return rc;
-  const bool two_cta = tp_cta_pairs() && comm.comm_ctas == 0 && (comm.rows_per_rank % 256) == 0 &&
-                       use_cta_pairs(M, N, block_n, 1, max_ctas);
+  const bool two_cta = tp_cta_pairs() && (comm.rows_per_rank % 256) == 0 && use_cta_pairs(M, N, block_n, 1, 0);
+  p.group_m = fused_group_m(comm.mb_per_rank / (two_cta ? 2 : 1));
   if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, two_cta ? 128 : block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
   if (rc) return rc;
   if ((rc = make_tmap(&tcm, c, M, N, ldc, 64, 32))) return rc;
   if (p.has_z || epilogue == EPI_MUL_AUX) { if ((rc = make_tmap(&tz, z, M, N, ldz, 64, 32))) return rc; } else tz = tcm;
   if (two_cta) {
-    if (!b_mn) return launch_2cta<false, false, FUSE_AG>(ta, tb, tcm, tz, p, stream, &tx, &comm);
-    return launch_2cta<false, true, FUSE_AG>(ta, tb, tcm, tz, p, stream, &tx, &comm);
+    if (!b_mn) return launch_2cta<false, false, FUSE_AG>(ta, tb, tcm, tz, p, stream, &tx, &comm, max_ctas);
+    return launch_2cta<false, true, FUSE_AG>(ta, tb, tcm, tz, p, stream, &tx, &comm, max_ctas);
   }
   if (block_n == 256) {
     if (!b_mn) return launch<256, false, false, FUSE_AG>(ta, tb, tcm, tz, p, max_ctas, stream, &tx, &comm);
@@ -1012,8 +1062,8 @@ extern "C" int qn_gemm_ag_bf16(const void* x_local, void* const* gather, void* c
 }
 
 // K4  GEMM -> reduce-scatter:  C_local[M/world, N] = sum_ranks( A[M, K] · B ) rows of this rank (+ bias)
-//   stage[r] / rs_flags[r]: rank r's symmetric staging buffer [world][M/world][N] and flags
-//   [(M/world/128) * 4 * ceil(N/64) * world] (host arrays of peer-mapped pointers).
+//   stage[r] / rs_flags[r]: rank r's symmetric staging buffer — [world][M/world/32 * ceil(N/64)] slab images of 4 KB —
+//   and flags [(M/world/128) * 4 * ceil(N/64) * world] (host arrays of peer-mapped pointers).
 extern "C" int qn_gemm_rs_bf16(const void* a, const void* b, void* c_local, void* const* stage, void* const* rs_flags,
                                int rank, int world, unsigned seq, int M, int N, int K, long long lda, long long ldb,
                                long long ldc, int b_mn, const void* bias, int block_n, int max_ctas,
@@ -1031,17 +1081,18 @@ extern "C" int qn_gemm_rs_bf16(const void* a, const void* b, void* c_local, void
   p.M = M; p.N = N; p.K = K;
   p.bias = static_cast<const __nv_bfloat16*>(bias);
   p.epilogue = bias ? EPI_BIAS : EPI_NONE;
-  CUtensorMap ta, tb, tcm, tx;
+  CUtensorMap ta, tb, tcm;
   int rc;
   if ((rc = make_tmap(&ta, a, M, K, lda, 64, BLOCK_M))) return rc;
-  const bool two_cta = tp_cta_pairs() && (comm.rows_per_rank % 256) == 0 && use_cta_pairs(M, N, block_n, 1, max_ctas);
+  const bool two_cta = tp_cta_pairs() && (comm.rows_per_rank % 256) == 0 && use_cta_pairs(M, N, block_n, 1, 0);
+  p.group_m = fused_group_m(comm.mb_per_rank / (two_cta ? 2 : 1));
   if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, two_cta ? 128 : block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
   if (rc) return rc;
   if ((rc = make_tmap(&tcm, c_local, comm.rows_per_rank, N, ldc, 64, 32))) return rc;
-  if ((rc = make_tmap(&tx, stage[rank], static_cast<uint64_t>(world) * comm.rows_per_rank, N, N, 64, 32))) return rc;
+  const CUtensorMap& tx = tcm;                 // unused by FUSE_RS (staged slabs move as raw 4 KB bulk copies)
   if (two_cta) {
-    if (!b_mn) return launch_2cta<false, false, FUSE_RS>(ta, tb, tcm, tcm, p, stream, &tx, &comm);
-    return launch_2cta<false, true, FUSE_RS>(ta, tb, tcm, tcm, p, stream, &tx, &comm);
+    if (!b_mn) return launch_2cta<false, false, FUSE_RS>(ta, tb, tcm, tcm, p, stream, &tx, &comm, max_ctas);
+    return launch_2cta<false, true, FUSE_RS>(ta, tb, tcm, tcm, p, stream, &tx, &comm, max_ctas);
   }
   if (block_n == 256) {
     if (!b_mn) return launch<256, false, false, FUSE_RS>(ta, tb, tcm, tcm, p, max_ctas, stream, &tx, &comm);
@@ -1114,6 +1165,36 @@ extern "C" int qn_write_flag(void* flag_base, long long index, unsigned value, c
   return static_cast<int>(cudaGetLastError());
 }
 extern "C" int qn_ag_done_base() { return static_cast<int>(qn::kAgDoneBase); }
+
+// Weight-gradient accumulation into an fp32 MAIN-GRAD buffer:  G[M, N] (fp32) += Aᵀ-stored · B-stored  (a: [K, M],
+// b: [K, N], both MN-major).  Every work unit (tile x K-slice) adds its TMEM accumulator straight into G with vector
+// red.global.add.f32 — the same epilogue split-K uses — so micro-batch gradients accumulate in fp32 with no zeroing,
+// no conversion pass and no elementwise add, and split-K comes for free.
+extern "C" int qn_gemm_bf16_wgrad_accum_f32(const void* a, const void* b, float* g32, int M, int N, int K, long long lda,
+                                            long long ldb, long long ldg, int splits, int block_n, cudaStream_t stream) {
+  using namespace qn;
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  if ((lda % 8) || (ldb % 8) || (ldg % 4) || (N % 4) || (reinterpret_cast<uintptr_t>(g32) & 15)) return 910;
+  if (block_n == 0) block_n = N > 128 ? 256 : 128;
+  const int num_kb = (K + 63) / 64;
+  if (splits > num_kb) splits = num_kb;
+  if (splits < 1) splits = 1;
+  {
+    const int per = (num_kb + splits - 1) / splits;
+    splits = (num_kb + per - 1) / per;
+  }
+  GemmParams p{};
+  p.M = M; p.N = N; p.K = K;
+  p.epilogue = EPI_NONE;
+  p.splits = splits; p.acc32 = g32; p.ld32 = static_cast<uint32_t>(ldg); p.acc_f32 = 1;
+  CUtensorMap ta, tb;
+  int rc;
+  if ((rc = make_tmap(&ta, a, K, M, lda, 64, BLOCK_K))) return rc;
+  if ((rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K))) return rc;
+  if (use_cta_pairs(M, N, block_n, splits, 0)) return launch_2cta<true, true>(ta, tb, ta, ta, p, stream);
+  if (block_n == 256) return launch<256, true, true>(ta, tb, ta, ta, p, 0, stream);
+  return launch<128, true, true>(ta, tb, ta, ta, p, 0, stream);
+}
 
 // Weight-gradient accumulation:  C[M, N] += Aᵀ-stored · B-stored  (a: [K, M], b: [K, N], both MN-major — the wgrad
 // layout dW += dYᵀ · X).  The epilogue reloads the old C tile by TMA, so micro-batch gradients accumulate straight into

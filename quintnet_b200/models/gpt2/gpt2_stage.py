@@ -25,6 +25,7 @@ import torch.nn as nn
 
 from ... import ops
 from ...core.communication import All_Gather, group_rank, group_size
+from ...parallel.data_parallel.components.bucket import grad_of
 from .gpt2_block import GPT2Block
 from .gpt2_embeddings import GPT2Embedding
 
@@ -133,9 +134,11 @@ class GPT2Stage(nn.Module):
             w = self.lm_head_weight
         else:
             return
-        if w.grad is None:
+        gw = grad_of(w)                      # fp32 main-grad bucket view when the buckets are high-precision
+        if gw is None:
             w.grad = torch.zeros_like(w)
-        dist.all_reduce(w.grad, op=dist.ReduceOp.SUM, group=g)
+            gw = w.grad
+        dist.all_reduce(gw, op=dist.ReduceOp.SUM, group=g)
 
     def sequence_parallel_params(self) -> List[nn.Parameter]:
         return [p for p in self.parameters()
@@ -144,7 +147,7 @@ class GPT2Stage(nn.Module):
     def sync_sequence_parallel_grads(self) -> None:
         if not self.sequence_parallel:
             return
-        grads = [p.grad for p in self.sequence_parallel_params() if p.grad is not None]
+        grads = [grad_of(p) for p in self.sequence_parallel_params() if grad_of(p) is not None]
         if not grads:
             return
         flat = torch.cat([g.reshape(-1) for g in grads])

@@ -83,6 +83,17 @@ def wgrad(w_param, dy2: torch.Tensor, x2: torch.Tensor, N: int, K: int, M: int):
     or ``None`` after ADDING it into ``w_param.grad`` inside the GEMM epilogue when fused weight-gradient
     accumulation is on and the gradient buffer exists (micro-batches after the first)."""
     from . import fused_wgrad_accumulation, wgrad_done
+    mg = getattr(w_param, "main_grad", None) if w_param is not None else None
+    if (fused_wgrad_accumulation() and mg is not None and mg.dtype == torch.float32 and mg.dim() == 2
+            and tuple(mg.shape) == (N, K) and mg.stride(1) == 1 and mg.stride(0) % 4 == 0 and K % 4 == 0
+            and mg.data_ptr() % 16 == 0):
+        # fp32 main-grad bucket view: the GEMM epilogue red.adds its accumulator tiles straight into it
+        rc = _lib().qn_gemm_bf16_wgrad_accum_f32(dy2.data_ptr(), x2.data_ptr(), mg.data_ptr(), N, K, M, dy2.stride(0),
+                                                 x2.stride(0), mg.stride(0), _auto_splits(N, K, M), 0, native.stream())
+        native.check(rc, f"qn_gemm_bf16_wgrad_accum_f32(N={N},K={K},M={M})")
+        native.count()
+        wgrad_done(w_param)
+        return None
     g = getattr(w_param, "grad", None) if w_param is not None else None
     if (fused_wgrad_accumulation() and g is not None and g.dtype == torch.bfloat16 and g.dim() == 2
             and tuple(g.shape) == (N, K) and g.stride(1) == 1 and g.stride(0) % 8 == 0 and K % 4 == 0

@@ -32,7 +32,12 @@ class _LinearAccumRef(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = dy2.t() @ x2
             wp = ctx.w_param
-            if wp.grad is not None:
+            mg = getattr(wp, "main_grad", None)
+            if mg is not None:                      # fp32 main-grad bucket view (low-precision parameters)
+                mg.add_(dw.to(mg.dtype))
+                wgrad_done(wp)
+                dw = None
+            elif wp.grad is not None:
                 wp.grad.add_(dw.to(wp.grad.dtype))
                 wgrad_done(wp)
                 dw = None

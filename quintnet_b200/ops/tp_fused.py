@@ -4,8 +4,9 @@
 ``linear_reduce_scatter`` Y_local[M/tp, N] = RS( X[M, K/tp] · W_localᵀ (+ b on its owner) )  (RowParallel forward)
 
 Each is ONE launch of the tcgen05 GEMM kernel (``csrc/gemm.cu``, ``FUSE_AG`` / ``FUSE_RS``) that moves the
-activations itself: pushes of the local shard into the peers' gather buffers, or epilogue stores of partial
-tiles into the owner's staging buffer, synchronised by release/acquire flags — no NCCL call.  The backward of
+activations itself with TMA bulk copies on peer-mapped addresses: a one-thread copy pump per CTA streams the local
+shard into the peers' gather buffers, or the epilogue bulk-stores partial slabs into the owner's staging buffer,
+synchronised by release/acquire flags — no NCCL call.  The backward of
 one op is the other op (plus local wgrad GEMMs), so a Megatron sequence-parallel block issues exactly four
 fused GEMM+collective launches per direction.
 
@@ -160,7 +161,7 @@ def _ag_gemm(ws: _Workspace, x_local: torch.Tensor, b: torch.Tensor, b_mn: bool,
 def _gemm_rs(ws: _Workspace, a: torch.Tensor, b: torch.Tensor, b_mn: bool, N: int, K: int, bias):
     """returns Y_local [M/world, N]"""
     M = a.shape[0]
-    ws.ensure(M * N * 2)
+    ws.ensure(M * ((N + 63) // 64) * 128)            # [world][M/world/32 * ceil(N/64)] slab images of 4 KB
     ws.seq_rs += 1
     par = ws.seq_rs & 1
     y = torch.empty((M // ws.world, N), dtype=torch.bfloat16, device=a.device)

@@ -26,13 +26,23 @@ class FusedAdamW(torch.optim.Optimizer):
 
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 0.01, buckets: Optional[List[GradientBucket]] = None,
-                 master_weights: Optional[bool] = None, capacity_mb: int = 256):
+                 master_weights: Optional[bool] = None, capacity_mb: int = 256,
+                 grad_dtype: Optional[torch.dtype] = None):
+        """``grad_dtype=torch.float32`` with bf16 parameters = fp32 MAIN-GRAD buckets: micro-batch gradients are
+        accumulated in fp32 (by post-accumulate hooks, or directly by the wgrad GEMM epilogue — see
+        ``ops.set_fused_wgrad_accumulation``) instead of in bf16 ``.grad`` tensors."""
         params = [p for p in params if p.requires_grad]
         defaults = dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
         super().__init__(params, defaults)
         self._step = 0
+        self._hooks = []
         if buckets is None:
-            buckets = self._make_buckets(params, capacity_mb)
+            buckets = self._make_buckets(params, capacity_mb, grad_dtype)
+            for b in buckets:
+                if b.grad_dtype != b.param_dtype:      # nobody else owns these buckets: absorb at accumulate time
+                    for j, p in enumerate(b.parameters):
+                        self._hooks.append(p.register_post_accumulate_grad_hook(
+                            lambda param, b=b, j=j: b.absorb(param, j)))
         self.buckets = buckets
         self.state_flat = []
         for b in self.buckets:
@@ -46,11 +56,12 @@ class FusedAdamW(torch.optim.Optimizer):
             })
 
     @staticmethod
-    def _make_buckets(params, capacity_mb) -> List[GradientBucket]:
+    def _make_buckets(params, capacity_mb, grad_dtype=None) -> List[GradientBucket]:
         groups = {}
         for p in params:
             groups.setdefault((p.device, p.dtype), []).append(p)
-        return [GradientBucket(i, ps, ps[0].dtype, flatten_parameters=True)
+        return [GradientBucket(i, ps, grad_dtype if (grad_dtype is not None and ps[0].dtype != torch.float32)
+                               else ps[0].dtype, flatten_parameters=True)
                 for i, ps in enumerate(groups.values())]
 
     @classmethod

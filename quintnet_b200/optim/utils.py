@@ -9,6 +9,8 @@ from typing import Iterable, Optional
 import torch
 import torch.distributed as dist
 
+from ..parallel.data_parallel.components.bucket import grad_of
+
 
 def _axis(pg_manager, name):
     if pg_manager is None:
@@ -29,8 +31,8 @@ def counts_for_norm(p: torch.Tensor, tp_rank: int, pp_size: int) -> bool:
 def global_grad_norm(parameters: Iterable[torch.Tensor], pg_manager=None) -> Optional[torch.Tensor]:
     tp_group, tp_rank, tp_size = _axis(pg_manager, "tp")
     pp_group, _, pp_size = _axis(pg_manager, "pp")
-    grads = [p.grad for p in parameters
-             if p.grad is not None and counts_for_norm(p, tp_rank, pp_size)]
+    grads = [grad_of(p) for p in parameters
+             if grad_of(p) is not None and counts_for_norm(p, tp_rank, pp_size)]
     all_params_have_device = None
     if grads:
         all_params_have_device = grads[0].device
@@ -57,12 +59,17 @@ def _zero_norm(pg_manager):
 
 
 def clip_grad_norm_global(parameters, max_norm: float, pg_manager=None) -> Optional[torch.Tensor]:
-    params = [p for p in parameters if p.grad is not None]
+    params = [p for p in parameters if grad_of(p) is not None]
     norm = global_grad_norm(params, pg_manager)
     if norm is None or not params:
         return norm
     coef = (max_norm / (norm + 1e-6)).clamp(max=1.0)
-    torch._foreach_mul_([p.grad for p in params], coef.to(params[0].grad.dtype))
+    by_dtype = {}
+    for p in params:
+        g = grad_of(p)
+        by_dtype.setdefault(g.dtype, []).append(g)
+    for dt, gs in by_dtype.items():
+        torch._foreach_mul_(gs, coef.to(dt))
     return norm
 
 

@@ -20,6 +20,16 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+def grad_of(p: torch.Tensor) -> Optional[torch.Tensor]:
+    """The gradient of ``p`` as the optimizer will see it.  With high-precision main-grad buckets (bf16 parameters,
+    fp32 bucket) that is ``p.main_grad`` — the fp32 bucket view every micro-batch gradient is accumulated into —
+    and ``p.grad`` is only a transient of the current backward; otherwise it is ``p.grad`` (itself a bucket view).
+    Everything that reads gradients between backward and the optimizer step (global-norm clipping, the tied-weight
+    and sequence-parallel gradient syncs, optimizers) goes through this accessor."""
+    mg = getattr(p, "main_grad", None)
+    return mg if mg is not None else p.grad
+
+
 class GradientBucket:
     def __init__(self, bucket_id: int, parameters: List[nn.Parameter], grad_dtype: Optional[torch.dtype] = None,
                  pad_to: int = 1, flatten_parameters: bool = False, allocator=None):
@@ -72,7 +82,9 @@ class GradientBucket:
                 if self.grad_dtype == p.dtype:
                     p.grad = v
                 else:
-                    p.grad = None  # low-precision param, high-precision bucket: hook copies
+                    p.grad = None  # low-precision param, high-precision bucket: hooks accumulate into main_grad
+            if self.grad_dtype != p.dtype:
+                p.main_grad = v
 
     def absorb(self, p: nn.Parameter, idx: int) -> None:
         """Make sure the freshly accumulated grad of ``p`` is inside the bucket."""

@@ -263,8 +263,11 @@ class InterleavedOneFOneBSchedule(PipelineSchedule):
                     g = take(tick.unit) if s < S - 1 else None
                     x, y = saved_in.pop((v, m)), saved_out.pop((v, m))
                     self._bwd_done += 1
-                    # this chunk's gradients are final once its last micro-batch went backward: let DP reduce them
-                    _set_grad_sync(t.model, m == M - 1)
+                    # gradient sync only on the globally LAST backward unit: DataParallel's end-of-backward callback
+                    # reduces every bucket that has not been launched — also those of chunks whose gradients are
+                    # still accumulating — so enabling it per chunk would all-reduce the whole model V times (and
+                    # scale the gradients by dp on every extra pass under ReductionStrategy.SUM)
+                    _set_grad_sync(t.model, self._bwd_done == bwd_total)
                     produced = wrap.backward(x, y, g)
                     if s == 0:
                         produced = None

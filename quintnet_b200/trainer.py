@@ -44,7 +44,8 @@ def build_optimizer(model, config: dict, pg_manager, default: str = "adam", weig
         if isinstance(model, DataParallel) and all(b.flat_param is not None for b in model.buckets.values()):
             return FusedAdamW.from_data_parallel(model, lr=lr, weight_decay=wd)
         if not isinstance(model, DataParallel):
-            return FusedAdamW(model.parameters(), lr=lr, weight_decay=wd)
+            from .coordinators.main_coordinator import resolve_main_grad_dtype
+            return FusedAdamW(model.parameters(), lr=lr, weight_decay=wd, grad_dtype=resolve_main_grad_dtype(config))
     if kind == "adam":
         return torch.optim.Adam(model.parameters(), lr=lr)
     return torch.optim.AdamW(model.parameters(), lr=lr, weight_decay=wd)
@@ -68,9 +69,13 @@ class _TrainerBase:
         self.grad_acc_steps = int(config.get("grad_acc_steps", 1))
         self.max_grad_norm = float(config.get("max_grad_norm", 0.0))
         self.logger = StepLogger(config.get("log_jsonl"), self.global_rank)
+        from . import ops
+        from .coordinators.main_coordinator import resolve_main_grad_dtype
         if config.get("fuse_wgrad_accumulation") is not None:
-            from . import ops
             ops.set_fused_wgrad_accumulation(bool(config["fuse_wgrad_accumulation"]))
+        elif resolve_main_grad_dtype(config) is not None and os.environ.get("QUINTNET_FUSE_WGRAD_ACCUM") is None:
+            # fp32 main grads: let the wgrad GEMMs accumulate straight into them (no bf16 round trip per micro-batch)
+            ops.set_fused_wgrad_accumulation(True)
         self.start_epoch = 0
         self.global_step = 0
 
