@@ -221,6 +221,8 @@ def build_config(args, mesh, impl):
         cfg.update({"dtype": "float32" if args.cpu else "bfloat16", "zero_stage": zero,
                     "sequence_parallel": bool(sp) and tp > 1, "seed": 0, "weight_decay": 0.01,
                     "bucket_cap_mb": 128, "pp_balance": "auto"})
+        if os.environ.get("QN_BENCH_MAIN_GRAD"):            # A/B knob: "param" = accumulate gradients in bf16
+            cfg["main_grad_dtype"] = os.environ["QN_BENCH_MAIN_GRAD"]
         if args.virtual_stages > 1 and pp > 1 and M % pp == 0:
             cfg["virtual_pipeline_stages"] = args.virtual_stages
     return cfg, M

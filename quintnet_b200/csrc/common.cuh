@@ -71,10 +71,24 @@ QN_DEVICE bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint: the hardware parks the warp (no issue slots, no polling traffic) until the phase
+// completes or ~`ns` nanoseconds passed.  On a power-capped part (B200 runs dense GEMMs at the 1 kW cap) idle warps that
+// busy-poll cost clock frequency for the warps that do the work, so every barrier wait in this library sleeps.
+QN_DEVICE bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
 QN_DEVICE void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
+  while (!mbar_try_wait_hint(bar, parity, 20000u)) {      // each failed probe slept up to ~20 us
     if (clock64() - t0 > QN_WATCHDOG_CYCLES) {
       printf("[quintnet_b200] mbarrier watchdog: block %d thread %d parity %u\n", blockIdx.x, threadIdx.x, parity);
       __trap();

@@ -73,6 +73,10 @@ struct TpComm {
   uint32_t seq;                       // launch sequence number of this workspace (flags hold seq values)
   uint32_t rows_per_rank, mb_per_rank;
   const __nv_bfloat16* x_local;       // AG: [rows_per_rank, K] contiguous
+  __nv_bfloat16* x_full;              // AG (optional): private [M, K] tensor that receives the COMPLETE gathered operand
+                                      // (own rows straight from the pump, peers' rows copied out of the gather buffer
+                                      // by the pumps once their flags are up) — the forward keeps it for the wgrad
+                                      // GEMM of the backward pass without a separate clone of the gather buffer
   __nv_bfloat16* gather[TP_MAX];      // AG: every rank's gather buffer [M, K] (peer mappings)
   uint32_t* ag_flags[TP_MAX];         // AG: every rank's per-8-row flags [M / 8]
   __nv_bfloat16* stage[TP_MAX];       // RS: every rank's staging buffer [world][slabs_per_rank] x 4 KB slab images
@@ -349,8 +353,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_arrive_expect_tx(&pump_bar[slot], bytes);
           bulk_load_1d(buf, src + off, bytes, &pump_bar[slot]);
           mbar_wait(&pump_bar[slot], (cnt / kPumpRing) & 1);
-          for (int pr = 1; pr <= tc.world; ++pr)     // peers first, the local copy last
+          for (int pr = 1; pr < tc.world; ++pr)      // peers first, the local copy last
             bulk_store_1d(reinterpret_cast<uint8_t*>(tc.gather[(tc.rank + pr) % tc.world]) + shard_off + off, buf, bytes);
+          bulk_store_1d(reinterpret_cast<uint8_t*>(tc.x_full ? tc.x_full : tc.gather[tc.rank]) + shard_off + off, buf, bytes);
           tma_store_commit();
           ++cnt;
         }
@@ -371,6 +376,32 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         fence_proxy_async_all();
         __threadfence_system();
         for (uint32_t i = 0; i < npend; ++i) publish(pend_u[i]);
+      }
+      // second duty (background): peers' rows, gather buffer -> x_full, as their units land
+      if (tc.x_full != nullptr && !(tc.debug & 4u)) {
+        for (int pr = 1; pr < tc.world; ++pr) {
+          const uint32_t srcr = (tc.rank + pr) % tc.world;
+          const size_t src_off = static_cast<size_t>(srcr) * tc.rows_per_rank * p.K * 2;
+          for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
+            wait_flag_ge(tc.ag_flags[tc.rank] + srcr * units + u, tc.seq);
+            fence_proxy_async_all();
+            for (uint32_t pc = 0; pc < npiece; ++pc) {
+              const uint32_t off_in_unit = pc * kPumpSlot;
+              const uint32_t bytes = min(kPumpSlot, unit_bytes - off_in_unit);
+              const size_t off = src_off + static_cast<size_t>(u) * unit_bytes + off_in_unit;
+              const uint32_t slot = cnt % kPumpRing;
+              uint8_t* buf = smem_ring + slot * kPumpSlot;
+              tma_store_wait_read<kPumpRing - 1>();
+              mbar_arrive_expect_tx(&pump_bar[slot], bytes);
+              bulk_load_1d(buf, reinterpret_cast<const uint8_t*>(tc.gather[tc.rank]) + off, bytes, &pump_bar[slot]);
+              mbar_wait(&pump_bar[slot], (cnt / kPumpRing) & 1);
+              bulk_store_1d(reinterpret_cast<uint8_t*>(tc.x_full) + off, buf, bytes);
+              tma_store_commit();
+              ++cnt;
+            }
+          }
+        }
+        tma_store_wait_all<0>();
       }
     }
   } else if (FUSE == FUSE_AG && tc.ag_mode == AG_LSU && (warp == 2 || warp == 3)) {
@@ -1018,16 +1049,19 @@ static uint32_t fused_group_m(uint32_t tile_rows_per_rank) {
 // K3  all-gather -> GEMM:  C[M, N] = epilogue( AG(x_local)[M, K] · B )
 //   x_local [M/world, K] contiguous; gather[r] / ag_flags[r]: rank r's symmetric gather buffer [M, K] and flags [M/32]
 //   (host arrays of `world` peer-mapped pointers); b as in qn_gemm_bf16; seq: per-workspace launch counter (>= 1).
+//   x_full (optional, pump mode only): private [M, K] tensor that receives the complete gathered operand.
 extern "C" int qn_gemm_ag_bf16(const void* x_local, void* const* gather, void* const* ag_flags, int rank, int world,
                                unsigned seq, const void* b, void* c, int M, int N, int K, long long ldb,
                                long long ldc, int b_mn, int epilogue, const void* bias, void* z, long long ldz,
-                               int block_n, int max_ctas, cudaStream_t stream) {
+                               int block_n, int max_ctas, void* x_full, cudaStream_t stream) {
   using namespace qn;
   TpComm comm{};
   if (int rc = fill_comm(comm, rank, world, seq, M)) return rc;
   if ((K % 8) || (ldb % 8) || (ldc % 8)) return 910;
   comm.x_local = static_cast<const __nv_bfloat16*>(x_local);
   if (reinterpret_cast<uintptr_t>(x_local) & 15) return 910;
+  if (x_full != nullptr && (comm.ag_mode != AG_PUMP || (reinterpret_cast<uintptr_t>(x_full) & 15))) return 918;
+  comm.x_full = static_cast<__nv_bfloat16*>(x_full);
   for (int r = 0; r < world; ++r) {
     comm.gather[r] = static_cast<__nv_bfloat16*>(gather[r]);
     comm.ag_flags[r] = static_cast<uint32_t*>(ag_flags[r]);

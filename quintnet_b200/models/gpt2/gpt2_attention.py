@@ -72,7 +72,9 @@ class GPT2Attention(nn.Module):
         if self.use_rope:
             cos, sin = self._rope(T, qkv.device)
             q, k = ops.rope(q, cos, sin), ops.rope(k, cos, sin)
-        o = ops.attention(q, k, v, causal=True, dropout_p=self.attn_pdrop, training=self.training)
+        # (RoPE / head_dim != 64 variants: the packed tcgen05 kernel does not apply; long sequences use the library
+        # kernel here, short ones the native shared-memory kernel)
+        o = ops.attention(q, k, v, causal=True, dropout_p=self.attn_pdrop, training=self.training, allow_library=True)
         o = o.transpose(1, 2).reshape(B, T, Hl * d)
         o = self.c_proj(o)
         return o if raw else ops.dropout_add(o, residual, self.resid_pdrop, self.training)

@@ -79,13 +79,25 @@ def gelu(x):
     return reference.gelu(x)
 
 
-def attention(q, k, v, causal: bool, dropout_p: float = 0.0, scale=None, training: bool = True):
-    """q,k,v: [B, H, T, d] -> [B, H, T, d]"""
+def attention(q, k, v, causal: bool, dropout_p: float = 0.0, scale=None, training: bool = True,
+              allow_library: bool = False):
+    """q,k,v: [B, H, T, d] -> [B, H, T, d].  On CUDA this is the native shared-memory kernel for short sequences;
+    shapes it cannot take raise unless the caller opts into the library path (``allow_library=True``, or
+    ``QUINTNET_ALLOW_FALLBACK=1``) — no silent fallback."""
     if q.is_cuda:
-        # library attention (cuDNN/flash SDPA) until the native kernel is enabled
+        p = dropout_p if training else 0.0
+        if _use_native("attention", q):
+            from . import cuda_ops
+            if cuda_ops.small_attention_ok(q, k, v, p):
+                # short sequences (ViT: T = 50, d = 16): whole head in one CTA's shared memory, fwd and bwd one launch each
+                return cuda_ops.small_attention(q, k, v, causal, scale)
+            if not allow_library and os.environ.get("QUINTNET_ALLOW_FALLBACK", "0") != "1":
+                raise RuntimeError(
+                    f"no native attention kernel for q{tuple(q.shape)} {q.dtype} dropout={p}: the packed tcgen05 flash "
+                    "kernel needs head_dim 64 (ops.attention_qkvpacked) and the shared-memory kernel needs bf16, "
+                    "dropout 0 and T*T*8 + 4*T*(d+1)*4 <= 200 KB.  Set QUINTNET_ALLOW_FALLBACK=1 to use torch SDPA.")
         import torch.nn.functional as F
-        return F.scaled_dot_product_attention(q, k, v, is_causal=causal, scale=scale,
-                                              dropout_p=dropout_p if training else 0.0)
+        return F.scaled_dot_product_attention(q, k, v, is_causal=causal, scale=scale, dropout_p=p)
     return reference.attention(q, k, v, causal, dropout_p, scale, training)
 
 

@@ -683,3 +683,65 @@ def attention_qkvpacked(qkv: torch.Tensor, H: int, causal: bool, p_drop: float =
     if scale is None:
         scale = 1.0 / 8.0   # 1/sqrt(64)
     return _AttnPacked.apply(qkv, H, causal, p_drop, scale)
+
+
+# ------------------------------------------------- short-sequence attention (whole head in shared memory)
+def small_attention_ok(q, k, v, dropout_p: float) -> bool:
+    """True if the one-CTA-per-head kernel (``csrc/attention_small.cu``) can take these [B, H, T, d] views."""
+    if not (q.is_cuda and q.dtype == k.dtype == v.dtype == torch.bfloat16 and dropout_p == 0.0 and q.dim() == 4):
+        return False
+    if q.shape != k.shape or q.shape != v.shape:
+        return False
+    T, d = q.shape[2], q.shape[3]
+    if not _lib().qn_small_attn_fits(T, d):
+        return False
+    return all(t.stride(3) == 1 and all(int(st) % 8 == 0 for st in t.stride()[:3]) and t.data_ptr() % 16 == 0
+               for t in (q, k, v))
+
+
+def _strides3(*ts):
+    import ctypes
+    vals = []
+    for t in ts:
+        vals += [t.stride(0), t.stride(1), t.stride(2)]
+    return (ctypes.c_longlong * len(vals))(*vals)
+
+
+class _SmallAttention(torch.autograd.Function):
+    """softmax(Q·Kᵀ·scale [causal]) · V with Q, K, V, scores and probabilities resident in one CTA's shared memory.
+    Inputs are [B, H, T, d] VIEWS (any batch / head / token strides); the output is a [B, H, T, d] view of a
+    contiguous [B, T, H·d] buffer, so the caller's ``transpose(1, 2).reshape(B, T, H·d)`` is free."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, causal, scale):
+        B, H, T, d = q.shape
+        buf = torch.empty((B, T, H, d), dtype=torch.bfloat16, device=q.device)
+        o = buf.permute(0, 2, 1, 3)
+        need = any(ctx.needs_input_grad[:3])
+        rc = _lib().qn_small_attn_fwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr(), None, B, H, T, d,
+                                      _strides3(q, k, v, o), float(scale), int(causal), native.stream())
+        native.check(rc, "qn_small_attn_fwd")
+        native.count()
+        if need:
+            ctx.save_for_backward(q, k, v)
+        ctx.args = (B, H, T, d, float(scale), int(causal))
+        return o
+
+    @staticmethod
+    def backward(ctx, do):
+        q, k, v = ctx.saved_tensors
+        B, H, T, d, scale, causal = ctx.args
+        if do.stride(3) != 1 or any(int(st) % 8 for st in do.stride()[:3]) or do.data_ptr() % 16:
+            do = do.contiguous()
+        dq, dk, dv = (torch.empty_strided(t.shape, t.stride(), dtype=t.dtype, device=t.device) for t in (q, k, v))
+        rc = _lib().qn_small_attn_bwd(q.data_ptr(), k.data_ptr(), v.data_ptr(), do.data_ptr(), dq.data_ptr(),
+                                      dk.data_ptr(), dv.data_ptr(), B, H, T, d, _strides3(q, k, v, do), scale, causal,
+                                      native.stream())
+        native.check(rc, "qn_small_attn_bwd")
+        native.count()
+        return dq, dk, dv, None, None
+
+
+def small_attention(q, k, v, causal: bool, scale=None):
+    scale = (q.shape[-1] ** -0.5) if scale is None else scale
+    return _SmallAttention.apply(q, k, v, bool(causal), float(scale))

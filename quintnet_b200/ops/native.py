@@ -134,6 +134,9 @@ _SIGNATURES = {
     "qn_gemm_set_flag_watchdog": [ctypes.c_longlong],
     "qn_gemm_bf16_wgrad_accum": [_P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _P],
     "qn_gemm_bf16_wgrad_accum_f32": [_P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _P],
+    "qn_small_attn_fits": [_I, _I],
+    "qn_small_attn_fwd": [_P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _I, _P],
+    "qn_small_attn_bwd": [_P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P, _F, _I, _P],
     "qn_write_flag": [_P, _L, ctypes.c_uint, _P],
     "qn_ag_done_base": [],
     "qn_gemm_fp8": [_P, _P, _P, _I, _I, _I, _L, _L, _L, _P, _P, _I, _P, _P, _L, _I, _P],

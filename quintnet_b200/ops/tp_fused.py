@@ -27,7 +27,7 @@ from . import native, symm
 from .cuda_ops import EPI_BIAS, EPI_BIAS_GELU, EPI_MUL_AUX, EPI_NONE, colsum, gemm, wgrad
 
 _P, _I, _L, _U32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_uint
-native.declare("qn_gemm_ag_bf16", [_P, _P, _P, _I, _I, _U32, _P, _P, _I, _I, _I, _L, _L, _I, _I, _P, _P, _L, _I, _I, _P])
+native.declare("qn_gemm_ag_bf16", [_P, _P, _P, _I, _I, _U32, _P, _P, _I, _I, _I, _L, _L, _I, _I, _P, _P, _L, _I, _I, _P, _P])
 native.declare("qn_gemm_rs_bf16", [_P, _P, _P, _P, _P, _I, _I, _U32, _I, _I, _I, _L, _L, _L, _I, _P, _I, _I, _P])
 
 _FLAG_BYTES = 1 << 20
@@ -95,6 +95,7 @@ def can_fuse(rows_total: int, group, *dims) -> bool:
 # publishes one flag per destination; the AG->GEMM kernel then runs without push warps and only acquires that flag
 # before its first remote tile.  No SM, register or L1 involvement in the transfer.
 _AG_MODE_CE = os.environ.get("QN_TP_AG_MODE", "") == "ce"
+_AG_MODE = {"c": "ce", "l": "lsu"}.get(os.environ.get("QN_TP_AG_MODE", "pump")[:1], "pump")
 _cudart = None
 
 
@@ -130,11 +131,11 @@ def _ag_gemm(ws: _Workspace, x_local: torch.Tensor, b: torch.Tensor, b_mn: bool,
              bias, z, out_full_x: bool, transient: bool = False):
     """returns (Y [M, N], X_full [M, K] or None).
 
-    The kernel leaves the complete gathered operand in this rank's symmetric gather buffer (peers' rows arrive
-    by NVLink push, own rows are written by the same push warps).  ``transient=True`` returns that buffer as a
-    view — valid until the next-but-one all-gather launch of this workspace recycles it, i.e. long enough for
-    the weight-gradient GEMM that immediately follows in backward; otherwise one copy is taken (forward:
-    the operand must survive until backward)."""
+    ``transient=True`` (backward): the kernel leaves the complete gathered operand in this rank's symmetric gather
+    buffer (peers' rows arrive by NVLink, own rows are written by the same copy pumps) and that buffer is returned
+    as a view — valid until the next-but-one all-gather launch of this workspace recycles it, i.e. long enough for
+    the weight-gradient GEMM that immediately follows.  Otherwise (forward: the operand must survive until
+    backward) the pumps assemble it in a private tensor while the GEMM runs — no separate clone of the buffer."""
     rows = x_local.shape[0]
     M = rows * ws.world
     ws.ensure(M * K * 2)
@@ -142,12 +143,17 @@ def _ag_gemm(ws: _Workspace, x_local: torch.Tensor, b: torch.Tensor, b_mn: bool,
     par = ws.seq_ag & 1
     y = torch.empty((M, N), dtype=torch.bfloat16, device=x_local.device)
     ce_event = _copy_engine_allgather(ws, x_local, par, rows, K) if _AG_MODE_CE else None
+    x_priv = None
+    if out_full_x and not transient and _AG_MODE == "pump":
+        x_priv = torch.empty((M, K), dtype=torch.bfloat16, device=x_local.device)
     rc = native.require().qn_gemm_ag_bf16(
         x_local.data_ptr(), ws.ptrs(ws.gather[par]), ws.ptrs(ws.ag_flags), ws.rank, ws.world, ws.seq_ag,
         b.data_ptr(), y.data_ptr(), M, N, K, b.stride(0), N, int(b_mn), epilogue, native.ptr(bias), native.ptr(z),
-        z.stride(0) if z is not None else 0, 0, 0, native.stream())
+        z.stride(0) if z is not None else 0, 0, 0, native.ptr(x_priv), native.stream())
     native.check(rc, f"qn_gemm_ag_bf16(M={M},N={N},K={K})")
     native.count()
+    if x_priv is not None:
+        return y, x_priv
     x_full = None
     if out_full_x:
         if ce_event is not None:               # the local rows reach the gather buffer on the side stream

@@ -233,8 +233,7 @@ def test_flag_watchdog_fires_on_dropped_collective(tmp_path):
 # 4-rank variants of the in-kernel collectives (group sizes beyond the 2-rank axes of the 2x2x2 mesh).  Written
 # without hardware access in round 1 -> opt-in until they have run once (QN_RUN_UNVALIDATED=1).
 # --------------------------------------------------------------------------------------------------------
-_unvalidated = pytest.mark.skipif(__import__("os").environ.get("QN_RUN_UNVALIDATED") != "1",
-                                  reason="first hardware run pending (QN_RUN_UNVALIDATED=1)")
+_unvalidated = pytest.mark.gpu          # (were opt-in in round 1; they run by default now)
 
 
 @_unvalidated

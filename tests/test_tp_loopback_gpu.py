@@ -65,12 +65,16 @@ def _run_ag(world, M, N, K, b_mn, epi, pairs, mode, launches=3):
         ys = [torch.empty(M, N, dtype=torch.bfloat16, device="cuda") for _ in range(world)]
         zs = [torch.empty(M, N, dtype=torch.bfloat16, device="cuda") if epi == EPI_BIAS_GELU else aux[r] for r in range(world)]
         par = seq & 1
+        # odd launches also ask for the private gathered-operand tensor (forward mode), even ones use the buffer view
+        xfull = [torch.zeros(M, K, dtype=torch.bfloat16, device="cuda") if (mode == "pump" and seq % 2 == 1) else None
+                 for _ in range(world)]
         for r in range(world):
             rc = lib.qn_gemm_ag_bf16(xs[r].data_ptr(), _ptrs(gather[par]), _ptrs(flags), r, world, seq, ws[r].data_ptr(),
                                      ys[r].data_ptr(), M, N, K, ws[r].stride(0), N, int(b_mn), epi,
                                      bias[r].data_ptr() if bias[r] is not None else None,
                                      zs[r].data_ptr() if zs[r] is not None else None, N if zs[r] is not None else 0,
-                                     0, cap, streams[r].cuda_stream)
+                                     0, cap, xfull[r].data_ptr() if xfull[r] is not None else None,
+                                     streams[r].cuda_stream)
             assert rc == 0, rc
         torch.cuda.synchronize()
         xf = torch.cat(xs).float()
@@ -88,8 +92,10 @@ def _run_ag(world, M, N, K, b_mn, epi, pairs, mode, launches=3):
             if epi == EPI_MUL_AUX:
                 ref = ref * aux[r].float()
             torch.testing.assert_close(ys[r].float(), ref, atol=6e-2, rtol=3e-2)
-            # the kernel leaves the complete gathered operand in every rank's gather buffer
-            if mode != "ce":
+            # the kernel leaves the complete gathered operand in the private tensor / in every rank's gather buffer
+            if xfull[r] is not None:
+                torch.testing.assert_close(xfull[r].float(), xf, atol=0, rtol=0)
+            elif mode != "ce":
                 torch.testing.assert_close(gather[par][r].view(M, K).float(), xf, atol=0, rtol=0)
         xs = [_rnd(rows, K) for _ in range(world)]           # new data next launch (stale buffers must not pass)
 
