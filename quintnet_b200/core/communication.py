@@ -102,6 +102,18 @@ def _reduce_scatter_tensor(out: torch.Tensor, x: torch.Tensor, group) -> None:
     out.copy_(full.chunk(n, dim=0)[r])
 
 
+def _sum_all_reduce(x: torch.Tensor, group) -> torch.Tensor:
+    """Out-of-place SUM all-reduce.  Small CUDA messages (the latency-bound TP activations of the ViT path: <= 512 KB)
+    go through the one-launch NVLS / P2P kernel over symmetric memory; everything else through the backend."""
+    if x.is_cuda:
+        from ..ops import symm
+        if symm.oneshot_ok(x, group):
+            return symm.all_reduce_small(x, group)
+    out = x.contiguous().clone()  # never alias the producer's buffer
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
 # --------------------------------------------------------------------------
 # autograd collectives
 # --------------------------------------------------------------------------
@@ -112,9 +124,7 @@ class All_Reduce(torch.autograd.Function):
     def forward(ctx, x: torch.Tensor, group=None):
         if group_size(group) == 1:
             return x
-        out = x.contiguous().clone()  # never alias the producer's buffer
-        dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
-        return out
+        return _sum_all_reduce(x, group)
 
     @staticmethod
     def backward(ctx, grad):
@@ -137,9 +147,7 @@ class Copy_To_Parallel(torch.autograd.Function):
     def backward(ctx, grad):
         if group_size(ctx.group) == 1:
             return grad, None
-        g = grad.contiguous().clone()
-        dist.all_reduce(g, op=dist.ReduceOp.SUM, group=ctx.group)
-        return g, None
+        return _sum_all_reduce(grad, ctx.group), None
 
 
 class All_Gather(torch.autograd.Function):

@@ -29,8 +29,9 @@ from . import native
 
 _P, _I, _L, _F, _U32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_uint
 native.declare("qn_allreduce", [_P, _P, _P, _I, _I, _L, _I, _F, _U32, _I, _P])
-native.declare("qn_reduce_scatter_sqnorm", [_P, _P, _I, _I, _P, _P, _P, _L, _I, _F, _U32, _I, _P])
-native.declare("qn_adamw_allgather", [_P, _P, _I, _I, _P, _P, _P, _P, _P, _L, _I, _F, _F, _F, _F, _F, _F, _F,
+native.declare("qn_reduce_scatter_sqnorm", [_P, _P, _P, _I, _I, _P, _P, _P, _L, _I, _F, _U32, _I, _P])
+native.declare("qn_allreduce_oneshot", [_P, _P, _P, _I, _I, _P, _P, _L, _I, _F, _P, _L, _I, _P])
+native.declare("qn_adamw_allgather", [_P, _P, _P, _I, _I, _P, _P, _P, _P, _P, _L, _I, _F, _F, _F, _F, _F, _F, _F,
                                       _U32, _I, _P])
 native.declare("qn_ipc_get_handle", [_P, _P])
 native.declare("qn_ipc_open_handle", [_P, ctypes.POINTER(ctypes.c_void_p)])
@@ -38,7 +39,8 @@ native.declare("qn_malloc", [ctypes.POINTER(ctypes.c_void_p), _L])
 native.declare("qn_memset0", [_P, _L, _P])
 
 SIGNAL_PAD_BYTES = 64 * 1024
-COMM_BLOCKS = int(os.environ.get("QUINTNET_COMM_BLOCKS", "32"))
+COMM_BLOCKS = int(os.environ.get("QUINTNET_COMM_BLOCKS", "48"))      # <= 64 (signal-pad layout of csrc/comm.cu)
+ONESHOT_MAX_BYTES = int(os.environ.get("QUINTNET_ONESHOT_MAX_BYTES", str(512 * 1024)))
 _DT = {torch.float32: 0, torch.bfloat16: 1}
 
 
@@ -81,6 +83,7 @@ class SymmBuffer:
 _registry: List[SymmBuffer] = []
 _pads: Dict[Tuple[int, str], SymmBuffer] = {}
 _disabled_reason: Optional[str] = None
+_pad_configured = False
 
 
 def lookup(t: torch.Tensor) -> Optional[Tuple[SymmBuffer, int]]:
@@ -100,6 +103,14 @@ def _group_key(group) -> int:
 
 def _torch_symm_alloc(nbytes: int, device, group):
     import torch.distributed._symmetric_memory as sm
+    global _pad_configured
+    if not _pad_configured:
+        _pad_configured = True
+        try:
+            if sm.get_signal_pad_size() < SIGNAL_PAD_BYTES:
+                sm.set_signal_pad_size(SIGNAL_PAD_BYTES)
+        except Exception:  # noqa: BLE001 — older torch / allocations already made: the default pad (9216 B) is enough
+            pass
     t = sm.empty(nbytes, dtype=torch.uint8, device=device)
     try:
         h = sm.rendezvous(t, group=group)
@@ -228,7 +239,8 @@ def reduce_scatter_sqnorm(flat_grad: torch.Tensor, out_shard: torch.Tensor, scal
                           mask: Optional[torch.Tensor], sq: torch.Tensor) -> None:
     b, off = lookup(flat_grad)
     arr, sig = b.ptr_arrays(off)
-    rc = native.require().qn_reduce_scatter_sqnorm(arr, sig, b.rank, b.world, out_shard.data_ptr(),
+    mc = (b.mc_ptr + off) if b.mc_ptr else None           # NVLS: the switch forms the sum (multimem.ld_reduce)
+    rc = native.require().qn_reduce_scatter_sqnorm(arr, sig, mc, b.rank, b.world, out_shard.data_ptr(),
                                                    native.ptr(mask), sq.data_ptr(), flat_grad.numel(),
                                                    _DT[flat_grad.dtype], float(scale), b.next_epoch(2),
                                                    COMM_BLOCKS, native.stream())
@@ -242,10 +254,63 @@ def adamw_allgather(flat_param: torch.Tensor, st: dict, coef: Optional[torch.Ten
     arr, sig = b.ptr_arrays(off)
     if coef is not None and coef.dtype != torch.float32:
         coef = coef.float()
-    rc = native.require().qn_adamw_allgather(arr, sig, b.rank, b.world, st["grad"].data_ptr(),
+    mc = (b.mc_ptr + off) if b.mc_ptr else None           # NVLS: one multimem.st replicates the new parameters
+    rc = native.require().qn_adamw_allgather(arr, sig, mc, b.rank, b.world, st["grad"].data_ptr(),
                                              st["master"].data_ptr(), st["m"].data_ptr(), st["v"].data_ptr(),
                                              native.ptr(coef), flat_param.numel(), _DT[flat_param.dtype], lr,
                                              beta1, beta2, eps, weight_decay, 1.0 - beta1 ** step,
                                              1.0 - beta2 ** step, b.next_epoch(2), COMM_BLOCKS, native.stream())
     native.check(rc, "qn_adamw_allgather")
     native.count()
+
+
+# ------------------------------------------------------------------ small-message one-shot all-reduce
+class _OneShotWorkspace:
+    def __init__(self, group, device):
+        self.stage = alloc_bytes(2 * ONESHOT_MAX_BYTES, device, group)
+        self.stage.tensor.zero_()
+        self.counters = torch.zeros(64, dtype=torch.int32, device=device)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+
+
+_oneshot: Dict[int, _OneShotWorkspace] = {}
+
+
+def oneshot_ok(x: torch.Tensor, group) -> bool:
+    return (x.is_cuda and x.dtype in _DT and x.numel() * x.element_size() <= ONESHOT_MAX_BYTES
+            and "allreduce" in native._enabled_set() and available(group))
+
+
+def all_reduce_small(x: torch.Tensor, group, scale: float = 1.0) -> torch.Tensor:
+    """Out-of-place SUM all-reduce (x ``scale``) of a small tensor in ONE launch and one NVLink round trip: copy-in to a
+    symmetric staging half, one cross-rank flag barrier, NVLS ``multimem.ld_reduce`` (or a load per peer) straight into
+    the result.  Replaces the NCCL all-reduce of the latency-bound TP activations (reference
+    ``core/communication.py:495-518``); CUDA-graph replayable (the launch counter lives on the device)."""
+    key = _group_key(group)
+    if key not in _oneshot:
+        _oneshot[key] = _OneShotWorkspace(group, x.device)
+    ws = _oneshot[key]
+    b = ws.stage
+    xc = x.contiguous()
+    vn = 8 if x.dtype == torch.bfloat16 else 4
+    n = xc.numel()
+    npad = (n + vn - 1) // vn * vn
+    if npad != n or xc.data_ptr() % 16:
+        buf = torch.zeros(npad, dtype=x.dtype, device=x.device)
+        buf[:n].copy_(xc.reshape(-1))
+        src = buf
+        out = torch.empty(npad, dtype=x.dtype, device=x.device)
+    else:
+        src = xc
+        out = torch.empty_like(xc)
+    if _fault_injected("drop_collective", b.rank):
+        return out.reshape(-1)[:n].view(x.shape)
+    arr, sig = b.ptr_arrays(0)
+    blocks = max(1, min(16, (npad // vn + 511) // 512))
+    rc = native.require().qn_allreduce_oneshot(arr, sig, b.mc_ptr or None, b.rank, b.world, src.data_ptr(), out.data_ptr(),
+                                               npad, _DT[x.dtype], float(scale), ws.counters.data_ptr(),
+                                               ONESHOT_MAX_BYTES, blocks, native.stream())
+    native.check(rc, "qn_allreduce_oneshot")
+    native.count()
+    return out.reshape(-1)[:n].view(x.shape)

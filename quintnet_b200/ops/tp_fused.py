@@ -95,7 +95,11 @@ def can_fuse(rows_total: int, group, *dims) -> bool:
 # publishes one flag per destination; the AG->GEMM kernel then runs without push warps and only acquires that flag
 # before its first remote tile.  No SM, register or L1 involvement in the transfer.
 _AG_MODE_CE = os.environ.get("QN_TP_AG_MODE", "") == "ce"
-_AG_MODE = {"c": "ce", "l": "lsu"}.get(os.environ.get("QN_TP_AG_MODE", "pump")[:1], "pump")
+
+
+def _ag_mode() -> str:
+    """Read per call (the micro-benchmarks switch modes at run time); must mirror fill_comm() in csrc/gemm.cu."""
+    return {"c": "ce", "l": "lsu"}.get((os.environ.get("QN_TP_AG_MODE") or "pump")[:1], "pump")
 _cudart = None
 
 
@@ -142,9 +146,9 @@ def _ag_gemm(ws: _Workspace, x_local: torch.Tensor, b: torch.Tensor, b_mn: bool,
     ws.seq_ag += 1
     par = ws.seq_ag & 1
     y = torch.empty((M, N), dtype=torch.bfloat16, device=x_local.device)
-    ce_event = _copy_engine_allgather(ws, x_local, par, rows, K) if _AG_MODE_CE else None
+    ce_event = _copy_engine_allgather(ws, x_local, par, rows, K) if _ag_mode() == "ce" else None
     x_priv = None
-    if out_full_x and not transient and _AG_MODE == "pump":
+    if out_full_x and not transient and _ag_mode() == "pump":
         x_priv = torch.empty((M, K), dtype=torch.bfloat16, device=x_local.device)
     rc = native.require().qn_gemm_ag_bf16(
         x_local.data_ptr(), ws.ptrs(ws.gather[par]), ws.ptrs(ws.ag_flags), ws.rank, ws.world, ws.seq_ag,

@@ -105,6 +105,26 @@ class PipelineTrainer:
         self.model.train()
         return self.schedule.train_step(data_loader, tensor_shapes, device, dtype)
 
+    def _pad_batch_for_sequence_parallel(self, batch, key):
+        """A sequence-parallel stage splits the micro-batch over the TP group: a validation batch (other batch size, ragged
+        last batch) that is not divisible by tp is padded with rows whose labels are all ``ignore_index`` — they add
+        nothing to the loss sum or the token count."""
+        from .schedule import unwrap_stage
+        stage = unwrap_stage(self.model)
+        if not getattr(stage, "sequence_parallel", False) or self.task_type != "clm":
+            return batch
+        n = dist.get_world_size(stage.tp_group) if getattr(stage, "tp_group", None) is not None else 1
+        b = batch[key].shape[0]
+        if n <= 1 or b % n == 0:
+            return batch
+        pad = n - b % n
+        out = dict(batch)
+        for k, v in batch.items():
+            if torch.is_tensor(v) and v.dim() >= 1 and v.shape[0] == b:
+                fill = -100 if k == "labels" else 0
+                out[k] = torch.cat([v, torch.full((pad,) + tuple(v.shape[1:]), fill, dtype=v.dtype, device=v.device)])
+        return out
+
     @torch.no_grad()
     def evaluate(self, val_loader, tensor_shapes, device, dtype):
         """Forward-only pipeline over ``val_loader``.
@@ -135,6 +155,7 @@ class PipelineTrainer:
             if "image" in batch:
                 batch = {"images": batch["image"], "labels": batch["label"]}
             key = "input_ids" if self.task_type == "clm" else "images"
+            batch = self._pad_batch_for_sequence_parallel(batch, key)
             bsz = batch[key].shape[0]
             shapes = (bsz,) + tuple(tensor_shapes[1:])
             if hasattr(self.model, "get_tensor_shapes"):

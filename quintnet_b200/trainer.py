@@ -180,11 +180,18 @@ class Trainer(_TrainerBase):
         nb = 0
         M = self.grad_acc_steps
         is_ddp = hasattr(self.model, "require_backward_grad_sync")
+        # only whole accumulation groups reach an optimizer step: a ragged tail of len(loader) % M micro-batches is
+        # dropped (like drop_last) instead of leaking un-synchronised gradients into the next epoch's first step
+        n_total = len(self.train_loader) if hasattr(self.train_loader, "__len__") else None
+        limit = (n_total // M) * M if (n_total is not None and n_total >= M) else n_total
+        zero_grads(self.model, self.optimizer)
         for i, batch in enumerate(self.train_loader):
+            if limit is not None and i >= limit and limit >= M:
+                break
             images, labels = _unpack_classification(batch)
             images = images.to(self.device, non_blocking=True).to(self.dtype)
             labels = labels.to(self.device, non_blocking=True)
-            last = (i + 1) % M == 0
+            last = (i + 1) % M == 0 or (limit is not None and limit < M and i + 1 == limit)   # fewer than M batches: one step
             if is_ddp:
                 self.model.require_backward_grad_sync = last
             out = self.model(images)

@@ -37,7 +37,7 @@ def run_case(kind, N, K, b_mn, epi, iters=12):
         w = rnd(K, N) if b_mn else rnd(N, K)
         bias = rnd(N) if epi in (EPI_BIAS, EPI_BIAS_GELU) else None
         z = rnd(M, N) if epi in (EPI_BIAS_GELU, EPI_MUL_AUX) else None
-        fn = lambda: tp_fused._ag_gemm(ws, x, w, b_mn, N, K, epi, bias, z, False)
+        fn = lambda: tp_fused._ag_gemm(ws, x, w, b_mn, N, K, epi, bias, z, True, transient=b_mn)
     else:
         a = rnd(M, K)
         w = rnd(K, N) if b_mn else rnd(N, K)
@@ -79,19 +79,23 @@ for name, kind, N, K, b_mn, epi in CASES:
     e1.record(); torch.cuda.synchronize()
     if rank == 0:
         print(f"{name} plain GEMM (no comm, no epilogue) back-to-back {e0.elapsed_time(e1) * 1e3 / 12:6.1f} us  dbg=-", flush=True)
-for comm in (0,):
-    os.environ["QN_TP_COMM_CTAS"] = str(comm)
+MODES = [m for m in os.environ.get("QN_BENCH_TP_MODES", "pump:1,lsu:1,pump:0").split(",") if m]
+for spec in MODES:
+    mode, pairs = spec.split(":")
+    os.environ["QN_TP_AG_MODE"] = mode
+    os.environ["QN_TP_2CTA"] = pairs
     for dbg in (0,):
         os.environ["QN_TP_DEBUG"] = str(dbg)
         for name, kind, N, K, b_mn, epi in CASES:
             t, tb = run_case(kind, N, K, b_mn, epi)
-            out[f"{name} comm={comm} dbg={dbg}"] = {"us_isolated": round(t, 1), "us_back_to_back": round(tb, 1)}
+            out[f"{name} ag={mode} pairs={pairs} dbg={dbg}"] = {"us_isolated": round(t, 1), "us_back_to_back": round(tb, 1)}
             if rank == 0:
-                print(f"{name} comm={comm:2d} dbg={dbg:2d}: isolated {t:6.1f} us  back-to-back {tb:6.1f} us", flush=True)
-os.environ["QN_TP_COMM_CTAS"] = "0"
+                print(f"{name} ag={mode:4s} pairs={pairs} dbg={dbg:2d}: isolated {t:6.1f} us  back-to-back {tb:6.1f} us", flush=True)
+os.environ["QN_TP_AG_MODE"] = "pump"
+os.environ["QN_TP_2CTA"] = "1"
 os.environ["QN_TP_DEBUG"] = "0"
 if rank == 0:
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open("gpurun_out/tp_kernel_times.json", "w"), indent=1)
+    json.dump(out, open("gpurun_out/r2_tp_kernel_times.json", "w"), indent=1)
 dist.barrier()
 dist.destroy_process_group()

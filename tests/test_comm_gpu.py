@@ -33,6 +33,36 @@ def _allreduce(rank, world):
         print(f"symm backend={b.backend} multicast={'yes' if b.mc_ptr else 'no'}")
 
 
+def _oneshot(rank, world):
+    """one-launch small all-reduce (NVLS / P2P one-shot, device-side launch counter) vs NCCL, many launches in a row"""
+    from quintnet_b200.ops import symm
+    dev = torch.device("cuda", rank)
+    g = dist.group.WORLD
+    for dtype, n in ((torch.bfloat16, 8 * 50 * 64), (torch.float32, 1), (torch.bfloat16, 100003), (torch.float32, 65536)):
+        for it in range(5):
+            torch.manual_seed(100 * rank + it)
+            x = torch.randn(n, device=dev).to(dtype)
+            ref = x.float().clone()
+            dist.all_reduce(ref)
+            y = symm.all_reduce_small(x, g, 1.0)
+            tol = 1e-5 if dtype == torch.float32 else 2e-2
+            err = ((y.float() - ref).abs().max() / ref.abs().max().clamp(min=1e-6)).item()
+            assert err < tol, (dtype, n, it, err)
+    # CUDA-graph replay: the launch counter lives on the device, so a captured launch stays in lock-step
+    x = torch.randn(4096, device=dev).to(torch.bfloat16)
+    symm.all_reduce_small(x, g)
+    torch.cuda.synchronize(); dist.barrier()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr):
+        y = symm.all_reduce_small(x, g)
+    for it in range(4):
+        x.copy_(torch.randn(4096, device=dev).to(torch.bfloat16))
+        ref = x.float().clone(); dist.all_reduce(ref)
+        gr.replay()
+        torch.cuda.synchronize()
+        assert ((y.float() - ref).abs().max() / ref.abs().max()).item() < 2e-2
+
+
 def _ddp_native(rank, world):
     """DataParallel with the NVLink backend == averaged reference gradients."""
     import torch.nn as nn
@@ -92,6 +122,10 @@ def _zero1_native(rank, world):
 
 def test_allreduce_kernel():
     run_distributed(_allreduce, 2, backend="nccl")
+
+
+def test_oneshot_small_allreduce():
+    run_distributed(_oneshot, 2, backend="nccl")
 
 
 def test_ddp_nvlink_backend():
@@ -238,6 +272,6 @@ _unvalidated = pytest.mark.gpu          # (were opt-in in round 1; they run by d
 
 @_unvalidated
 @pytest.mark.multigpu(4)
-@pytest.mark.parametrize("fn", ["_allreduce", "_zero1_native", "_tp_fused", "_sp_mlp"])
+@pytest.mark.parametrize("fn", ["_allreduce", "_oneshot", "_zero1_native", "_tp_fused", "_sp_mlp"])
 def test_in_kernel_collectives_world4(fn):
     run_distributed(globals()[fn], 4, backend="nccl")
