@@ -548,7 +548,8 @@ def run_vit(args):
     else:
         from quintnet_b200 import Trainer, get_strategy, init_process_groups
         from quintnet_b200.models import Model
-        cfg.update(dtype="float32" if args.cpu else "bfloat16", tp_method="paired")
+        cfg.update(dtype="float32" if args.cpu else "bfloat16", tp_method="paired",
+                   cuda_graphs=(not args.cpu) and os.environ.get("QN_VIT_GRAPHS", "1") == "1")
         dtype_name = "fp32" if args.cpu else "bf16"
     pg = init_process_groups(cfg["device_type"], cfg["mesh_dim"], cfg["mesh_name"])
     g = torch.Generator().manual_seed(100 + pg.get_coordinates_tensor_search(rank)[0])

@@ -82,6 +82,12 @@ def compose(model: Optional[nn.Module], pg_manager, config: dict, *, use_tp: boo
     """``stage_chunks``: the V model chunks of this rank for the interleaved (virtual-stage) pipeline."""
     device = resolve_device(pg_manager, config)
     dtype = resolve_dtype(config)
+    if use_pp and pg_manager.axis_size("pp") > 1 and bool(config.get("pp_direction_channels", True)):
+        # one communicator per pipeline direction: pre-posted activation receives overlap the running backward
+        from ..core.communication import register_pipeline_channels
+        fwd_g, bwd_g = pg_manager.device_mesh.get_channel_groups("pp", 2)
+        if fwd_g is not None and bwd_g is not None:
+            register_pipeline_channels(pg_manager.get_group("pp"), fwd_g, bwd_g)
     if stage_chunks is not None:
         from ..parallel.pipeline_parallel.interleaved import VirtualPipelineWrapper
         model = VirtualPipelineWrapper(stage_chunks, pg_manager.device_mesh, pg_manager.axis_rank("pp"),

@@ -296,6 +296,66 @@ def _peer(pp_group, pp_rank: int, delta: int) -> int:
     return dist.get_global_rank(pp_group, pp_rank + delta)
 
 
+# Direction channels.  NCCL executes the p2p operations of ONE communicator in issue order on one stream, so a receive
+# posted behind a send that still waits for its producer kernel cannot make progress.  With a dedicated communicator per
+# direction (activations travel on the forward channel, gradients on the backward channel) a pre-posted receive of the
+# NEXT micro-batch's activations completes while the current backward is still computing.  Registered per pp group by
+# ``coordinators.compose`` (``DeviceMesh.get_channel_groups``); without a registration both directions use the pp group.
+_channels: dict = {}
+
+
+def register_pipeline_channels(pp_group, fwd_group, bwd_group) -> None:
+    _channels[id(pp_group)] = (fwd_group, bwd_group)
+
+
+def _channel(pp_group, forward: bool):
+    ch = _channels.get(id(pp_group))
+    if ch is None:
+        return pp_group
+    return ch[0] if forward else ch[1]
+
+
+class PendingRecv:
+    """A receive that has been POSTED (its buffer is being filled by the communication stream) but not yet waited for."""
+
+    def __init__(self, buf: Optional[torch.Tensor], works, needs_grad: bool):
+        self.buf, self.works, self.needs_grad = buf, works, needs_grad
+
+    def wait(self) -> Optional[torch.Tensor]:
+        if self.buf is None:
+            return None
+        for w in self.works:
+            w.wait()                       # stream-ordered on CUDA: the compute stream waits, the host does not
+        self.works = []
+        if self.needs_grad:
+            self.buf.requires_grad_(True)
+        return self.buf
+
+
+def post_recv(direction: str, pp_group, pp_rank: int, device, dtype, shapes, is_first_stage: bool = False,
+              is_last_stage: bool = False) -> PendingRecv:
+    """Post the receive of the next activation (``direction='forward'``, from the previous stage) or gradient
+    (``'backward'``, from the next stage) and return immediately; ``.wait()`` when the tensor is consumed."""
+    fwd = direction == "forward"
+    if (fwd and is_first_stage) or (not fwd and is_last_stage):
+        return PendingRecv(None, [], False)
+    buf = torch.empty(tuple(shapes), device=device, dtype=dtype)
+    g = _channel(pp_group, fwd)
+    works = _launch([dist.P2POp(dist.irecv, buf, _peer(pp_group, pp_rank, -1 if fwd else +1), g)])
+    return PendingRecv(buf, works, fwd)
+
+
+def post_send(direction: str, pp_group, pp_rank: int, tensor: torch.Tensor, is_first_stage: bool = False,
+              is_last_stage: bool = False) -> None:
+    """Asynchronous send of an activation to the next stage (``'forward'``) or a gradient to the previous one."""
+    fwd = direction == "forward"
+    if (fwd and is_last_stage) or (not fwd and is_first_stage):
+        return
+    t = tensor.detach().contiguous()
+    g = _channel(pp_group, fwd)
+    _inflight.add(_launch([dist.P2POp(dist.isend, t, _peer(pp_group, pp_rank, +1 if fwd else -1), g)]), t)
+
+
 def _launch(ops):
     return dist.batch_isend_irecv(ops) if ops else []
 
@@ -321,31 +381,20 @@ def pipeline_communicate(
     if operation == "recv_forward":
         if is_first_stage:
             return None
-        buf = torch.empty(tuple(shapes), device=device, dtype=dtype)
-        works = _launch([dist.P2POp(dist.irecv, buf, _peer(pp_group, pp_rank, -1), pp_group)])
-        for w in works:
-            w.wait()
-        buf.requires_grad_(True)
-        out = buf
+        out = post_recv("forward", pp_group, pp_rank, device, dtype, shapes).wait()
     elif operation == "recv_backward":
         if is_last_stage:
             return None
-        buf = torch.empty(tuple(shapes), device=device, dtype=dtype)
-        works = _launch([dist.P2POp(dist.irecv, buf, _peer(pp_group, pp_rank, +1), pp_group)])
-        for w in works:
-            w.wait()
-        out = buf
+        out = post_recv("backward", pp_group, pp_rank, device, dtype, shapes).wait()
     elif operation == "send_forward":
         if is_last_stage:
             return None
-        t = tensor.detach().contiguous()
-        _inflight.add(_launch([dist.P2POp(dist.isend, t, _peer(pp_group, pp_rank, +1), pp_group)]), t)
+        post_send("forward", pp_group, pp_rank, tensor)
         out = None
     elif operation == "send_backward":
         if is_first_stage:
             return None
-        t = tensor.detach().contiguous()
-        _inflight.add(_launch([dist.P2POp(dist.isend, t, _peer(pp_group, pp_rank, -1), pp_group)]), t)
+        post_send("backward", pp_group, pp_rank, tensor)
         out = None
     else:
         raise ValueError(f"unknown pipeline operation {operation!r}")
@@ -382,17 +431,23 @@ def bidirectional_pipeline_communicate(
         peer, recv_needs_grad = _peer(pp_group, pp_rank, -1), True
     else:
         raise ValueError(f"unknown pipeline operation {operation!r}")
-    recv = torch.empty(tuple(recv_shapes), device=device, dtype=dtype)
-    t = send_tensor.detach().contiguous()
-    works = _launch([
-        dist.P2POp(dist.isend, t, peer, pp_group),
-        dist.P2POp(dist.irecv, recv, peer, pp_group),
-    ])
-    # with batch_isend_irecv the works complete together; waiting is stream-ordered on CUDA
-    for w in works:
-        w.wait()
-    if recv_needs_grad:
-        recv.requires_grad_(True)
+    send_fwd = operation == "send_fwd_recv_bwd"
+    if id(pp_group) in _channels:
+        # direction channels: the send stays in flight on its own communicator, only the receive is waited for
+        post_send("forward" if send_fwd else "backward", pp_group, pp_rank, send_tensor)
+        recv = post_recv("backward" if send_fwd else "forward", pp_group, pp_rank, device, dtype, recv_shapes).wait()
+    else:
+        recv = torch.empty(tuple(recv_shapes), device=device, dtype=dtype)
+        t = send_tensor.detach().contiguous()
+        works = _launch([
+            dist.P2POp(dist.isend, t, peer, pp_group),
+            dist.P2POp(dist.irecv, recv, peer, pp_group),
+        ])
+        # with batch_isend_irecv the works complete together; waiting is stream-ordered on CUDA
+        for w in works:
+            w.wait()
+        if recv_needs_grad:
+            recv.requires_grad_(True)
     if VERBOSE:
         STEP += 1
         print(f"[p2p {STEP}] rank {dist.get_rank()} {operation} peer={peer}", flush=True)

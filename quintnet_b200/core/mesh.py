@@ -112,6 +112,23 @@ class DeviceMesh:
             self._groups[name] = my_group
             self._group_ranks[name] = mine
 
+    def get_channel_groups(self, name: str, n: int = 2):
+        """``n`` extra process groups over this rank's fibre of axis ``name`` (same ranks, separate communicators) —
+        e.g. one per pipeline direction so that pre-posted receives do not queue behind sends.  COLLECTIVE: every rank of
+        the job must call it (all fibres are created canonically, like the axis groups).  Cached."""
+        key = f"{name}#channels{n}"
+        if key in self._groups:
+            return self._groups[key]
+        mine = [None] * n
+        if name in self.mesh_name and self.world_size > 1:
+            for ranks in self._all_fibres[name]:
+                for c in range(n):
+                    g = dist.new_group(ranks=ranks, backend=self.backend, timeout=self.timeout) if len(ranks) > 1 else None
+                    if self.rank in ranks:
+                        mine[c] = g
+        self._groups[key] = tuple(mine)
+        return self._groups[key]
+
     # ---------------------------------------------------------------- queries
     def axis_size(self, name: str) -> int:
         """Size of a named axis; an axis that is not part of the mesh has size 1."""

@@ -78,9 +78,12 @@ struct TpComm {
                                       // by the pumps once their flags are up) — the forward keeps it for the wgrad
                                       // GEMM of the backward pass without a separate clone of the gather buffer
   __nv_bfloat16* gather[TP_MAX];      // AG: every rank's gather buffer [M, K] (peer mappings)
-  uint32_t* ag_flags[TP_MAX];         // AG: every rank's per-8-row flags [M / 8]
+  uint32_t* ag_flags[TP_MAX];         // AG: every rank's flags: [kAgDoneBase + src] = "src's whole shard has landed" (pump /
+                                      // external), [kLocalCntBase] = this rank's grid-arrival counter; per-8-row flags
+                                      // [M / 8] in the round-1 LSU mode
   __nv_bfloat16* stage[TP_MAX];       // RS: every rank's staging buffer [world][slabs_per_rank] x 4 KB slab images
-  uint32_t* rs_flags[TP_MAX];         // RS: every rank's flags [slabs_per_rank][world]
+  uint32_t* rs_flags[TP_MAX];         // RS: every rank's flags: [kAgDoneBase + src] = "all of src's partial slabs for this rank
+                                      // have landed", [kLocalCntBase] = this rank's epilogue-warp arrival counter
   uint32_t ag_mode;                   // AG_PUMP: one bulk-copy pump thread per CTA (default); AG_LSU: two push warps
                                       // per CTA with 16-byte stores (round-1 kernel, kept for A/B timing);
                                       // AG_EXTERNAL: the shard is copied by someone else (copy engine on a side
@@ -90,8 +93,10 @@ struct TpComm {
 };
 
 constexpr uint32_t kAgDoneBase = 200000;      // flag index of the per-source "whole shard has landed" flags (external push)
-constexpr uint32_t kPumpSlot = 16384;         // AG pump: bytes per ring slot (one 8-row unit at K <= 1024)
-constexpr uint32_t kPumpRing = 2;
+constexpr uint32_t kLocalCntBase = kAgDoneBase + 32;   // index of this rank's own grid-arrival counter (same flag buffer)
+constexpr uint32_t kPumpSlot = 8192;          // AG pump: bytes per ring slot
+constexpr uint32_t kPumpRing = 4;             // 4 x 8 KB, loads issued kPumpAhead pieces ahead of the stores
+constexpr uint32_t kPumpAhead = 2;
 constexpr uint32_t kSmemLimit = 232448;       // 227 KB per CTA on sm_100a
 
 QN_DEVICE void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
@@ -222,7 +227,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t mb128 = m_blk * kMbPerTile + cta_rank;          // this CTA's 128-row block of A
           a_remote = (mb128 / tc.mb_per_rank) != static_cast<uint32_t>(tc.rank);
           if (a_remote && !(tc.debug & 4u)) {   // the peer's pushes of these 128 rows must have landed
-            if (tc.ag_mode == AG_EXTERNAL) {
+            if (tc.ag_mode != AG_LSU) {   // pump / external: ONE flag per source rank = "its whole shard has landed"
               if (lane == 0) wait_flag_ge(tc.ag_flags[tc.rank] + kAgDoneBase + mb128 / tc.mb_per_rank, tc.seq);
             } else if (lane < 16) {
               wait_flag_ge(tc.ag_flags[tc.rank] + mb128 * 16 + lane, tc.seq);                // 16 8-row units in parallel
@@ -325,81 +330,70 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (FUSE == FUSE_AG && warp == 3 && tc.ag_mode == AG_PUMP) {
     // ------------------------------------------------ all-gather copy pump (this rank's shard -> every rank)
-    // One thread.  Units of 8 rows (16*K bytes, contiguous in x_local and in every gather buffer) are dealt
-    // round-robin over the CTAs; a unit moves in pieces of <= kPumpSlot bytes: bulk load -> ring slot -> one bulk
-    // store per destination (peers over NVLink + the local gather buffer, which then holds the complete gathered
-    // operand for the weight-gradient GEMM).  A unit's flag is published when its store groups have COMPLETED
-    // (cp.async.bulk.wait_group without .read: the writes are performed), two groups behind the pump head.
-    if (lane == 0 && !(tc.debug & 8u)) {
-      const uint32_t units = tc.rows_per_rank / 8;
-      const uint32_t unit_bytes = 16u * p.K;
-      const uint32_t npiece = (unit_bytes + kPumpSlot - 1) / kPumpSlot;
+    // One thread per CTA.  The shard (contiguous in x_local and in every gather buffer) is cut into kPumpSlot-byte
+    // pieces dealt round-robin over the CTAs; a piece moves bulk load -> ring slot -> one bulk store per destination
+    // (peers over NVLink + the local copy, which makes the complete gathered operand available to the weight-gradient
+    // GEMM), loads running kPumpAhead pieces ahead of the stores.  NO per-piece completion wait or fence: a system
+    // fence drains the SM's outstanding NVLink writes, so publishing per unit serialised the pump on the link round
+    // trip (measured: round-1 LSU push and the first TMA pump both cost ~25-30 us per kernel).  Instead every pump
+    // waits ONCE for its store groups, fences once and arrives on a local counter; the last arrival of the grid
+    // publishes ONE flag per peer: "rank r's whole shard has landed".
+    if (lane == 0) {
+      const size_t shard_bytes = static_cast<size_t>(tc.rows_per_rank) * p.K * 2;
+      const uint32_t npieces = static_cast<uint32_t>((shard_bytes + kPumpSlot - 1) / kPumpSlot);
+      const uint32_t mine = (tc.debug & 8u) ? 0u : (npieces > blockIdx.x ? (npieces - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u);
       const uint8_t* src = reinterpret_cast<const uint8_t*>(tc.x_local);
-      const size_t shard_off = static_cast<size_t>(tc.rank) * tc.rows_per_rank * p.K * 2;
-      uint32_t cnt = 0;                              // pieces issued (= store groups committed)
-      uint32_t pend_u[3] = {0, 0, 0}, pend_g[3] = {0, 0, 0}, npend = 0;   // units whose last group is not yet known complete
-      auto publish = [&](uint32_t u) {
-        for (int pr = 1; pr < tc.world; ++pr)
-          st_relaxed_sys(tc.ag_flags[(tc.rank + pr) % tc.world] + tc.rank * units + u, tc.seq);
+      const size_t shard_off = static_cast<size_t>(tc.rank) * shard_bytes;
+      uint8_t* local_dst = reinterpret_cast<uint8_t*>(tc.x_full ? tc.x_full : tc.gather[tc.rank]);
+      uint32_t cnt = 0;                              // ring uses so far (slot = cnt % kPumpRing)
+      auto run = [&](const uint8_t* from, size_t base_off, bool to_peers, uint32_t n_mine, size_t total_bytes) {
+        for (uint32_t it = 0; it < n_mine + kPumpAhead; ++it) {
+          if (it < n_mine) {
+            const size_t off = static_cast<size_t>(blockIdx.x + it * gridDim.x) * kPumpSlot;
+            const uint32_t bytes = static_cast<uint32_t>(min(static_cast<size_t>(kPumpSlot), total_bytes - off));
+            const uint32_t slot = (cnt + it) % kPumpRing;
+            tma_store_wait_read<kPumpRing - kPumpAhead - 1>();     // the store that last read this slot has drained it
+            mbar_arrive_expect_tx(&pump_bar[slot], bytes);
+            bulk_load_1d(smem_ring + slot * kPumpSlot, from + off, bytes, &pump_bar[slot]);
+          }
+          if (it >= kPumpAhead) {
+            const uint32_t j = it - kPumpAhead;
+            const size_t off = static_cast<size_t>(blockIdx.x + j * gridDim.x) * kPumpSlot;
+            const uint32_t bytes = static_cast<uint32_t>(min(static_cast<size_t>(kPumpSlot), total_bytes - off));
+            const uint32_t slot = (cnt + j) % kPumpRing;
+            uint8_t* buf = smem_ring + slot * kPumpSlot;
+            mbar_wait(&pump_bar[slot], ((cnt + j) / kPumpRing) & 1);
+            if (to_peers)
+              for (int pr = 1; pr < tc.world; ++pr)
+                bulk_store_1d(reinterpret_cast<uint8_t*>(tc.gather[(tc.rank + pr) % tc.world]) + base_off + off, buf, bytes);
+            bulk_store_1d(local_dst + base_off + off, buf, bytes);
+            tma_store_commit();
+          }
+        }
+        cnt += n_mine;
       };
-      for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
-        for (uint32_t pc = 0; pc < npiece; ++pc) {
-          const uint32_t off_in_unit = pc * kPumpSlot;
-          const uint32_t bytes = min(kPumpSlot, unit_bytes - off_in_unit);
-          const size_t off = static_cast<size_t>(u) * unit_bytes + off_in_unit;
-          const uint32_t slot = cnt % kPumpRing;
-          uint8_t* buf = smem_ring + slot * kPumpSlot;
-          tma_store_wait_read<kPumpRing - 1>();      // the stores that last read this slot have drained it
-          mbar_arrive_expect_tx(&pump_bar[slot], bytes);
-          bulk_load_1d(buf, src + off, bytes, &pump_bar[slot]);
-          mbar_wait(&pump_bar[slot], (cnt / kPumpRing) & 1);
-          for (int pr = 1; pr < tc.world; ++pr)      // peers first, the local copy last
-            bulk_store_1d(reinterpret_cast<uint8_t*>(tc.gather[(tc.rank + pr) % tc.world]) + shard_off + off, buf, bytes);
-          bulk_store_1d(reinterpret_cast<uint8_t*>(tc.x_full ? tc.x_full : tc.gather[tc.rank]) + shard_off + off, buf, bytes);
-          tma_store_commit();
-          ++cnt;
-        }
-        // lazily publish: keep up to 3 units pending; the oldest one's groups are complete once at most 2 newer
-        // groups are outstanding
-        if (npend == 3) {
-          tma_store_wait_all<2>();                   // groups <= cnt - 3 complete; pend_g[0] <= cnt - 3 by construction
-          fence_proxy_async_all();
-          __threadfence_system();
-          publish(pend_u[0]);
-          pend_u[0] = pend_u[1]; pend_g[0] = pend_g[1]; pend_u[1] = pend_u[2]; pend_g[1] = pend_g[2];
-          npend = 2;
-        }
-        pend_u[npend] = u; pend_g[npend] = cnt; ++npend;
-      }
-      if (npend) {
-        tma_store_wait_all<0>();
-        fence_proxy_async_all();
+      run(src, shard_off, true, mine, shard_bytes);
+      tma_store_wait_all<0>();                       // every piece of this CTA has been performed at its destinations
+      fence_proxy_async_all();
+      __threadfence_system();
+      uint32_t* lcnt = tc.ag_flags[tc.rank] + kLocalCntBase;
+      uint32_t prev;
+      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(lcnt) : "memory");
+      if (prev == gridDim.x - 1) {                   // last pump of the grid: the whole shard is out
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(lcnt), "r"(0u) : "memory");
         __threadfence_system();
-        for (uint32_t i = 0; i < npend; ++i) publish(pend_u[i]);
+        for (int pr = 1; pr < tc.world; ++pr)
+          st_relaxed_sys(tc.ag_flags[(tc.rank + pr) % tc.world] + kAgDoneBase + tc.rank, tc.seq);
       }
-      // second duty (background): peers' rows, gather buffer -> x_full, as their units land
+      // second duty (background): peers' rows, gather buffer -> x_full, once their shards have landed
       if (tc.x_full != nullptr && !(tc.debug & 4u)) {
         for (int pr = 1; pr < tc.world; ++pr) {
           const uint32_t srcr = (tc.rank + pr) % tc.world;
-          const size_t src_off = static_cast<size_t>(srcr) * tc.rows_per_rank * p.K * 2;
-          for (uint32_t u = blockIdx.x; u < units; u += gridDim.x) {
-            wait_flag_ge(tc.ag_flags[tc.rank] + srcr * units + u, tc.seq);
-            fence_proxy_async_all();
-            for (uint32_t pc = 0; pc < npiece; ++pc) {
-              const uint32_t off_in_unit = pc * kPumpSlot;
-              const uint32_t bytes = min(kPumpSlot, unit_bytes - off_in_unit);
-              const size_t off = src_off + static_cast<size_t>(u) * unit_bytes + off_in_unit;
-              const uint32_t slot = cnt % kPumpRing;
-              uint8_t* buf = smem_ring + slot * kPumpSlot;
-              tma_store_wait_read<kPumpRing - 1>();
-              mbar_arrive_expect_tx(&pump_bar[slot], bytes);
-              bulk_load_1d(buf, reinterpret_cast<const uint8_t*>(tc.gather[tc.rank]) + off, bytes, &pump_bar[slot]);
-              mbar_wait(&pump_bar[slot], (cnt / kPumpRing) & 1);
-              bulk_store_1d(reinterpret_cast<uint8_t*>(tc.x_full) + off, buf, bytes);
-              tma_store_commit();
-              ++cnt;
-            }
-          }
+          wait_flag_ge(tc.ag_flags[tc.rank] + kAgDoneBase + srcr, tc.seq);
+          fence_proxy_async_all();
+          const uint32_t m2 = npieces > blockIdx.x ? (npieces - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+          run(reinterpret_cast<const uint8_t*>(tc.gather[tc.rank]) + static_cast<size_t>(srcr) * shard_bytes,
+              static_cast<size_t>(srcr) * shard_bytes, false, m2, shard_bytes);
         }
         tma_store_wait_all<0>();
       }
@@ -437,24 +431,28 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     uint8_t* sbuf = smem_epi + (warp - kEpiWarp0) * C::EPI_PER_WARP;
     uint8_t* srow = sbuf + lane * 128;
     uint32_t as = 0, aphase = 0, aux_phase = 0;
-    // FUSE_RS: slab counter (staging buffer = slab & 1; every slab commits exactly one bulk group) and the flags of
-    // remote slabs whose store group is not yet known to be complete (published two groups behind, one fence per pair)
+    // FUSE_RS: slab counter (staging buffer = slab & 1; every slab commits exactly one bulk group).  Remote slabs are
+    // fire-and-forget: no per-slab completion wait, fence or flag (a system fence drains the SM's outstanding NVLink
+    // writes — one per slab put the link round trip on the epilogue's critical path).  When a warp has issued its last
+    // remote slab (i.e. at its first own slab, or at the end of its tile loop) it waits ONCE for its store groups,
+    // fences once and arrives on a local counter; the last of the grid's epilogue warps publishes ONE flag per peer:
+    // "every partial slab rank r owes you has landed".  Own tiles come last, so that flag is normally up already.
     uint32_t rs_slab = 0;
-    uint32_t* pend0 = nullptr; uint32_t* pend1 = nullptr; uint32_t* pend2 = nullptr; uint32_t* pend3 = nullptr;
-    uint32_t npend = 0;
-    auto publish_pending = [&](bool all) {     // lane 0 only
-      if (npend == 0) return;
-      if (all) tma_store_wait_all<0>(); else tma_store_wait_all<2>();   // !all: called with 4 pending -> the oldest 2 are complete
+    bool rs_signaled = false, rs_peers_ready = false;
+    auto rs_signal = [&]() {                   // lane 0 only
+      if (rs_signaled) return;
+      rs_signaled = true;
+      tma_store_wait_all<0>();
       fence_proxy_async_all();
       __threadfence_system();
-      st_relaxed_sys(pend0, tc.seq);
-      if (npend > 1) st_relaxed_sys(pend1, tc.seq);
-      if (all) {
-        if (npend > 2) st_relaxed_sys(pend2, tc.seq);
-        if (npend > 3) st_relaxed_sys(pend3, tc.seq);
-        npend = 0;
-      } else {
-        pend0 = pend2; pend1 = pend3; npend -= 2;
+      uint32_t* lcnt = tc.rs_flags[tc.rank] + kLocalCntBase;
+      uint32_t prev;
+      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(lcnt) : "memory");
+      if (prev == gridDim.x * 8 - 1) {         // last epilogue warp of the grid
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(lcnt), "r"(0u) : "memory");
+        __threadfence_system();
+        for (int pr = 1; pr < tc.world; ++pr)
+          st_relaxed_sys(tc.rs_flags[(tc.rank + pr) % tc.world] + kAgDoneBase + tc.rank, tc.seq);
       }
     };
     for (uint32_t work = worker; work < num_work; work += n_cta) {
@@ -513,11 +511,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint64_t* ab = &aux_bar[warp - kEpiWarp0];
           ++rs_slab;
           if (lane == 0) {
+            if (mine) rs_signal();                 // everything this warp owes its peers is out before it starts waiting
             if (mine && !(tc.debug & 1u)) {
-              publish_pending(true);               // everything this warp sent is visible before it starts waiting
               tma_store_wait_read<0>();            // both staging buffers are free
               const uint32_t src = (tc.rank + 1) % tc.world;       // first peer's partial: load overlaps the TMEM read
-              wait_flag_ge(tc.rs_flags[tc.rank] + slab_id * tc.world + src, tc.seq);
+              if (!rs_peers_ready) {               // once per warp: every peer's partial slabs for this rank have landed
+                for (int pr = 1; pr < tc.world; ++pr)
+                  wait_flag_ge(tc.rs_flags[tc.rank] + kAgDoneBase + (tc.rank + pr) % tc.world, tc.seq);
+                rs_peers_ready = true;
+              }
               fence_proxy_async_all();
               mbar_arrive_expect_tx(ab, 4096);
               bulk_load_1d(pbuf, reinterpret_cast<const uint8_t*>(tc.stage[tc.rank]) +
@@ -559,8 +561,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               __syncwarp();
               if (pr + 1 < tc.world && lane == 0) {                 // next peer's partial into the same landing zone
                 const uint32_t src = (tc.rank + pr + 1) % tc.world;
-                wait_flag_ge(tc.rs_flags[tc.rank] + slab_id * tc.world + src, tc.seq);
-                fence_proxy_async_all();
                 mbar_arrive_expect_tx(ab, 4096);
                 bulk_load_1d(pbuf, reinterpret_cast<const uint8_t*>(tc.stage[tc.rank]) +
                                        (static_cast<size_t>(src) * slabs_per_rank + slab_id) * 4096, 4096, ab);
@@ -585,9 +585,6 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               bulk_store_1d(reinterpret_cast<uint8_t*>(tc.stage[owner]) +
                                 (static_cast<size_t>(tc.rank) * slabs_per_rank + slab_id) * 4096, obuf, 4096);
               tma_store_commit();
-              uint32_t* fl = tc.rs_flags[owner] + slab_id * tc.world + tc.rank;
-              if (npend == 0) pend0 = fl; else if (npend == 1) pend1 = fl; else if (npend == 2) pend2 = fl; else pend3 = fl;
-              if (++npend == 4) publish_pending(false);
             }
           }
           continue;
@@ -736,7 +733,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if constexpr (FUSE == FUSE_RS) { if (lane == 0) publish_pending(true); }
+    if constexpr (FUSE == FUSE_RS) { if (lane == 0) rs_signal(); }
     if (lane == 0) tma_store_wait_all<0>();
   }
 

@@ -229,7 +229,7 @@ ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                     const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean_in,
                     const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ dadd,
                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop, float* __restrict__ acc,
-                    int rows, int cols, const LnDropout dr) {
+                    int rows, int cols, const LnDropout dr, const int want_colsum) {
   extern __shared__ __align__(128) uint8_t lnf_smem[];
   __shared__ uint64_t full[LNF_STAGES];
   __shared__ float s_stat[LNF_STAGES][LNF_R][4];          // mean, rstd, c1, c2 per row
@@ -266,12 +266,14 @@ ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
       if (blk < nblk) issue(blk, st);
     }
   }
-  float g2[CV][8], ag[CV][8], ab[CV][8];
+  // ad: column sums of the gradient that leaves through the branch input (dx_drop, or dx without dropout) = the
+  // bias gradient of the Linear layer that produced the branch — saves that layer a separate column-sum pass
+  float g2[CV][8], ag[CV][8], ab[CV][8], ad[CV][8];
 #pragma unroll
   for (int j = 0; j < CV; ++j) {
     const int vi = c + 128 * j;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { ag[j][e] = 0.f; ab[j][e] = 0.f; g2[j][e] = 0.f; }
+    for (int e = 0; e < 8; ++e) { ag[j][e] = 0.f; ab[j][e] = 0.f; g2[j][e] = 0.f; ad[j][e] = 0.f; }
     if (vi < nvec) Vec<__nv_bfloat16>::load(reinterpret_cast<const __nv_bfloat16*>(s_gamma) + vi * 8, g2[j]);
   }
 
@@ -343,6 +345,10 @@ ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
             }
             Vec<__nv_bfloat16>::store(dx_drop + grow * cols + vi * 8, o);
           }
+          if (want_colsum) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) ad[j][e] += __bfloat162float(__float2bfloat16(o[e]));   // sum what was stored
+          }
         }
       }
     }
@@ -354,14 +360,14 @@ ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
   }
   // ---- dgamma / dbeta: fold the two row halves through shared memory, one vector reduction per thread
   __syncthreads();
-  float* red = reinterpret_cast<float*>(lnf_smem);          // [128 * CV][16]; the ring is idle now
+  float* red = reinterpret_cast<float*>(lnf_smem);          // [128 * CV][24]; the ring is idle now
   if (h == 1) {
 #pragma unroll
     for (int j = 0; j < CV; ++j) {
       const int vi = c + 128 * j;
-      if (vi < nvec) {                                     // the scratch is only nvec * 64 bytes deep
+      if (vi < nvec) {                                     // the scratch is only nvec * 96 bytes deep
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { red[vi * 16 + e] = ag[j][e]; red[vi * 16 + 8 + e] = ab[j][e]; }
+        for (int e = 0; e < 8; ++e) { red[vi * 24 + e] = ag[j][e]; red[vi * 24 + 8 + e] = ab[j][e]; red[vi * 24 + 16 + e] = ad[j][e]; }
       }
     }
   }
@@ -372,7 +378,13 @@ ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
       const int vi = c + 128 * j;
       if (vi < nvec) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { ag[j][e] += red[vi * 16 + e]; ab[j][e] += red[vi * 16 + 8 + e]; }
+        for (int e = 0; e < 8; ++e) { ag[j][e] += red[vi * 24 + e]; ab[j][e] += red[vi * 24 + 8 + e]; ad[j][e] += red[vi * 24 + 16 + e]; }
+        if (want_colsum) {
+#pragma unroll
+          for (int q = 0; q < 2; ++q)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(acc + 2 * cols + vi * 8 + q * 4), "f"(ad[j][q * 4 + 0]),
+                         "f"(ad[j][q * 4 + 1]), "f"(ad[j][q * 4 + 2]), "f"(ad[j][q * 4 + 3]) : "memory");
+        }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(acc + vi * 8 + q * 4), "f"(ag[j][q * 4 + 0]),
@@ -388,7 +400,7 @@ ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
 template <int CV, bool HAS_ADD>
 static int launch_ln_bwd_fused(const void* dy, const void* x, const void* g, const float* mean, const float* rstd,
                                const void* dadd, void* dx, void* dx_drop, float* acc, int rows, int cols,
-                               const LnDropout dr, cudaStream_t s) {
+                               const LnDropout dr, cudaStream_t s, int want_colsum = 0) {
   const int nt = HAS_ADD ? 3 : 2;
   const int smem = LNF_STAGES * nt * LNF_R * cols * 2 + cols * 2;
   auto k = ln_bwd_fused_kernel<CV, HAS_ADD>;
@@ -399,14 +411,18 @@ static int launch_ln_bwd_fused(const void* dy, const void* x, const void* g, con
   const int grid = min(nblk, 148 * per_sm);
   using B = __nv_bfloat16;
   k<<<grid, LNF_THREADS, smem, s>>>((const B*)dy, (const B*)x, (const B*)g, mean, rstd, (const B*)dadd, (B*)dx,
-                                   (B*)dx_drop, acc, rows, cols, dr);
+                                   (B*)dx_drop, acc, rows, cols, dr, want_colsum);
   return static_cast<int>(cudaGetLastError());
 }
 
 template <typename T>
-__global__ void ln_finalize_kernel(const float* __restrict__ acc, T* __restrict__ dgamma, T* __restrict__ dbeta, int cols) {
+__global__ void ln_finalize_kernel(const float* __restrict__ acc, T* __restrict__ dgamma, T* __restrict__ dbeta, int cols,
+                                   T* __restrict__ colsum = nullptr) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c < cols) { dgamma[c] = static_cast<T>(acc[c]); dbeta[c] = static_cast<T>(acc[cols + c]); }
+  if (c < cols) {
+    dgamma[c] = static_cast<T>(acc[c]); dbeta[c] = static_cast<T>(acc[cols + c]);
+    if (colsum != nullptr) colsum[c] = static_cast<T>(acc[2 * cols + c]);
+  }
 }
 
 template <typename T>
@@ -436,22 +452,24 @@ static int ln_fwd(const void* x, const void* res, const void* g, const void* b, 
 template <typename T>
 static int ln_bwd(const void* dy, const void* x, const void* g, const float* mean, const float* rstd,
                   const void* dadd, void* dx, void* dgamma, void* dbeta, float* workspace, int nparts, int rows,
-                  int cols, void* dx_drop, const LnDropout dr, cudaStream_t s) {
+                  int cols, void* dx_drop, const LnDropout dr, cudaStream_t s, void* colsum = nullptr) {
   constexpr int VN = Vec<T>::N;
   if (cols % VN || cols > 32 * LN_MAXV * VN) return 920;
   (void)nparts;
   if (sizeof(T) == 2 && cols <= 2048 && rows >= 64 && getenv("QN_LN_BWD_SPLIT") == nullptr) {
     // fused single-pass kernel (bf16): fp32 accumulators [2 * cols] in the workspace, then bf16 conversion
-    cudaMemsetAsync(workspace, 0, 2ull * cols * sizeof(float), s);
+    const int wc = colsum != nullptr ? 1 : 0;
+    cudaMemsetAsync(workspace, 0, (2ull + wc) * cols * sizeof(float), s);
     int rc;
-    if (cols <= 1024) rc = dadd ? launch_ln_bwd_fused<1, true>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s)
-                                : launch_ln_bwd_fused<1, false>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s);
-    else rc = dadd ? launch_ln_bwd_fused<2, true>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s)
-                   : launch_ln_bwd_fused<2, false>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s);
+    if (cols <= 1024) rc = dadd ? launch_ln_bwd_fused<1, true>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s, wc)
+                                : launch_ln_bwd_fused<1, false>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s, wc);
+    else rc = dadd ? launch_ln_bwd_fused<2, true>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s, wc)
+                   : launch_ln_bwd_fused<2, false>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s, wc);
     if (rc) return rc;
-    ln_finalize_kernel<T><<<(cols + 255) / 256, 256, 0, s>>>(workspace, (T*)dgamma, (T*)dbeta, cols);
+    ln_finalize_kernel<T><<<(cols + 255) / 256, 256, 0, s>>>(workspace, (T*)dgamma, (T*)dbeta, cols, (T*)colsum);
     return static_cast<int>(cudaGetLastError());
   }
+  if (colsum != nullptr) return 921;          // only the fused single-pass kernel produces the column sums
   int grid = (rows + LN_WARPS - 1) / LN_WARPS;
   if (grid > 148 * 16) grid = 148 * 16;
   const int mv = (cols / VN + 31) / 32;
@@ -514,12 +532,15 @@ extern "C" int qn_layernorm_bwd(const void* dy, const void* x, const void* gamma
 }
 
 // backward of qn_dropout_add_layernorm_fwd:  dres = LN'(dy) + dsum ;  dx = dropout'(dres)
+//   colsum (optional, bf16 [cols]): column sums of the gradient w.r.t. the branch input x (dx, or dres when p == 0) — the
+//   bias gradient of the Linear that produced x; needs the fused kernel (cols <= 2048, rows >= 64), else error 921.
 extern "C" int qn_dropout_add_layernorm_bwd(const void* dy, const void* h, const void* gamma, const float* mean,
                                             const float* rstd, const void* dsum, void* dres, void* dx, void* dgamma,
                                             void* dbeta, float* workspace, int nparts, int rows, int cols, float p,
-                                            unsigned long long seed, unsigned long long offset, cudaStream_t s) {
+                                            unsigned long long seed, unsigned long long offset, void* colsum,
+                                            cudaStream_t s) {
   qn::LnDropout dr{0u, 1.0f, seed, offset};
   if (p > 0.f) { dr.threshold = (uint32_t)(p * 65536.0f); dr.scale = 1.0f / (1.0f - dr.threshold / 65536.0f); }
   return qn::ln_bwd<__nv_bfloat16>(dy, h, gamma, mean, rstd, dsum, dres, dgamma, dbeta, workspace, nparts, rows, cols,
-                                   dx, dr, s);
+                                   dx, dr, s, colsum);
 }

@@ -10,6 +10,7 @@ row-major contiguous bf16, leading dimensions multiples of 8 elements.
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -271,7 +272,26 @@ def mlp_ok(x, w1, b1, w2, b2) -> bool:
             and all(t.data_ptr() % 16 == 0 for t in ts) and M % 8 == 0)
 
 
+# Bias gradients that a producer kernel already computed (the fused LayerNorm backward sums the columns of the gradient
+# it hands to the branch): keyed by the gradient tensor's address, valid only while that very tensor object is alive
+# (weak reference) — a freed-and-reused address can never hit.
+import weakref
+
+_COLSUM_CACHE = {}
+
+
+def offer_colsum(grad: torch.Tensor, cs: torch.Tensor) -> None:
+    if len(_COLSUM_CACHE) > 64:
+        _COLSUM_CACHE.clear()
+    _COLSUM_CACHE[grad.data_ptr()] = (weakref.ref(grad), cs, grad.numel())
+
+
 def colsum(x2: torch.Tensor) -> torch.Tensor:
+    ent = _COLSUM_CACHE.pop(x2.data_ptr(), None)
+    if ent is not None:
+        ref, cs, n = ent
+        if ref() is not None and n == x2.numel() and cs.numel() == x2.shape[-1]:
+            return cs
     rows, cols = x2.shape
     acc = torch.empty(cols, dtype=torch.float32, device=x2.device)
     out = torch.empty(cols, dtype=torch.bfloat16, device=x2.device)
@@ -495,15 +515,21 @@ class _DropoutAddLayerNorm(torch.autograd.Function):
         dg = torch.empty(cols, dtype=h.dtype, device=h.device)
         db = torch.empty(cols, dtype=h.dtype, device=h.device)
         nparts = min(_LN_PARTS, (rows + 3) // 4)
-        ws = torch.empty(2 * nparts * cols, dtype=torch.float32, device=h.device)
+        ws = torch.empty(max(2 * nparts, 3) * cols, dtype=torch.float32, device=h.device)
+        # the fused single-pass kernel also sums the columns of the branch gradient (= bias gradient of the Linear
+        # that produced the branch output): offered to that layer's backward through the colsum cache
+        fused = cols <= 2048 and rows >= 64 and os.environ.get("QN_LN_BWD_SPLIT") is None and ctx.needs_input_grad[0]
+        cs = torch.empty(cols, dtype=h.dtype, device=h.device) if fused else None
         rc = _lib().qn_dropout_add_layernorm_bwd(dy2.data_ptr(), h.data_ptr(), w.data_ptr(), mean.data_ptr(),
                                                  rstd.data_ptr(), native.ptr(dh2), dres.data_ptr(), native.ptr(dx),
                                                  dg.data_ptr(), db.data_ptr(), ws.data_ptr(), nparts, rows, cols,
-                                                 p, seed, off, native.stream())
+                                                 p, seed, off, native.ptr(cs), native.stream())
         native.check(rc, "qn_dropout_add_layernorm_bwd")
         native.count(2)
         dres_v = dres.view(shape)
         dx_v = dx.view(shape) if dx is not None else dres_v
+        if cs is not None and dx is not None:        # (p == 0: dx aliases dres, which also feeds the residual stream)
+            offer_colsum(dx_v, cs)
         return dx_v, dres_v, dg.to(wdtype), db.to(wdtype), None, None
 
 

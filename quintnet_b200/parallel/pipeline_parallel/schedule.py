@@ -30,7 +30,7 @@ from typing import List, Optional
 import torch
 
 from ...core.communication import (bidirectional_pipeline_communicate, drain_pipeline_sends,
-                                   pipeline_communicate)
+                                   pipeline_communicate, post_recv, post_send)
 
 
 def unwrap_stage(model):
@@ -185,20 +185,25 @@ class OneFOneBSchedule(PipelineSchedule):
             inputs.append(x)
             outputs.append(y)
 
+        # steady state with PRE-POSTED receives: the gradient of the oldest in-flight micro-batch and the activations of
+        # the NEXT micro-batch are both posted before the backward runs, so they arrive on the communication streams
+        # (one communicator per direction, see core/communication.py) while this stage computes; sends stay in flight.
+        kw = dict(pp_group=t.pp_group, pp_rank=t.rank, is_first_stage=t.is_first_stage, is_last_stage=t.is_last_stage)
         x = self._comm("recv_forward", device, dtype, tensor_shapes) if n_steady > 0 else None
         for i in range(n_steady):
             last = i == n_steady - 1
             y = self._forward_step(x, data_loader, device, M)
-            g = self._bidir("send_fwd_recv_bwd", y, device, dtype, tensor_shapes)
+            if not t.is_last_stage:
+                post_send("forward", tensor=y, **kw)
+            g_pending = post_recv("backward", device=device, dtype=dtype, shapes=tensor_shapes, **kw)
+            x_pending = None if last else post_recv("forward", device=device, dtype=dtype, shapes=tensor_shapes, **kw)
             inputs.append(x)
             outputs.append(y)
             bx, by = inputs.pop(0), outputs.pop(0)
-            gx = self._backward_step(bx, by, g, M)
-            if last:
-                x = None
-                self._comm("send_backward", device, dtype, tensor_shapes, tensor=gx)
-            else:
-                x = self._bidir("send_bwd_recv_fwd", gx, device, dtype, tensor_shapes)
+            gx = self._backward_step(bx, by, g_pending.wait(), M)
+            if not t.is_first_stage:
+                post_send("backward", tensor=gx, **kw)
+            x = x_pending.wait() if x_pending is not None else None
 
         for _ in range(n_warm):
             bx, by = inputs.pop(0), outputs.pop(0)

@@ -73,6 +73,35 @@ class PipelineParallelWrapper(nn.Module):
             raise RuntimeError("tensor shapes unknown for this stage")
         return (batch_size,) + tuple(self.tensor_shapes)
 
+    # ------------------------------------------------------------ CUDA graphs
+    def enable_cuda_graphs(self, input_shape, dtype, input_is_float: bool = True) -> bool:
+        """Capture this stage's micro-batch forward AND backward into CUDA graphs (``torch.cuda.make_graphed_callables``):
+        the latency-bound regime (ViT-MNIST: a stage is ~150 kernels of a few microseconds each) is bound by launch
+        overhead, and a replay is two launches.  Every kernel of this library is capture-safe (raw launches on the
+        current stream, tensor maps / descriptors baked at capture, device-side launch counters in the one-shot
+        all-reduce), and NCCL collectives record into the graph.  Shapes become static: only micro-batches of exactly
+        ``input_shape`` take the graphed path (others run eagerly).  Returns False (and stays eager) if capture fails."""
+        if not (torch.cuda.is_available() and str(self.device).startswith("cuda")):
+            return False
+        try:
+            sample = torch.randn(tuple(input_shape), device=self.device, dtype=dtype)
+            if not self.is_first_stage and input_is_float:
+                sample.requires_grad_(True)
+            eager = self.local_module
+            was_training = eager.training
+            eager.train()
+            graphed = torch.cuda.make_graphed_callables(eager, (sample,), num_warmup_iters=3)
+            eager.train(was_training)
+            self.local_module = graphed
+            self._graphed_shape = tuple(input_shape)
+            for p in self.local_module.parameters():      # the warm-up / capture backward passes left garbage gradients
+                p.grad = None
+            return True
+        except Exception as e:  # noqa: BLE001 — capture is an optimisation; report and stay eager
+            print(f"[quintnet_b200] CUDA-graph capture of pipeline stage {self.rank} failed, running eagerly: "
+                  f"{type(e).__name__}: {str(e)[:300]}", flush=True)
+            return False
+
     # -------------------------------------------------------------- execution
     def forward(self, x, **kwargs):
         if kwargs:

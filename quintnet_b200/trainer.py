@@ -121,6 +121,29 @@ class Trainer(_TrainerBase):
         mb = self.micro_batch_size()
         self.config["micro_batch_size"] = mb
         self.tensor_shapes = tuple(self.model.get_tensor_shapes(mb))
+        if self.config.get("cuda_graphs", False):
+            self._enable_stage_graphs(mb)
+
+    def _enable_stage_graphs(self, mb: int):
+        """``cuda_graphs: true`` — graph the per-micro-batch stage body (forward + backward): see
+        ``PipelineParallelWrapper.enable_cuda_graphs``.  The gradient buckets are re-zeroed afterwards (capture ran
+        warm-up backward passes through the DP hooks)."""
+        from .parallel.pipeline_parallel.wrapper import PipelineParallelWrapper
+        m = self.model.model if (hasattr(self.model, "bucket_manager") and hasattr(self.model, "model")) else self.model
+        if not isinstance(m, PipelineParallelWrapper):
+            return
+        if m.is_first_stage:
+            shape = (mb, int(self.config.get("in_channels", 1)), int(self.config.get("img_size", 28)),
+                     int(self.config.get("img_size", 28)))
+        else:
+            shape = self.tensor_shapes
+        is_ddp = hasattr(self.model, "require_backward_grad_sync")
+        if is_ddp:
+            self.model.require_backward_grad_sync = False
+        self.graphed = m.enable_cuda_graphs(shape, self.dtype)
+        if is_ddp:
+            self.model.require_backward_grad_sync = True
+        zero_grads(self.model, self.optimizer)
 
     # -------------------------------------------------------------------- fit
     def fit(self):

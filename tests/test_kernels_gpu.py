@@ -450,3 +450,30 @@ def test_vit_block_uses_no_library_attention():
     names = [e.key for e in prof.key_averages()]
     assert any("small_attn_fwd" in n for n in names) and any("small_attn_bwd" in n for n in names), names
     assert not any(("fmha" in n.lower() or "flash" in n.lower() or "sdpa" in n.lower()) for n in names), names
+
+
+def test_layernorm_bwd_offers_bias_gradient():
+    """The fused LayerNorm backward also produces the column sums of the branch gradient (= bias gradient of the Linear
+    that fed the branch); the next backward op picks them up instead of launching a column-sum pass."""
+    from quintnet_b200.ops import cuda_ops
+    torch.manual_seed(7)
+    rows, cols = 4096, 1024
+    x0 = torch.randn(rows, cols, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    r = torch.randn(rows, cols, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    g = torch.randn(cols, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    b = torch.randn(cols, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    x = x0 * 1.0                                       # non-leaf: its gradient is the very tensor the LN backward returned
+    seen = []
+    x.register_hook(lambda gr: seen.append(gr))
+    y, h = cuda_ops.dropout_add_layer_norm(x, r, g, b, 1e-5, 0.1)
+    cuda_ops._COLSUM_CACHE.clear()
+    (y.float().pow(2).sum() + h.float().sum()).backward()
+    gx = seen[0]
+    ent = cuda_ops._COLSUM_CACHE.get(gx.data_ptr())
+    assert ent is not None and ent[0]() is not None
+    ref = gx.float().sum(0)
+    got = cuda_ops.colsum(gx.reshape(rows, cols))      # served from the cache (no kernel): same values as a fresh sum
+    assert gx.data_ptr() not in cuda_ops._COLSUM_CACHE
+    assert _rel(got, ref) < 1e-2, _rel(got, ref)
+    fresh = cuda_ops.colsum(gx.reshape(rows, cols))    # cache is empty now: the stand-alone kernel
+    assert _rel(fresh, ref) < 1e-2
