@@ -138,28 +138,41 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
 
   if (warp == 4) {
     // ------------------------------------------------ TMA producer (persistent: prefetches across work items)
-    if (lane == 0) {
+    // (the whole warp walks the loops with warp-uniform values; one elected lane issues — see the GEMM's MMA issuer)
+    {
       uint32_t kvc = 0, nitem = 0;                       // running K/V stage counter, items done
       for (uint32_t item = blockIdx.x; item < num_items; item += gridDim.x, ++nitem) {
         uint32_t qb, h, b;
         fwd_item(item, p, nq, qb, h, b);
         const uint32_t nkv = p.causal ? min(qb + 1, nkv_total) : nkv_total;
         mbar_wait(q_empty, (nitem & 1) ^ 1);             // previous item's S MMAs are done with the Q tile
-        mbar_arrive_expect_tx(q_full, TILE);
-        tma_load_4d(smem + FwdSmem::Q, &tmap, q_full, 0, h, qb * BQ, b);                   // slot 0*H + h
+        if (elect_one()) {
+          mbar_arrive_expect_tx(q_full, TILE);
+          tma_load_4d(smem + FwdSmem::Q, &tmap, q_full, 0, h, qb * BQ, b);                 // slot 0*H + h
+        }
+        __syncwarp();
         for (uint32_t j = 0; j < nkv; ++j, ++kvc) {
           const uint32_t s = kvc & 1, ph = (kvc >> 1) & 1;
           mbar_wait(&kv_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&kv_full[s], 2 * TILE);
-          tma_load_4d(smem + FwdSmem::K + s * TILE, &tmap, &kv_full[s], 0, p.H + h, j * BKV, b);
-          tma_load_4d(smem + FwdSmem::V + s * TILE, &tmap, &kv_full[s], 0, 2 * p.H + h, j * BKV, b);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&kv_full[s], 2 * TILE);
+            tma_load_4d(smem + FwdSmem::K + s * TILE, &tmap, &kv_full[s], 0, p.H + h, j * BKV, b);
+            tma_load_4d(smem + FwdSmem::V + s * TILE, &tmap, &kv_full[s], 0, 2 * p.H + h, j * BKV, b);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == 5) {
     // ---------------------------------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // Whole warp, warp-uniform control flow; only the tcgen05 instructions sit behind elect_one().  (Issuing from a
+    // divergent `lane == 0` region made the compiler wrap every MMA in an ELECT / R2UR / branch waterfall of ~40 SASS
+    // instructions: 12 MMAs per key block were paced by a single thread's instruction latency, not by the tensor pipe.)
+    {
       const uint32_t sQ = smem_u32(smem + FwdSmem::Q), sP = smem_u32(smem + FwdSmem::P);
+      const uint64_t dK0 = make_smem_desc_sw128(0, 1024, 0), dMN0 = make_smem_desc_sw128(0, 1024, TILE);
+      auto kdesc = [&](uint32_t addr) { return dK0 | static_cast<uint64_t>((addr & 0x3FFFF) >> 4); };
+      auto mndesc = [&](uint32_t addr) { return dMN0 | static_cast<uint64_t>((addr & 0x3FFFF) >> 4); };
       uint32_t kvc = 0, itc = 0, nitem = 0;
       for (uint32_t item = blockIdx.x; item < num_items; item += gridDim.x, ++nitem) {
         uint32_t qb, h, b;
@@ -171,20 +184,24 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
           const uint32_t sK = smem_u32(smem + FwdSmem::K + s * TILE), sV = smem_u32(smem + FwdSmem::V + s * TILE);
           mbar_wait(&kv_full[s], ph);
           tcgen05_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (uint32_t k = 0; k < D / 16; ++k)
-            umma_bf16_ss(tmem_S, make_smem_desc_sw128(sQ + k * 32, 1024, 0), make_smem_desc_sw128(sK + k * 32, 1024, 0),
-                         IDESC_S, k != 0);
-          umma_commit(s_full);
-          if (j + 1 == nkv) umma_commit(q_empty);        // Q may be overwritten by the next item's load
+            for (uint32_t k = 0; k < D / 16; ++k)
+              umma_bf16_ss(tmem_S, kdesc(sQ + k * 32), kdesc(sK + k * 32), IDESC_S, k != 0);
+            umma_commit(s_full);
+            if (j + 1 == nkv) umma_commit(q_empty);      // Q may be overwritten by the next item's load
+          }
+          __syncwarp();
           mbar_wait(p_full, itc & 1);
           tcgen05_fence_after();
+          if (elect_one()) {
 #pragma unroll
-          for (uint32_t k = 0; k < BKV / 16; ++k)
-            umma_bf16_ss(tmem_O, make_smem_desc_sw128(sP + (k >> 2) * TILE + (k & 3) * 32, 1024, 0),
-                         make_smem_desc_sw128(sV + k * 2048, 1024, TILE), IDESC_PV, k != 0);
-          umma_commit(&kv_empty[s]);
-          umma_commit(o_full);
+            for (uint32_t k = 0; k < BKV / 16; ++k)
+              umma_bf16_ss(tmem_O, kdesc(sP + (k >> 2) * TILE + (k & 3) * 32), mndesc(sV + k * 2048), IDESC_PV, k != 0);
+            umma_commit(&kv_empty[s]);
+            umma_commit(o_full);
+          }
+          __syncwarp();
         }
       }
     }
@@ -400,7 +417,7 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
   const uint32_t tmem_S = tmem, tmem_dP = tmem + 128, tmem_dV = tmem + 256, tmem_dK = tmem + 320, tmem_dQ = tmem + 384;
 
   if (warp == kTmaWarp) {
-    if (lane == 0) {
+    {   // whole warp, one elected lane issues
       uint32_t qc = 0, nitem = 0;
       for (uint32_t item = blockIdx.x; item < num_items; item += gridDim.x, ++nitem) {
         uint32_t kb, h, b;
@@ -408,22 +425,31 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         const uint32_t qb_first = p.causal ? kb : 0, niter = nq_total - qb_first;
         const uint32_t kvb = nitem & 1, kph = (nitem >> 1) & 1;
         mbar_wait(&kv_empty[kvb], kph ^ 1);
-        mbar_arrive_expect_tx(&kv_full[kvb], 2 * TILE);
-        tma_load_4d(smem + BwdSmem::K + kvb * TILE, &tmap_qkv, &kv_full[kvb], 0, p.H + h, kb * BKV, b);
-        tma_load_4d(smem + BwdSmem::V + kvb * TILE, &tmap_qkv, &kv_full[kvb], 0, 2 * p.H + h, kb * BKV, b);
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&kv_full[kvb], 2 * TILE);
+          tma_load_4d(smem + BwdSmem::K + kvb * TILE, &tmap_qkv, &kv_full[kvb], 0, p.H + h, kb * BKV, b);
+          tma_load_4d(smem + BwdSmem::V + kvb * TILE, &tmap_qkv, &kv_full[kvb], 0, 2 * p.H + h, kb * BKV, b);
+        }
+        __syncwarp();
         for (uint32_t it = 0; it < niter; ++it, ++qc) {
           const uint32_t s = qc & 1, ph = (qc >> 1) & 1;
           const uint32_t q0 = (qb_first + it) * BQ;
           mbar_wait(&q_empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&q_full[s], 2 * TILE);
-          tma_load_4d(smem + BwdSmem::Q + s * TILE, &tmap_qkv, &q_full[s], 0, h, q0, b);
-          tma_load_4d(smem + BwdSmem::DO + s * TILE, &tmap_do, &q_full[s], 0, h, q0, b);
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&q_full[s], 2 * TILE);
+            tma_load_4d(smem + BwdSmem::Q + s * TILE, &tmap_qkv, &q_full[s], 0, h, q0, b);
+            tma_load_4d(smem + BwdSmem::DO + s * TILE, &tmap_do, &q_full[s], 0, h, q0, b);
+          }
+          __syncwarp();
         }
       }
     }
   } else if (warp == kMmaWarp) {
-    if (lane == 0) {
+    {   // whole warp, warp-uniform control flow; tcgen05 instructions behind elect_one() (see the forward kernel)
       const uint32_t sP = smem_u32(smem + BwdSmem::P), sDS = smem_u32(smem + BwdSmem::DS);
+      const uint64_t dK0 = make_smem_desc_sw128(0, 1024, 0), dMN0 = make_smem_desc_sw128(0, 1024, TILE);
+      auto kdesc = [&](uint32_t addr) { return dK0 | static_cast<uint64_t>((addr & 0x3FFFF) >> 4); };
+      auto mndesc = [&](uint32_t addr) { return dMN0 | static_cast<uint64_t>((addr & 0x3FFFF) >> 4); };
       uint32_t qc = 0, itc = 0, nitem = 0;
       for (uint32_t item = blockIdx.x; item < num_items; item += gridDim.x, ++nitem) {
         uint32_t kb, h, b;
@@ -431,23 +457,25 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
         const uint32_t qb_first = p.causal ? kb : 0, niter = nq_total - qb_first;
         const uint32_t kvb = nitem & 1;
         const uint32_t sK = smem_u32(smem + BwdSmem::K + kvb * TILE), sV = smem_u32(smem + BwdSmem::V + kvb * TILE);
-        auto issue_s_dp = [&](uint32_t q_count) {     // S = Q·Kᵀ, dP = dO·Vᵀ of the query block in ring slot q_count
-          const uint32_t s = q_count & 1, ph = (q_count >> 1) & 1;
-          const uint32_t sQ = smem_u32(smem + BwdSmem::Q + s * TILE), sDO = smem_u32(smem + BwdSmem::DO + s * TILE);
-          mbar_wait(&q_full[s], ph);
+        auto wait_q = [&](uint32_t q_count) {         // all lanes: the query block in ring slot q_count has landed
+          mbar_wait(&q_full[q_count & 1], (q_count >> 1) & 1);
           tcgen05_fence_after();
+        };
+        auto issue_s_dp = [&](uint32_t q_count) {     // elected lane: S = Q·Kᵀ, dP = dO·Vᵀ of that query block
+          const uint32_t s = q_count & 1;
+          const uint32_t sQ = smem_u32(smem + BwdSmem::Q + s * TILE), sDO = smem_u32(smem + BwdSmem::DO + s * TILE);
 #pragma unroll
           for (uint32_t k = 0; k < D / 16; ++k)
-            umma_bf16_ss(tmem_S, make_smem_desc_sw128(sQ + k * 32, 1024, 0), make_smem_desc_sw128(sK + k * 32, 1024, 0),
-                         IDESC_S, k != 0);
+            umma_bf16_ss(tmem_S, kdesc(sQ + k * 32), kdesc(sK + k * 32), IDESC_S, k != 0);
 #pragma unroll
           for (uint32_t k = 0; k < D / 16; ++k)
-            umma_bf16_ss(tmem_dP, make_smem_desc_sw128(sDO + k * 32, 1024, 0), make_smem_desc_sw128(sV + k * 32, 1024, 0),
-                         IDESC_S, k != 0);
+            umma_bf16_ss(tmem_dP, kdesc(sDO + k * 32), kdesc(sV + k * 32), IDESC_S, k != 0);
           umma_commit(sdp_full);
         };
         mbar_wait(&kv_full[kvb], (nitem >> 1) & 1);
-        issue_s_dp(qc);
+        wait_q(qc);
+        if (elect_one()) issue_s_dp(qc);
+        __syncwarp();
         for (uint32_t it = 0; it < niter; ++it, ++qc, ++itc) {
           const uint32_t s = qc & 1;
           const uint32_t sQ = smem_u32(smem + BwdSmem::Q + s * TILE), sDO = smem_u32(smem + BwdSmem::DO + s * TILE);
@@ -455,28 +483,32 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_const
           tcgen05_fence_after();
           // the next block's S / dP go FIRST so the compute warps can start on them while the tensor pipe
           // is busy with this block's dV / dK / dQ
-          if (it + 1 < niter) issue_s_dp(qc + 1);
+          if (it + 1 < niter) wait_q(qc + 1);
           if (it == 0 && nitem > 0) {                  // previous item's dK / dV must have been read out
             mbar_wait(dkdv_empty, (nitem - 1) & 1);
             tcgen05_fence_after();
           }
+          if (elect_one()) {
+            if (it + 1 < niter) issue_s_dp(qc + 1);
 #pragma unroll
-          for (uint32_t k = 0; k < BQ / 16; ++k)     // dV += Pᵀ · dO   (A = P as MN-major, B = dO as MN-major)
-            umma_bf16_ss(tmem_dV, make_smem_desc_sw128(sP + k * 2048, 1024, TILE), make_smem_desc_sw128(sDO + k * 2048, 1024, TILE),
-                         IDESC_TT, (it | k) != 0);
+            for (uint32_t k = 0; k < BQ / 16; ++k)     // dV += Pᵀ · dO   (A = P as MN-major, B = dO as MN-major)
+              umma_bf16_ss(tmem_dV, mndesc(sP + k * 2048), mndesc(sDO + k * 2048), IDESC_TT, (it | k) != 0);
 #pragma unroll
-          for (uint32_t k = 0; k < BQ / 16; ++k)     // dK += dSᵀ · Q
-            umma_bf16_ss(tmem_dK, make_smem_desc_sw128(sDS + k * 2048, 1024, TILE), make_smem_desc_sw128(sQ + k * 2048, 1024, TILE),
-                         IDESC_TT, (it | k) != 0);
+            for (uint32_t k = 0; k < BQ / 16; ++k)     // dK += dSᵀ · Q
+              umma_bf16_ss(tmem_dK, mndesc(sDS + k * 2048), mndesc(sQ + k * 2048), IDESC_TT, (it | k) != 0);
 #pragma unroll
-          for (uint32_t k = 0; k < BKV / 16; ++k)    // dQ = dS · K     (A = dS K-major, B = K as MN-major)
-            umma_bf16_ss(tmem_dQ + (itc & 1) * 64, make_smem_desc_sw128(sDS + (k >> 2) * TILE + (k & 3) * 32, 1024, 0),
-                         make_smem_desc_sw128(sK + k * 2048, 1024, TILE), IDESC_PV, k != 0);
-          umma_commit(&q_empty[s]);
-          umma_commit(&dq_full[itc & 1]);
+            for (uint32_t k = 0; k < BKV / 16; ++k)    // dQ = dS · K     (A = dS K-major, B = K as MN-major)
+              umma_bf16_ss(tmem_dQ + (itc & 1) * 64, kdesc(sDS + (k >> 2) * TILE + (k & 3) * 32), mndesc(sK + k * 2048),
+                           IDESC_PV, k != 0);
+            umma_commit(&q_empty[s]);
+            umma_commit(&dq_full[itc & 1]);
+            if (it + 1 == niter) {
+              umma_commit(&kv_empty[kvb]);
+              umma_commit(done);
+            }
+          }
+          __syncwarp();
         }
-        umma_commit(&kv_empty[kvb]);
-        umma_commit(done);
       }
     }
   } else {

@@ -142,7 +142,7 @@ QN_DEVICE void tile_coords(uint32_t tile, uint32_t tiles_m, uint32_t tiles_n, ui
   n_blk = in_group / gsize;
 }
 
-template <uint32_t BLOCK_N, bool A_MN, bool B_MN, int FUSE, bool CTA2 = false, bool ACCUM = false>
+template <uint32_t BLOCK_N, bool A_MN, bool B_MN, int FUSE, bool CTA2 = false, bool ACCUM = false, bool FP8 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_z,
@@ -236,9 +236,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             fence_proxy_async_all();      // generic-proxy (NVLink) writes -> async-proxy (TMA) reads
           }
         }
-        if (lane != 0) continue;
+        // the whole warp walks the K loop (uniform values stay in uniform registers); one elected lane issues the TMA
         for (uint32_t kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
+          if (elect_one()) {
           uint8_t* sa = smem + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           const int32_t k0 = kb * BLOCK_K;
@@ -263,9 +264,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               for (uint32_t j = 0; j < C::B_ROWS / 64; ++j)
                 tma_load_2d_2cta(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + 64 * j, k0);
             }
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
-            continue;
-          }
+          } else {
           mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
           if constexpr (FUSE == FUSE_AG) {
             if (a_remote) tma_load_2d(sa, &tmap_x, &full_bar[stage], k0, m0);
@@ -284,19 +283,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (uint32_t j = 0; j < BLOCK_N / 64; ++j)
               tma_load_2d(sb + j * (BLOCK_K * 128), &tmap_b, &full_bar[stage], n0 + 64 * j, k0);
           }
+          }
+          }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // -------------------------------------------------------------- MMA issuer
-    if (lane == 0 && cta_rank == 0) {                 // CTA pair: only the leader issues (for both SMs)
-      constexpr uint32_t idesc = make_idesc_bf16(TILE_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
+    // The WHOLE warp walks the loop (all values warp-uniform -> uniform registers); only the tcgen05 instructions are
+    // predicated on one elected lane.  Issuing from inside a divergent `lane == 0` region instead made the compiler
+    // wrap every MMA in an ELECT / R2UR / branch "waterfall" (~40 SASS instructions per MMA on a single thread): the
+    // issue loop, not the tensor pipe, paced the kernel (ncu: tensor pipe 57 % active).  Descriptors are a per-stage
+    // base plus a constant per-k increment of the 14-bit address field.
+    if (cta_rank == 0) {                              // CTA pair: only the leader issues (for both SMs); warp-uniform
+      constexpr uint32_t idesc = FP8 ? make_idesc_e4m3(TILE_M, BLOCK_N)
+                                     : make_idesc_bf16(TILE_M, BLOCK_N, A_MN ? 1u : 0u, B_MN ? 1u : 0u);
       // K-major: 8-row groups are 1024 B apart, one atom along K.  MN-major: 8-K-row groups 1024 B apart,
       // 64-wide MN atoms BLOCK_K*128 B apart.
       constexpr uint32_t A_LBO = A_MN ? BLOCK_K * 128 : 0, B_LBO = B_MN ? BLOCK_K * 128 : 0;
-      constexpr uint32_t A_KSTEP = A_MN ? UMMA_K * 128 : UMMA_K * 2;
-      constexpr uint32_t B_KSTEP = B_MN ? UMMA_K * 128 : UMMA_K * 2;
+      constexpr uint32_t A_KSTEP = (A_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;      // in descriptor address units (16 B)
+      constexpr uint32_t B_KSTEP = (B_MN ? UMMA_K * 128 : UMMA_K * 2) >> 4;
+      const uint64_t a_hi = make_smem_desc_sw128(0, 1024, A_LBO), b_hi = make_smem_desc_sw128(0, 1024, B_LBO);
+      const uint32_t smem_base = smem_u32(smem);
       uint32_t stage = 0, phase = 0, as = 0, aphase = 0;
       for (uint32_t work = worker; work < num_work; work += n_cta) {
         const uint32_t split = work % splits;
@@ -307,24 +317,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         for (uint32_t kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint32_t sb = sa + C::A_BYTES;
+          const uint32_t sa = smem_base + stage * C::STAGE_BYTES;
+          const uint64_t adesc = a_hi | static_cast<uint64_t>((sa & 0x3FFFF) >> 4);
+          const uint64_t bdesc = b_hi | static_cast<uint64_t>(((sa + C::A_BYTES) & 0x3FFFF) >> 4);
+          const uint32_t acc0 = kb != kb_begin ? 1u : 0u;
+          if (elect_one()) {
 #pragma unroll
-          for (uint32_t k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t adesc = make_smem_desc_sw128(sa + k * A_KSTEP, 1024, A_LBO);
-            const uint64_t bdesc = make_smem_desc_sw128(sb + k * B_KSTEP, 1024, B_LBO);
-            if constexpr (CTA2) {
-              if (p.fp8) umma_f8_ss_2cta(tmem_d, adesc, bdesc, make_idesc_e4m3(TILE_M, BLOCK_N), ((kb - kb_begin) | k) != 0 ? 1u : 0u);
-              else umma_bf16_ss_2cta(tmem_d, adesc, bdesc, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
-            } else if (p.fp8) umma_f8_ss(tmem_d, adesc, bdesc, make_idesc_e4m3(BLOCK_M, BLOCK_N), ((kb - kb_begin) | k) != 0 ? 1u : 0u);
-            else umma_bf16_ss(tmem_d, adesc, bdesc, idesc, ((kb - kb_begin) | k) != 0 ? 1u : 0u);
+            for (uint32_t k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint32_t acc = k ? 1u : acc0;
+              if constexpr (CTA2) {
+                if constexpr (FP8) umma_f8_ss_2cta(tmem_d, adesc + k * A_KSTEP, bdesc + k * B_KSTEP, idesc, acc);
+                else umma_bf16_ss_2cta(tmem_d, adesc + k * A_KSTEP, bdesc + k * B_KSTEP, idesc, acc);
+              } else {
+                if constexpr (FP8) umma_f8_ss(tmem_d, adesc + k * A_KSTEP, bdesc + k * B_KSTEP, idesc, acc);
+                else umma_bf16_ss(tmem_d, adesc + k * A_KSTEP, bdesc + k * B_KSTEP, idesc, acc);
+              }
+            }
+            // frees the smem slot when these MMAs retire (CTA pair: in both CTAs, each has its own producer)
+            if constexpr (CTA2) umma_commit_2cta(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+            // accumulator complete -> epilogue (CTA pair: the epilogues of both CTAs)
+            if (kb + 1 == kb_end) { if constexpr (CTA2) umma_commit_2cta(&tmem_full[as]); else umma_commit(&tmem_full[as]); }
           }
-          // frees the smem slot when these MMAs retire (CTA pair: in both CTAs, each has its own producer)
-          if constexpr (CTA2) umma_commit_2cta(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        // accumulator complete -> epilogue (CTA pair: the epilogues of both CTAs)
-        if constexpr (CTA2) umma_commit_2cta(&tmem_full[as]); else umma_commit(&tmem_full[as]);
         if (++as == 2) { as = 0; aphase ^= 1; }
       }
     }
@@ -664,7 +680,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           tmem_ld_wait();
           float* f = reinterpret_cast<float*>(acc);
           const uint32_t nh = nc + hcol * 32;
-          if (p.fp8) {                                     // dequantise: per-row scale of A x per-column scale of B
+          if constexpr (FP8) {                             // dequantise: per-row scale of A x per-column scale of B
             const float sa = (m0 + lane < p.M) ? p.scale_a[m0 + lane] : 0.f;
 #pragma unroll
             for (uint32_t v = 0; v < 8; ++v) {
@@ -812,12 +828,12 @@ static bool use_cta_pairs(int M, int N, int block_n, int splits, int max_ctas) {
 }
 
 // CTA-pair (cta_group::2) launch: clusters of 2 CTAs, one 256 x 256 tile per cluster and step
-template <bool A_MN, bool B_MN, int FUSE = FUSE_NONE, bool ACCUM = false>
+template <bool A_MN, bool B_MN, int FUSE = FUSE_NONE, bool ACCUM = false, bool FP8 = false>
 static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tz,
                        const GemmParams& p, cudaStream_t stream, const CUtensorMap* tx = nullptr,
                        const TpComm* comm = nullptr, int max_ctas = 0) {
   using C = Cfg<256, true, FUSE>;
-  auto kern = gemm_bf16_kernel<256, A_MN, B_MN, FUSE, true, ACCUM>;
+  auto kern = gemm_bf16_kernel<256, A_MN, B_MN, FUSE, true, ACCUM, FP8>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -848,12 +864,12 @@ static int launch_2cta(const CUtensorMap& ta, const CUtensorMap& tb, const CUten
   return static_cast<int>(e != cudaSuccess ? e : cudaGetLastError());
 }
 
-template <uint32_t BLOCK_N, bool A_MN, bool B_MN, int FUSE = FUSE_NONE, bool ACCUM = false>
+template <uint32_t BLOCK_N, bool A_MN, bool B_MN, int FUSE = FUSE_NONE, bool ACCUM = false, bool FP8 = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tz,
                   const GemmParams& p, int max_ctas, cudaStream_t stream, const CUtensorMap* tx = nullptr,
                   const TpComm* comm = nullptr) {
   using C = Cfg<BLOCK_N, false, FUSE>;
-  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, FUSE, false, ACCUM>;
+  auto kern = gemm_bf16_kernel<BLOCK_N, A_MN, B_MN, FUSE, false, ACCUM, FP8>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES);
@@ -1178,9 +1194,9 @@ extern "C" int qn_gemm_fp8(const void* a8, const void* b8, void* c, int M, int N
   } else {
     tz = tc;
   }
-  if (two_cta) return launch_2cta<false, false>(ta, tb, tc, tz, p, stream);
-  if (block_n == 256) return launch<256, false, false>(ta, tb, tc, tz, p, 0, stream);
-  return launch<128, false, false>(ta, tb, tc, tz, p, 0, stream);
+  if (two_cta) return launch_2cta<false, false, FUSE_NONE, false, true>(ta, tb, tc, tz, p, stream);
+  if (block_n == 256) return launch<256, false, false, FUSE_NONE, false, true>(ta, tb, tc, tz, p, 0, stream);
+  return launch<128, false, false, FUSE_NONE, false, true>(ta, tb, tc, tz, p, 0, stream);
 }
 
 // Publish `value` at a (peer-mapped) flag after everything earlier in `stream` — e.g. a cudaMemcpyAsync into the

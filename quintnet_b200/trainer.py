@@ -57,6 +57,8 @@ class _TrainerBase:
     def __init__(self, model: nn.Module, train_loader, val_loader, config: dict, pg_manager):
         self.model, self.train_loader, self.val_loader = model, train_loader, val_loader
         self.config, self.pg_manager = config, pg_manager
+        if os.environ.get("QUINTNET_OUTPUT_DIR"):       # job launchers (tools/cluster.py) redirect the checkpoints
+            config["output_dir"] = os.environ["QUINTNET_OUTPUT_DIR"]
         self.device = resolve_device(pg_manager, config)
         self.dtype = resolve_dtype(config)
         self.global_rank = dist.get_rank() if dist.is_initialized() else 0

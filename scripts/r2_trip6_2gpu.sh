@@ -6,6 +6,9 @@ LOG=gpurun_out/r2_trip6.log
 step() { name=$1; shift; echo "== $name" | tee -a $LOG; timeout --signal=KILL "$@" >> $LOG 2>&1; echo "   rc=$?" | tee -a $LOG; }
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1"
 step "build (incremental)" 300 python -c "import __graft_entry__ as g; g.build()"
+step "kernel + loopback suites (new MMA issue path)" 500 python -m pytest -q -m gpu --timeout 180 -p no:cacheprovider -x tests/test_kernels_gpu.py tests/test_tp_loopback_gpu.py tests/test_models_gpu.py
+step "kernel timings" 200 python scripts/ncu_r2_targets.py --time
+step "sustained GEMM ours vs cuBLAS" 200 python scripts/bench_gemm_sustained.py
 step "comm tests (2 GPUs)" 300 python -m pytest tests/test_comm_gpu.py -q -m gpu -x --timeout 120 -p no:cacheprovider
 QN_BENCH_TP_MODES="pump:1,pump:0" step "tp microbench" 200 $TR --master-port 29860 scripts/bench_tp_kernels.py
 step "parity tp2 / dp2 / pp2 vs 1 GPU" 600 python -m pytest tests/test_parity_gpu.py -q -m gpu -x --timeout 500 -p no:cacheprovider

@@ -273,3 +273,42 @@ def test_reference_readme_launch_lines_work():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
     assert "Train Loss:" in out.stdout
+
+
+def test_cluster_workflow_on_a_volume_directory(tmp_path):
+    """tools.cluster — the reference's Modal workflow (upload_model / prepare_dataset / run_gpt2_training /
+    list_checkpoints / download_checkpoints / test_weight_shapes / merge_and_test_model / run_test) against a plain
+    volume directory: stage -> train (torchrun, 2 CPU ranks, pp=2) -> list -> merge + evaluate -> download."""
+    import yaml
+    from quintnet_b200.core.distributed_loading import save_random_hf_checkpoint
+    from quintnet_b200.models.gpt2 import GPT2Config
+    vol = tmp_path / "vol"
+    mc = {"vocab_size": 96, "n_positions": 16, "n_embd": 32, "n_layer": 2, "n_head": 2}
+    src = tmp_path / "tiny.safetensors"
+    save_random_hf_checkpoint(str(src), GPT2Config.from_dict(mc), seed=0)
+    cfg = {"batch_size": 8, "grad_acc_steps": 2, "num_epochs": 1, "learning_rate": 1e-3, "max_grad_norm": 1.0,
+           "num_workers": 0, "max_seq_length": 16, "max_target_length": 8, "max_samples": 16, "max_val_samples": 8,
+           "compute_generation_metrics": False, "vocab_size": 96, "mesh_dim": [1, 1, 2], "mesh_name": ["dp", "tp", "pp"],
+           "strategy_name": "3d", "schedule": "1f1b", "device_type": "cpu", "dtype": "float32", "model_config": mc}
+    cpath = tmp_path / "tiny.yaml"
+    cpath.write_text(yaml.safe_dump(cfg))
+    base = [sys.executable, "-m", "quintnet_b200.tools.cluster", "--volume", str(vol)]
+    run = lambda *a, **kw: subprocess.run(base + list(a), capture_output=True, text=True, timeout=600, cwd=ROOT, **kw)
+    r = run("upload-model", "--src", str(src))
+    assert r.returncode == 0 and (vol / "models" / "tiny.safetensors").exists(), r.stderr[-800:]
+    r = run("prepare-dataset", "--name", "toy", "--synthetic", "--max-length", "16", "--max-samples", "32")
+    assert r.returncode == 0 and (vol / "datasets" / "toy_tok16.pt").exists(), r.stderr[-800:]
+    r = run("train", "--workload", "gpt2", "--nproc", "2", "--run", "exp1", "--config", str(cpath), "--port", "29717",
+            "--", "--cpu", "--synthetic")
+    assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-1500:])
+    summary = json.loads(r.stdout.strip().splitlines()[-1])
+    assert summary["exit_code"] == 0 and summary["epochs"] and "train_loss" in summary["epochs"][0]
+    r = run("list-checkpoints", "--run", "exp1")
+    assert "final_model_pp0_tp0.pt" in r.stdout and "final_model_pp1_tp0.pt" in r.stdout, r.stdout
+    r = run("merge-and-test", "--run", "exp1", "--prefix", "final_model", "--max-samples", "8")
+    assert r.returncode == 0 and (vol / "checkpoints" / "exp1" / "final_model_merged.pt").exists(), (r.stdout[-800:], r.stderr[-800:])
+    assert "perplexity" in r.stdout
+    r = run("download-checkpoints", "--run", "exp1", "--dst", str(tmp_path / "dl"))
+    assert r.returncode == 0 and (tmp_path / "dl" / "final_model_merged.pt").exists()
+    r = run("test-weight-shapes", "--model", "gpt2_base", "--tp", "2", "--pp", "2")
+    assert r.returncode == 0, r.stderr[-800:]
