@@ -73,29 +73,51 @@ def build(force: bool = False, verbose: bool = True, jobs: int = 8) -> Path:
         objs.append(o)
         if not force and o.exists() and o.stat().st_mtime > max(s.stat().st_mtime, newest_hdr):
             continue
-        cmd = [nvcc_path(), *NVCC_FLAGS, "-I", str(CSRC), "-c", str(s), "-o", str(o)]
+        # every artefact is written under a temporary name and renamed into place: a snapshot of the tree (gpurun
+        # copies it to the GPU box at an arbitrary moment) never sees a half-written object or library
+        tmp = o.with_suffix(".o.tmp")
+        cmd = [nvcc_path(), *NVCC_FLAGS, "-I", str(CSRC), "-c", str(s), "-o", str(tmp)]
         if verbose:
             print("[quintnet_b200.build]", " ".join(cmd), flush=True)
-        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
+        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT), tmp, o))
         if len(procs) >= jobs:
             _wait(procs)
     _wait(procs)
-    need_link = force or not out.exists() or any(o.stat().st_mtime > out.stat().st_mtime for o in objs)
+    need_link = force or not out.exists() or any(o.stat().st_mtime > out.stat().st_mtime for o in objs) \
+        or not _loadable(out)
     if need_link:
-        cmd = [nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(out),
+        tmp = out.with_suffix(".so.tmp")
+        cmd = [nvcc_path(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp),
                *[str(o) for o in objs], "-lcudart"]
         if verbose:
             print("[quintnet_b200.build]", " ".join(cmd), flush=True)
         subprocess.check_call(cmd)
+        os.replace(tmp, out)
     return out
+
+
+def _loadable(path: Path) -> bool:
+    """ELF sanity check without dlopen (a CPU-only box may lack libcudart): magic + section table inside the file."""
+    try:
+        with open(path, "rb") as f:
+            head = f.read(64)
+            if len(head) < 64 or head[:4] != b"\x7fELF":
+                return False
+            import struct
+            shoff, = struct.unpack_from("<Q", head, 0x28)
+            shentsize, shnum = struct.unpack_from("<HH", head, 0x3A)
+            return path.stat().st_size >= shoff + shentsize * shnum
+    except OSError:
+        return False
 
 
 def _wait(procs):
     while procs:
-        s, p = procs.pop(0)
+        s, p, tmp, o = procs.pop(0)
         outp = p.communicate()[0].decode()
         if p.returncode != 0:
             raise RuntimeError(f"nvcc failed for {s}:\n{outp}")
+        os.replace(tmp, o)
         if outp.strip():
             print(outp)
 
