@@ -32,12 +32,32 @@ def linear(x, w, b=None, act: Optional[str] = None, fp8: bool = False):
     on the reference path."""
     if _use_native("gemm", x) and x.dtype == torch.bfloat16:
         from . import cuda_ops
+        if fp8 and _FP8_RECIPE == "mxfp8" and cuda_ops.mxfp8_ok(x.shape[-1], w.shape[0]) and \
+                (b is None or b.dtype == torch.bfloat16):
+            return cuda_ops.linear_mxfp8(x, w, b, act)            # block-scaled: tcgen05.mma.kind::mxf8f6f4.block_scale
         if fp8 and cuda_ops.fp8_ok(x.shape[-1], w.shape[0]):
-            return cuda_ops.linear_fp8(x, w, b, act)
+            return cuda_ops.linear_fp8(x, w, b, act)              # row-wise scales: kind::f8f6f4 + epilogue dequant
         return cuda_ops.linear(x, w, b, act)
     if fp8:
-        return reference.linear_fp8(x, w, b, act)
+        return reference.linear_fp8(x, w, b, act, recipe=_FP8_RECIPE)
     return reference.linear(x, w, b, act)
+
+
+_FP8_RECIPE = os.environ.get("QUINTNET_FP8_RECIPE", "mxfp8")
+
+
+def set_fp8_recipe(recipe: str) -> None:
+    """``"mxfp8"`` (default): OCP MX block scaling — e4m3 elements, one UE8M0 scale per 32 elements along K, applied
+    inside the tensor core (``tcgen05.mma.kind::mxf8f6f4.block_scale``); ``"rowwise"``: one fp32 scale per row,
+    multiplied back in the GEMM epilogue (round-1 kernel)."""
+    global _FP8_RECIPE
+    if recipe not in ("mxfp8", "rowwise"):
+        raise ValueError(f"unknown fp8 recipe {recipe!r}")
+    _FP8_RECIPE = recipe
+
+
+def fp8_recipe() -> str:
+    return _FP8_RECIPE
 
 
 def mlp(x, w1, b1, w2, b2):

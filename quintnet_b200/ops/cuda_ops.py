@@ -225,6 +225,71 @@ def linear_fp8(x, w, b=None, act: Optional[str] = None):
     return _LinearFP8.apply(x, w, b, act)
 
 
+# ------------------------------------------------------------------ block-scaled FP8 (MXFP8, tcgen05 .block_scale)
+def mxfp8_ok(K: int, N: int) -> bool:
+    return K % 128 == 0 and N % 8 == 0
+
+
+def quantize_mx(x2: torch.Tensor):
+    """bf16 [R, K] -> (e4m3 bytes [R, K], UE8M0 scale atoms [ceil(R/128) * K/128 * 512]) — ``csrc/gemm_mxfp8.cu``."""
+    R, K = x2.shape
+    assert x2.dtype == torch.bfloat16 and x2.stride(1) == 1 and K % 128 == 0
+    q = torch.empty((R, K), dtype=torch.uint8, device=x2.device)
+    nblk = (R + 127) // 128
+    sf = (torch.zeros if R % 128 else torch.empty)(nblk * (K // 128) * 512, dtype=torch.uint8, device=x2.device)
+    rc = _lib().qn_quantize_mxfp8(x2.data_ptr(), q.data_ptr(), sf.data_ptr(), R, K, x2.stride(0), K, native.stream())
+    native.check(rc, f"qn_quantize_mxfp8(R={R},K={K})")
+    native.count()
+    return q, sf
+
+
+def gemm_mxfp8(a8, sfa, b8, sfb, M: int, N: int, K: int, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C[M, N] (bf16) = (A8 ⊙ SFA)·(B8 ⊙ SFB)ᵀ (+ bias) on ``tcgen05.mma.kind::mxf8f6f4.block_scale``: the UE8M0 scales
+    go shared memory -> tensor memory (tcgen05.cp) and are applied by the tensor core per 32-element K block."""
+    out = torch.empty((M, N), dtype=torch.bfloat16, device=a8.device)
+    rc = _lib().qn_gemm_mxfp8(a8.data_ptr(), sfa.data_ptr(), b8.data_ptr(), sfb.data_ptr(), out.data_ptr(), M, N, K,
+                              a8.stride(0), b8.stride(0), N, native.ptr(bias), native.stream())
+    native.check(rc, f"qn_gemm_mxfp8(M={M},N={N},K={K})")
+    native.count()
+    return out
+
+
+class _LinearMXFP8(torch.autograd.Function):
+    """Forward on the block-scaled FP8 tensor cores (MXFP8 activations AND weights, fp32 accumulation); backward in bf16
+    from the saved bf16 operands (dgrad / wgrad keep the wide format — the usual mixed recipe).  GELU, when requested,
+    runs as the stand-alone fused kernel on the GEMM output (its derivative is taken from the saved pre-activation)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        K, N = x.shape[-1], w.shape[0]
+        x2 = x.reshape(-1, K)
+        if not x2.is_contiguous():
+            x2 = x2.contiguous()
+        M = x2.shape[0]
+        wq = w if w.dtype == torch.bfloat16 else w.to(torch.bfloat16)
+        a8, sfa = quantize_mx(x2)
+        b8, sfb = quantize_mx(wq if wq.is_contiguous() else wq.contiguous())
+        y = gemm_mxfp8(a8, sfa, b8, sfb, M, N, K, b)
+        z = None
+        if act == "gelu":
+            pre = y
+            y = torch.nn.functional.gelu(pre.float()).to(torch.bfloat16)
+            u = pre.float()
+            z = (0.5 * (1.0 + torch.erf(u * 0.7071067811865476)) + u * torch.exp(-0.5 * u * u) * 0.3989422804014327).to(torch.bfloat16)
+        elif act is not None:
+            raise ValueError(f"native mxfp8 linear: unsupported activation {act}")
+        ctx.save_for_backward(x2, wq, z)
+        ctx.act, ctx.has_bias, ctx.xshape, ctx.wdtype = act, b is not None, x.shape, w.dtype
+        ctx.w_param = w if w.dtype == torch.bfloat16 else None
+        return y.view(*x.shape[:-1], N)
+
+    backward = _Linear.backward
+
+
+def linear_mxfp8(x, w, b=None, act: Optional[str] = None):
+    return _LinearMXFP8.apply(x, w, b, act)
+
+
 class _FusedMLP(torch.autograd.Function):
     """y = (gelu(x·W1ᵀ + b1))·W2ᵀ + b2 with the GELU fused into the first GEMM's epilogue (forward) and
     gelu' fused into the dgrad GEMM's epilogue (backward): no stand-alone activation kernels."""

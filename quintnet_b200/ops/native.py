@@ -163,6 +163,8 @@ _SIGNATURES = {
     "qn_ag_done_base": [],
     "qn_gemm_fp8": [_P, _P, _P, _I, _I, _I, _L, _L, _L, _P, _P, _I, _P, _P, _L, _I, _P],
     "qn_quantize_rowwise_e4m3": [_P, _P, _P, _I, _I, _L, _L, _P],
+    "qn_quantize_mxfp8": [_P, _P, _P, _I, _I, _L, _L, _P],
+    "qn_gemm_mxfp8": [_P, _P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _P, _P],
     "qn_gemm_bf16": [_P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _P, _P, _L, _I, _I, _P],
     "qn_gemm_bf16_splitk": [_P, _P, _P, _P, _I, _I, _I, _L, _L, _L, _I, _I, _I, _I, _P],
     "qn_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],

@@ -70,7 +70,36 @@ def fake_quant_rowwise_e4m3(t: torch.Tensor) -> torch.Tensor:
     return t + (q.to(t.dtype) - t).detach()
 
 
-def linear_fp8(x, w, b=None, act: Optional[str] = None):
+def mx_scales_e8m0(t: torch.Tensor, block: int = 32):
+    """OCP MX shared exponents of a [..., K] tensor: one power-of-two scale per ``block`` elements along K,
+    e = floor(log2(amax)) - 8 (8 = emax of e4m3), 2^-127 for an all-zero block.  Returns (biased uint8 [.., K/block],
+    fp32 scale values)."""
+    t2 = t.detach().float()
+    K = t2.shape[-1]
+    blk = t2.reshape(*t2.shape[:-1], K // block, block)
+    amax = blk.abs().amax(dim=-1)
+    e = torch.floor(torch.log2(amax.clamp(min=1e-38))) - 8.0
+    # exact floor(log2) through frexp (log2 of a float can round up just below a power of two)
+    m, ex = torch.frexp(amax)
+    e = torch.where(amax > 0, ex.float() - 1.0 - 8.0, torch.full_like(amax, -127.0)).clamp(-127.0, 127.0)
+    return (e + 127.0).to(torch.uint8), torch.exp2(e)
+
+
+def fake_quant_mxfp8(t: torch.Tensor, block: int = 32) -> torch.Tensor:
+    """MXFP8 quantise -> dequantise along the last dim (e4m3 elements x UE8M0 block scales): the numerics of the
+    block-scaled tensor-core GEMM (``csrc/gemm_mxfp8.cu``), straight-through gradient."""
+    t2 = t.detach().float()
+    K = t2.shape[-1]
+    _, scale = mx_scales_e8m0(t2, block)
+    blk = t2.reshape(*t2.shape[:-1], K // block, block)
+    q = (blk / scale.unsqueeze(-1)).clamp(-448.0, 448.0).to(torch.float8_e4m3fn).float() * scale.unsqueeze(-1)
+    q = q.reshape(t2.shape)
+    return t + (q.to(t.dtype) - t).detach()
+
+
+def linear_fp8(x, w, b=None, act: Optional[str] = None, recipe: str = "rowwise"):
+    if recipe == "mxfp8" and x.shape[-1] % 32 == 0:
+        return linear(fake_quant_mxfp8(x), fake_quant_mxfp8(w), b, act)
     return linear(fake_quant_rowwise_e4m3(x), fake_quant_rowwise_e4m3(w), b, act)
 
 

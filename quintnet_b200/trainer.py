@@ -73,6 +73,8 @@ class _TrainerBase:
         self.logger = StepLogger(config.get("log_jsonl"), self.global_rank)
         from . import ops
         from .coordinators.main_coordinator import resolve_main_grad_dtype
+        if config.get("fp8_recipe"):
+            ops.set_fp8_recipe(str(config["fp8_recipe"]))
         if config.get("fuse_wgrad_accumulation") is not None:
             ops.set_fused_wgrad_accumulation(bool(config["fuse_wgrad_accumulation"]))
         elif resolve_main_grad_dtype(config) is not None and os.environ.get("QUINTNET_FUSE_WGRAD_ACCUM") is None:

@@ -477,3 +477,48 @@ def test_layernorm_bwd_offers_bias_gradient():
     assert _rel(got, ref) < 1e-2, _rel(got, ref)
     fresh = cuda_ops.colsum(gx.reshape(rows, cols))    # cache is empty now: the stand-alone kernel
     assert _rel(fresh, ref) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (256, 384, 512), (1000, 264, 1024), (16384 // 4, 4096, 1024)])
+def test_mxfp8_block_scaled_gemm(M, N, K):
+    """Block-scaled FP8 GEMM (tcgen05.mma.kind::mxf8f6f4.block_scale, UE8M0 scales through tcgen05.cp) vs an fp32
+    emulation of the SAME quantisation: the quantiser must be bit-exact, the GEMM exact up to fp32 accumulation order."""
+    from quintnet_b200.ops import cuda_ops, reference
+    torch.manual_seed(51)
+    # magnitudes spread over many binades so that different 32-element blocks really get different exponents
+    a = (torch.randn(M, K, device="cuda") * torch.exp2(torch.randint(-6, 7, (M, K // 32), device="cuda").float()).repeat_interleave(32, 1)).to(torch.bfloat16)
+    b = (torch.randn(N, K, device="cuda") * torch.exp2(torch.randint(-4, 5, (N, K // 32), device="cuda").float()).repeat_interleave(32, 1)).to(torch.bfloat16)
+    bias = torch.randn(N, device="cuda").to(torch.bfloat16) if N % 8 == 0 else None
+    a8, sfa = cuda_ops.quantize_mx(a)
+    b8, sfb = cuda_ops.quantize_mx(b)
+    # quantiser: element bytes and block exponents equal the reference emulation
+    ea, sa = reference.mx_scales_e8m0(a)
+    qa_ref = (a.float().view(M, K // 32, 32) / sa.unsqueeze(-1)).clamp(-448, 448).to(torch.float8_e4m3fn).view(M, K)
+    assert torch.equal(a8.view(torch.float8_e4m3fn).float(), qa_ref.float())
+    rows = torch.arange(M, device="cuda")
+    for j in range(0, K // 32, max(K // 32 // 3, 1)):
+        kb, jj = j // 4, j % 4
+        off = ((rows // 128) * (K // 128) + kb) * 512 + (rows % 32) * 16 + ((rows % 128) // 32) * 4 + jj
+        assert torch.equal(sfa[off], ea[:, j])
+    c = cuda_ops.gemm_mxfp8(a8, sfa, b8, sfb, M, N, K, bias)
+    ref = reference.fake_quant_mxfp8(a.float()) @ reference.fake_quant_mxfp8(b.float()).t()
+    if bias is not None:
+        ref = ref + bias.float()
+    assert _rel(c, ref) < 6e-3, _rel(c, ref)               # bf16 output rounding only
+
+
+def test_mxfp8_linear_autograd_and_recipe():
+    from quintnet_b200 import ops
+    from quintnet_b200.ops import reference
+    torch.manual_seed(52)
+    x = torch.randn(4, 64, 256, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    w = (torch.randn(512, 256, device="cuda") * 0.05).to(torch.bfloat16).requires_grad_(True)
+    b = torch.randn(512, device="cuda").to(torch.bfloat16).requires_grad_(True)
+    assert ops.fp8_recipe() == "mxfp8"
+    y = ops.linear(x, w, b, "gelu", fp8=True)
+    y.float().pow(2).mean().backward()
+    xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, b))
+    yr = reference.linear_fp8(xr, wr, br, "gelu", recipe="mxfp8")
+    yr.pow(2).mean().backward()
+    assert _rel(y, yr) < 2e-2
+    assert _rel(x.grad, xr.grad) < 5e-2 and _rel(w.grad, wr.grad) < 5e-2 and _rel(b.grad, br.grad) < 5e-2
