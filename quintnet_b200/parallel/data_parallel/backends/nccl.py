@@ -39,6 +39,13 @@ class NVLinkBackend(TorchDistributedBackend):
         buf = symm.lookup(tensor)
         if buf is None or self.get_world_size(group) == 1:
             return super().all_reduce_async(tensor, scale, group)
+        if self._tp_spin_kernels_active():
+            # The in-kernel all-reduce spins on peer flags while it holds its SMs.  The fused TP GEMM+collective
+            # kernels spin on peer flags too: co-resident on a dp x tp grid, each kind can keep the other's peer
+            # kernel from getting the SMs it needs and close a cross-GPU wait cycle.  With fused TP active the
+            # reduction therefore runs in stream order on the compute stream (no side-stream overlap).
+            symm.all_reduce_(buf, tensor, scale)
+            return _EventHandle(None)
         ready = torch.cuda.Event()
         ready.record()
         s = self.comm_stream
@@ -48,3 +55,9 @@ class NVLinkBackend(TorchDistributedBackend):
             done = torch.cuda.Event()
             done.record(s)
         return _EventHandle(done)
+
+    @staticmethod
+    def _tp_spin_kernels_active() -> bool:
+        import sys
+        m = sys.modules.get("quintnet_b200.ops.tp_fused")
+        return bool(m is not None and getattr(m, "_workspaces", None))
