@@ -20,5 +20,9 @@ for M, N, K in ((16384, 4096, 1024), (16384, 1024, 4096), (16384, 3072, 1024), (
     t8 = timeit(lambda: cuda_ops.gemm_fp8(qa, sa, qw, sw, M, N, K, out=out))
     t16 = timeit(lambda: cuda_ops.gemm(a, w, M, N, K, out=out))
     tq = timeit(lambda: cuda_ops.quantize_rowwise(a))
+    ma, sfa = cuda_ops.quantize_mx(a); mw, sfw = cuda_ops.quantize_mx(w)
+    tmx = timeit(lambda: cuda_ops.gemm_mxfp8(ma, sfa, mw, sfw, M, N, K))
+    tqmx = timeit(lambda: cuda_ops.quantize_mx(a))
     fl = 2.0 * M * N * K
-    print(f"{M}x{N}x{K}: fp8 {t8:6.1f} us ({fl / t8 / 1e6:6.0f} TFLOP/s)  bf16 {t16:6.1f} us ({fl / t16 / 1e6:6.0f} TFLOP/s)  quantize A {tq:5.1f} us")
+    print(f"{M}x{N}x{K}: mxfp8 block-scaled {tmx:6.1f} us ({fl / tmx / 1e6:6.0f} TFLOP/s)  fp8 row-wise {t8:6.1f} us ({fl / t8 / 1e6:6.0f} TFLOP/s)  "
+          f"bf16 {t16:6.1f} us ({fl / t16 / 1e6:6.0f} TFLOP/s)  quantize A: mx {tqmx:5.1f} us / row-wise {tq:5.1f} us", flush=True)

@@ -343,7 +343,7 @@ def test_fp8_linear_autograd(act):
     dy = torch.randn_like(y)
     y.backward(dy)
     xr, wr, br = (t.detach().float().requires_grad_(True) for t in (x, w, b))
-    yr = reference.linear_fp8(xr, wr, br, act)
+    yr = reference.linear_fp8(xr, wr, br, act, recipe=ops.fp8_recipe() if x.shape[-1] % 128 == 0 else "rowwise")
     yr.backward(dy.float())
     assert _rel(y, yr) < 2e-2, _rel(y, yr)
     assert _rel(x.grad, xr.grad) < 5e-2 and _rel(w.grad, wr.grad) < 5e-2 and _rel(b.grad, br.grad) < 2e-2
