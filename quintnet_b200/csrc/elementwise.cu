@@ -194,6 +194,16 @@ extern "C" int qn_colsum(const void* x, float* acc, void* out, int rows, int col
   f32_to_bf16_kernel<<<(cols + 255) / 256, 256, 0, s>>>(acc, (__nv_bfloat16*)out, cols);
   return (int)cudaGetLastError();
 }
+// acc32[cols] += column sums of x (fp32 accumulation straight into a main-grad buffer: no memset, no conversion)
+extern "C" int qn_colsum_accum_f32(const void* x, float* acc32, int rows, int cols, long long ld, cudaStream_t s) {
+  if ((cols % 8) || (ld % 8)) return 930;
+  int gy = (rows + 31) / 32;
+  const int gx = (cols + 63) / 64;
+  const int cap = (148 * 8 + gx - 1) / gx;
+  if (gy > cap) gy = cap;
+  colsum_kernel<<<dim3(gx, gy), 256, 0, s>>>((const __nv_bfloat16*)x, acc32, rows, cols, ld);
+  return (int)cudaGetLastError();
+}
 extern "C" int qn_rope(const void* x, void* y, const float* cosp, const float* sinp, int B, int H, int T, int d,
                        long long sb, long long sh, long long st, int backward, cudaStream_t s) {
   if (d % 2) return 930;

@@ -229,7 +229,11 @@ ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                     const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean_in,
                     const float* __restrict__ rstd_in, const __nv_bfloat16* __restrict__ dadd,
                     __nv_bfloat16* __restrict__ dx, __nv_bfloat16* __restrict__ dx_drop, float* __restrict__ acc,
-                    int rows, int cols, const LnDropout dr, const int want_colsum) {
+                    int rows, int cols, const LnDropout dr, const int want_colsum, float* __restrict__ acc_g,
+                    float* __restrict__ acc_b) {
+  // dgamma / dbeta accumulators: acc / acc + cols by default, or caller-provided fp32 buffers (the parameters' main
+  // grads: the kernel then accumulates the LayerNorm weight gradients in place, nothing to finalize or add later)
+  if (acc_g == nullptr) { acc_g = acc; acc_b = acc + cols; }
   extern __shared__ __align__(128) uint8_t lnf_smem[];
   __shared__ uint64_t full[LNF_STAGES];
   __shared__ float s_stat[LNF_STAGES][LNF_R][4];          // mean, rstd, c1, c2 per row
@@ -387,9 +391,9 @@ ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(acc + vi * 8 + q * 4), "f"(ag[j][q * 4 + 0]),
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(acc_g + vi * 8 + q * 4), "f"(ag[j][q * 4 + 0]),
                        "f"(ag[j][q * 4 + 1]), "f"(ag[j][q * 4 + 2]), "f"(ag[j][q * 4 + 3]) : "memory");
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(acc + cols + vi * 8 + q * 4), "f"(ab[j][q * 4 + 0]),
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(acc_b + vi * 8 + q * 4), "f"(ab[j][q * 4 + 0]),
                        "f"(ab[j][q * 4 + 1]), "f"(ab[j][q * 4 + 2]), "f"(ab[j][q * 4 + 3]) : "memory");
         }
       }
@@ -400,7 +404,8 @@ ln_bwd_fused_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
 template <int CV, bool HAS_ADD>
 static int launch_ln_bwd_fused(const void* dy, const void* x, const void* g, const float* mean, const float* rstd,
                                const void* dadd, void* dx, void* dx_drop, float* acc, int rows, int cols,
-                               const LnDropout dr, cudaStream_t s, int want_colsum = 0) {
+                               const LnDropout dr, cudaStream_t s, int want_colsum = 0, float* acc_g = nullptr,
+                               float* acc_b = nullptr) {
   const int nt = HAS_ADD ? 3 : 2;
   const int smem = LNF_STAGES * nt * LNF_R * cols * 2 + cols * 2;
   auto k = ln_bwd_fused_kernel<CV, HAS_ADD>;
@@ -411,7 +416,7 @@ static int launch_ln_bwd_fused(const void* dy, const void* x, const void* g, con
   const int grid = min(nblk, 148 * per_sm);
   using B = __nv_bfloat16;
   k<<<grid, LNF_THREADS, smem, s>>>((const B*)dy, (const B*)x, (const B*)g, mean, rstd, (const B*)dadd, (B*)dx,
-                                   (B*)dx_drop, acc, rows, cols, dr, want_colsum);
+                                   (B*)dx_drop, acc, rows, cols, dr, want_colsum, acc_g, acc_b);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -420,7 +425,7 @@ __global__ void ln_finalize_kernel(const float* __restrict__ acc, T* __restrict_
                                    T* __restrict__ colsum = nullptr) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < cols) {
-    dgamma[c] = static_cast<T>(acc[c]); dbeta[c] = static_cast<T>(acc[cols + c]);
+    if (dgamma != nullptr) { dgamma[c] = static_cast<T>(acc[c]); dbeta[c] = static_cast<T>(acc[cols + c]); }
     if (colsum != nullptr) colsum[c] = static_cast<T>(acc[2 * cols + c]);
   }
 }
@@ -452,24 +457,27 @@ static int ln_fwd(const void* x, const void* res, const void* g, const void* b, 
 template <typename T>
 static int ln_bwd(const void* dy, const void* x, const void* g, const float* mean, const float* rstd,
                   const void* dadd, void* dx, void* dgamma, void* dbeta, float* workspace, int nparts, int rows,
-                  int cols, void* dx_drop, const LnDropout dr, cudaStream_t s, void* colsum = nullptr) {
+                  int cols, void* dx_drop, const LnDropout dr, cudaStream_t s, void* colsum = nullptr,
+                  float* main_g = nullptr, float* main_b = nullptr) {
   constexpr int VN = Vec<T>::N;
   if (cols % VN || cols > 32 * LN_MAXV * VN) return 920;
   (void)nparts;
   if (sizeof(T) == 2 && cols <= 2048 && rows >= 64 && getenv("QN_LN_BWD_SPLIT") == nullptr) {
     // fused single-pass kernel (bf16): fp32 accumulators [2 * cols] in the workspace, then bf16 conversion
     const int wc = colsum != nullptr ? 1 : 0;
-    cudaMemsetAsync(workspace, 0, (2ull + wc) * cols * sizeof(float), s);
+    const bool in_place = main_g != nullptr && main_b != nullptr;      // dgamma / dbeta go straight into fp32 main grads
+    if (!in_place || wc) cudaMemsetAsync(workspace, 0, (2ull + wc) * cols * sizeof(float), s);
     int rc;
-    if (cols <= 1024) rc = dadd ? launch_ln_bwd_fused<1, true>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s, wc)
-                                : launch_ln_bwd_fused<1, false>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s, wc);
-    else rc = dadd ? launch_ln_bwd_fused<2, true>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s, wc)
-                   : launch_ln_bwd_fused<2, false>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s, wc);
+    if (cols <= 1024) rc = dadd ? launch_ln_bwd_fused<1, true>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s, wc, main_g, main_b)
+                                : launch_ln_bwd_fused<1, false>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s, wc, main_g, main_b);
+    else rc = dadd ? launch_ln_bwd_fused<2, true>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s, wc, main_g, main_b)
+                   : launch_ln_bwd_fused<2, false>(dy, x, g, mean, rstd, dadd, dx, dx_drop, workspace, rows, cols, dr, s, wc, main_g, main_b);
     if (rc) return rc;
-    ln_finalize_kernel<T><<<(cols + 255) / 256, 256, 0, s>>>(workspace, (T*)dgamma, (T*)dbeta, cols, (T*)colsum);
+    if (in_place && !wc) return 0;
+    ln_finalize_kernel<T><<<(cols + 255) / 256, 256, 0, s>>>(workspace, in_place ? nullptr : (T*)dgamma, (T*)dbeta, cols, (T*)colsum);
     return static_cast<int>(cudaGetLastError());
   }
-  if (colsum != nullptr) return 921;          // only the fused single-pass kernel produces the column sums
+  if (colsum != nullptr || main_g != nullptr) return 921;   // only the fused single-pass kernel has these outputs
   int grid = (rows + LN_WARPS - 1) / LN_WARPS;
   if (grid > 148 * 16) grid = 148 * 16;
   const int mv = (cols / VN + 31) / 32;
@@ -538,9 +546,11 @@ extern "C" int qn_dropout_add_layernorm_bwd(const void* dy, const void* h, const
                                             const float* rstd, const void* dsum, void* dres, void* dx, void* dgamma,
                                             void* dbeta, float* workspace, int nparts, int rows, int cols, float p,
                                             unsigned long long seed, unsigned long long offset, void* colsum,
-                                            cudaStream_t s) {
+                                            float* main_g, float* main_b, cudaStream_t s) {
+  //   main_g / main_b (optional, fp32 [cols]): the LayerNorm weight / bias MAIN-GRAD buffers — dgamma / dbeta are
+  //   accumulated into them in place (dgamma / dbeta outputs are then not written)
   qn::LnDropout dr{0u, 1.0f, seed, offset};
   if (p > 0.f) { dr.threshold = (uint32_t)(p * 65536.0f); dr.scale = 1.0f / (1.0f - dr.threshold / 65536.0f); }
   return qn::ln_bwd<__nv_bfloat16>(dy, h, gamma, mean, rstd, dsum, dres, dgamma, dbeta, workspace, nparts, rows, cols,
-                                   dx, dr, s, colsum);
+                                   dx, dr, s, colsum, main_g, main_b);
 }

@@ -133,6 +133,7 @@ class _Linear(torch.autograd.Function):
         ctx.act, ctx.has_bias, ctx.xshape = act, b is not None, x.shape
         ctx.wdtype = w.dtype
         ctx.w_param = w if w.dtype == torch.bfloat16 else None      # target of fused gradient accumulation
+        ctx.b_param = b
         return y.view(*x.shape[:-1], N)
 
     @staticmethod
@@ -155,7 +156,7 @@ class _Linear(torch.autograd.Function):
             if dw is not None and ctx.wdtype != torch.bfloat16:
                 dw = dw.to(ctx.wdtype)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dy2)
+            db = bias_grad(getattr(ctx, "b_param", None), dy2)
         return dx, dw, db, None
 
 
@@ -216,6 +217,7 @@ class _LinearFP8(torch.autograd.Function):
         ctx.save_for_backward(x2, wq, z)
         ctx.act, ctx.has_bias, ctx.xshape, ctx.wdtype = act, b is not None, x.shape, w.dtype
         ctx.w_param = w if w.dtype == torch.bfloat16 else None
+        ctx.b_param = b
         return y.view(*x.shape[:-1], N)
 
     backward = _Linear.backward
@@ -281,6 +283,7 @@ class _LinearMXFP8(torch.autograd.Function):
         ctx.save_for_backward(x2, wq, z)
         ctx.act, ctx.has_bias, ctx.xshape, ctx.wdtype = act, b is not None, x.shape, w.dtype
         ctx.w_param = w if w.dtype == torch.bfloat16 else None
+        ctx.b_param = b
         return y.view(*x.shape[:-1], N)
 
     backward = _Linear.backward
@@ -306,6 +309,7 @@ class _FusedMLP(torch.autograd.Function):
         y = gemm(a, w2, M, w2.shape[0], I, epilogue=EPI_BIAS if b2 is not None else EPI_NONE, bias=b2)
         ctx.save_for_backward(x2, w1, w2, z, a)
         ctx.xshape, ctx.has_b1, ctx.has_b2 = x.shape, b1 is not None, b2 is not None
+        ctx.b1_param, ctx.b2_param = b1, b2
         return y.view(*x.shape[:-1], w2.shape[0])
 
     @staticmethod
@@ -318,10 +322,10 @@ class _FusedMLP(torch.autograd.Function):
             dy2 = dy2.contiguous()
         dz = gemm(dy2, w2, M, I, O, b_mn=True, epilogue=EPI_MUL_AUX, z=z)      # (dY·W2) ⊙ gelu'(z), z := gelu'
         dw2 = wgrad(w2, dy2, a, O, I, M) if ctx.needs_input_grad[3] else None
-        db2 = colsum(dy2) if (ctx.has_b2 and ctx.needs_input_grad[4]) else None
+        db2 = bias_grad(ctx.b2_param, dy2) if (ctx.has_b2 and ctx.needs_input_grad[4]) else None
         dx = gemm(dz, w1, M, E, I, b_mn=True).view(ctx.xshape) if ctx.needs_input_grad[0] else None
         dw1 = wgrad(w1, dz, x2, I, E, M) if ctx.needs_input_grad[1] else None
-        db1 = colsum(dz) if (ctx.has_b1 and ctx.needs_input_grad[2]) else None
+        db1 = bias_grad(ctx.b1_param, dz) if (ctx.has_b1 and ctx.needs_input_grad[2]) else None
         return dx, dw1, db1, dw2, db2
 
 
@@ -364,6 +368,22 @@ def colsum(x2: torch.Tensor) -> torch.Tensor:
                                   native.stream()), "qn_colsum")
     native.count(3)
     return out
+
+
+def bias_grad(b_param, dy2: torch.Tensor):
+    """Bias gradient = column sums of dY.  With fp32 main grads and fused accumulation the sums are accumulated straight
+    into ``b_param.main_grad`` by the kernel (one launch, nothing for autograd to add) and ``None`` is returned."""
+    from . import fused_wgrad_accumulation, wgrad_done
+    mg = getattr(b_param, "main_grad", None) if b_param is not None else None
+    if (fused_wgrad_accumulation() and mg is not None and mg.dtype == torch.float32 and mg.dim() == 1
+            and mg.numel() == dy2.shape[-1] and mg.is_contiguous() and dy2.data_ptr() not in _COLSUM_CACHE):
+        rows, cols = dy2.shape
+        native.check(_lib().qn_colsum_accum_f32(dy2.data_ptr(), mg.data_ptr(), rows, cols, dy2.stride(0), native.stream()),
+                     "qn_colsum_accum_f32")
+        native.count()
+        wgrad_done(b_param)
+        return None
+    return colsum(dy2)
 
 
 def linear(x, w, b=None, act: Optional[str] = None):
@@ -560,6 +580,7 @@ class _DropoutAddLayerNorm(torch.autograd.Function):
         native.count()
         ctx.save_for_backward(h, wq, mean, rstd)
         ctx.args = (float(p), seed, off, x.shape, w.dtype)
+        ctx.ln_params = (w, b)                      # targets of in-place fp32 main-grad accumulation (if they have one)
         return y.view(x.shape), h.view(x.shape)
 
     @staticmethod
@@ -583,18 +604,30 @@ class _DropoutAddLayerNorm(torch.autograd.Function):
         ws = torch.empty(max(2 * nparts, 3) * cols, dtype=torch.float32, device=h.device)
         # the fused single-pass kernel also sums the columns of the branch gradient (= bias gradient of the Linear
         # that produced the branch output): offered to that layer's backward through the colsum cache
-        fused = cols <= 2048 and rows >= 64 and os.environ.get("QN_LN_BWD_SPLIT") is None and ctx.needs_input_grad[0]
+        single_pass = cols <= 2048 and rows >= 64 and os.environ.get("QN_LN_BWD_SPLIT") is None
+        fused = single_pass and ctx.needs_input_grad[0]
         cs = torch.empty(cols, dtype=h.dtype, device=h.device) if fused else None
+        # fp32 main grads: dgamma / dbeta are accumulated in place by the kernel (no finalize pass, no adds by autograd)
+        from . import fused_wgrad_accumulation, wgrad_done
+        wp, bp = getattr(ctx, "ln_params", (None, None))
+        mg_w, mg_b = getattr(wp, "main_grad", None), getattr(bp, "main_grad", None)
+        in_place = (single_pass and fused_wgrad_accumulation() and mg_w is not None and mg_b is not None
+                    and mg_w.dtype == torch.float32 and mg_b.dtype == torch.float32 and mg_w.numel() == cols
+                    and mg_b.numel() == cols and mg_w.is_contiguous() and mg_b.is_contiguous())
         rc = _lib().qn_dropout_add_layernorm_bwd(dy2.data_ptr(), h.data_ptr(), w.data_ptr(), mean.data_ptr(),
                                                  rstd.data_ptr(), native.ptr(dh2), dres.data_ptr(), native.ptr(dx),
                                                  dg.data_ptr(), db.data_ptr(), ws.data_ptr(), nparts, rows, cols,
-                                                 p, seed, off, native.ptr(cs), native.stream())
+                                                 p, seed, off, native.ptr(cs), mg_w.data_ptr() if in_place else None,
+                                                 mg_b.data_ptr() if in_place else None, native.stream())
         native.check(rc, "qn_dropout_add_layernorm_bwd")
         native.count(2)
         dres_v = dres.view(shape)
         dx_v = dx.view(shape) if dx is not None else dres_v
         if cs is not None and dx is not None:        # (p == 0: dx aliases dres, which also feeds the residual stream)
             offer_colsum(dx_v, cs)
+        if in_place:
+            wgrad_done(wp)
+            return dx_v, dres_v, None, None, None, None
         return dx_v, dres_v, dg.to(wdtype), db.to(wdtype), None, None
 
 

@@ -170,7 +170,8 @@ _SIGNATURES = {
     "qn_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _I, _P],
     "qn_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _P],
     "qn_dropout_add_layernorm_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _F, _F, _U, _U, _P],
-    "qn_dropout_add_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _U, _U, _P, _P],
+    "qn_dropout_add_layernorm_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _F, _U, _U, _P, _P, _P, _P],
+    "qn_colsum_accum_f32": [_P, _P, _I, _I, _L, _P],
     "qn_dropout_add_fwd": [_P, _P, _P, _L, _F, _U, _U, _P],
     "qn_dropout_bwd": [_P, _P, _L, _F, _U, _U, _P],
     "qn_gelu_fwd": [_P, _P, _L, _P],

@@ -24,7 +24,7 @@ import torch
 import torch.distributed as dist
 
 from . import native, symm
-from .cuda_ops import EPI_BIAS, EPI_BIAS_GELU, EPI_MUL_AUX, EPI_NONE, colsum, gemm, wgrad
+from .cuda_ops import EPI_BIAS, EPI_BIAS_GELU, EPI_MUL_AUX, EPI_NONE, bias_grad, colsum, gemm, wgrad
 
 _P, _I, _L, _U32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes.c_uint
 native.declare("qn_gemm_ag_bf16", [_P, _P, _P, _I, _I, _U32, _P, _P, _I, _I, _I, _L, _L, _I, _I, _P, _P, _L, _I, _I, _P, _P])
@@ -198,6 +198,7 @@ class _AllGatherLinear(torch.autograd.Function):
         y, x_full = _ag_gemm(ws, x2, w, False, N, K, epi, b, z, need_x)
         ctx.save_for_backward(x_full, w, z)
         ctx.group, ctx.has_bias, ctx.xshape = group, b is not None, x.shape
+        ctx.b_param = b
         return y.view(x.shape[0] * ws.world, *x.shape[1:-1], N)
 
     @staticmethod
@@ -217,7 +218,7 @@ class _AllGatherLinear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = wgrad(w, dy2, x_full, N, K, M)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dy2)
+            db = bias_grad(ctx.b_param, dy2)
         return dx, dw, db, None, None
 
 
@@ -232,6 +233,7 @@ class _LinearReduceScatter(torch.autograd.Function):
         y = _gemm_rs(ws, x2, w, False, N, K, b)
         ctx.save_for_backward(x2, w)
         ctx.group, ctx.has_bias, ctx.xshape = group, b is not None, x.shape
+        ctx.b_param = b
         return y.view(x.shape[0] // ws.world, *x.shape[1:-1], N)
 
     @staticmethod
@@ -247,7 +249,7 @@ class _LinearReduceScatter(torch.autograd.Function):
         # dX = AG(dY_local) · W   (W [N, K] stored [K_red = N, N_out = K] -> MN-major B)
         dx, dy_full = _ag_gemm(ws, dy2, w, True, K, N, EPI_NONE, None, None, need_full, transient=True)
         dw = wgrad(w, dy_full, x2, N, K, M) if ctx.needs_input_grad[1] else None
-        db = colsum(dy_full) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
+        db = bias_grad(ctx.b_param, dy_full) if (ctx.has_bias and ctx.needs_input_grad[2]) else None
         return dx.view(ctx.xshape), dw, db, None
 
 
@@ -268,6 +270,7 @@ class _SequenceParallelMLP(torch.autograd.Function):
         y = _gemm_rs(ws, a, w2, False, w2.shape[0], I, b2)
         ctx.save_for_backward(x_full, w1, w2, g, a)
         ctx.group, ctx.has_b1, ctx.has_b2, ctx.xshape = group, b1 is not None, b2 is not None, x.shape
+        ctx.b1_param, ctx.b2_param = b1, b2
         return y.view(*x.shape[:-1], w2.shape[0])
 
     @staticmethod
@@ -283,10 +286,10 @@ class _SequenceParallelMLP(torch.autograd.Function):
         # dZ = (AG(dY_local) · W2) ⊙ gelu'(z)   — gelu' applied in the fused kernel's epilogue
         dz, dy_full = _ag_gemm(ws, dy2, w2, True, I, O, EPI_MUL_AUX, None, g, True, transient=True)
         dw2 = wgrad(w2, dy_full, a, O, I, M)
-        db2 = colsum(dy_full) if ctx.has_b2 else None
+        db2 = bias_grad(ctx.b2_param, dy_full) if ctx.has_b2 else None
         dx = _gemm_rs(ws, dz, w1, True, E, I, None).view(ctx.xshape)             # dX_local = RS(dZ · W1)
         dw1 = wgrad(w1, dz, x_full, I, E, M)
-        db1 = colsum(dz) if ctx.has_b1 else None
+        db1 = bias_grad(ctx.b1_param, dz) if ctx.has_b1 else None
         return dx, dw1, db1, dw2, db2, None
 
 

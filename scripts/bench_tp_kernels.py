@@ -79,14 +79,19 @@ for name, kind, N, K, b_mn, epi in CASES:
     e1.record(); torch.cuda.synchronize()
     if rank == 0:
         print(f"{name} plain GEMM (no comm, no epilogue) back-to-back {e0.elapsed_time(e1) * 1e3 / 12:6.1f} us  dbg=-", flush=True)
-MODES = [m for m in os.environ.get("QN_BENCH_TP_MODES", "pump:1,lsu:1,pump:0").split(",") if m]
+# mode:pairs[:dbg]  — dbg = QN_TP_DEBUG attribution knobs (results WRONG when set): AG 4 skip waits, 8 skip push, 12 both;
+# RS 1 skip the peer wait + add
+MODES = [m for m in os.environ.get("QN_BENCH_TP_MODES", "pump:1,pump:1:4,pump:1:8,pump:1:12,pump:1:1").split(",") if m]
 for spec in MODES:
-    mode, pairs = spec.split(":")
+    parts = spec.split(":")
+    mode, pairs = parts[0], parts[1]
     os.environ["QN_TP_AG_MODE"] = mode
     os.environ["QN_TP_2CTA"] = pairs
-    for dbg in (0,):
+    for dbg in (int(parts[2]) if len(parts) > 2 else 0,):
         os.environ["QN_TP_DEBUG"] = str(dbg)
         for name, kind, N, K, b_mn, epi in CASES:
+            if dbg and ((kind == "ag") != bool(dbg & 12)):
+                continue                                   # knob does not apply to this kernel family
             t, tb = run_case(kind, N, K, b_mn, epi)
             out[f"{name} ag={mode} pairs={pairs} dbg={dbg}"] = {"us_isolated": round(t, 1), "us_back_to_back": round(tb, 1)}
             if rank == 0:

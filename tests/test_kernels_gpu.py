@@ -522,3 +522,35 @@ def test_mxfp8_linear_autograd_and_recipe():
     yr.pow(2).mean().backward()
     assert _rel(y, yr) < 2e-2
     assert _rel(x.grad, xr.grad) < 5e-2 and _rel(w.grad, wr.grad) < 5e-2 and _rel(b.grad, br.grad) < 5e-2
+
+
+def test_bias_and_layernorm_grads_accumulate_into_main_grad():
+    """fp32 main grads: the bias column-sum kernel and the fused LayerNorm backward accumulate their parameter gradients
+    IN PLACE (no finalize pass, nothing for autograd to add), twice in a row = micro-batch accumulation."""
+    from quintnet_b200 import ops
+    from quintnet_b200.ops import cuda_ops
+    torch.manual_seed(61)
+    rows, cols = 2048, 1024
+    mk = lambda *s: torch.nn.Parameter(torch.randn(*s, device="cuda").to(torch.bfloat16))
+    g, b, bias = mk(cols), mk(cols), mk(cols)
+    for p_ in (g, b, bias):
+        p_.main_grad = torch.zeros(cols, device="cuda")
+    ref_g = torch.zeros(cols, device="cuda"); ref_b = torch.zeros(cols, device="cuda"); ref_bias = torch.zeros(cols, device="cuda")
+    ops.set_fused_wgrad_accumulation(True)
+    try:
+        for it in range(2):
+            x = torch.randn(rows, cols, device="cuda").to(torch.bfloat16).requires_grad_(True)
+            r = torch.randn(rows, cols, device="cuda").to(torch.bfloat16).requires_grad_(True)
+            y, h = cuda_ops.dropout_add_layer_norm(x, r, g, b, 1e-5, 0.0)
+            dy = torch.randn_like(y)
+            torch.autograd.backward([y, h], [dy, torch.zeros_like(h)])
+            assert g.grad is None and b.grad is None
+            hf = (x.float() + r.float()).detach()
+            xhat = (hf - hf.mean(-1, keepdim=True)) * torch.rsqrt(hf.var(-1, unbiased=False, keepdim=True) + 1e-5)
+            ref_g += (dy.float() * xhat).sum(0); ref_b += dy.float().sum(0)
+            d2 = torch.randn(rows, cols, device="cuda").to(torch.bfloat16)
+            assert cuda_ops.bias_grad(bias, d2) is None
+            ref_bias += d2.float().sum(0)
+    finally:
+        ops.set_fused_wgrad_accumulation(False)
+    assert _rel(g.main_grad, ref_g) < 2e-3 and _rel(b.main_grad, ref_b) < 2e-3 and _rel(bias.main_grad, ref_bias) < 1e-4
