@@ -112,6 +112,8 @@ class Trainer(_TrainerBase):
         self._make_lr_sched(len(train_loader) if hasattr(train_loader, "__len__") else 0)
         if self.is_pipeline:
             self._setup_pipeline_training()
+        elif self.config.get("cuda_graphs", False):
+            self._enable_model_graphs(self.micro_batch_size())
 
     def _setup_pipeline_training(self):
         self.pipeline_trainer = PipelineTrainer(
@@ -127,6 +129,34 @@ class Trainer(_TrainerBase):
         self.tensor_shapes = tuple(self.model.get_tensor_shapes(mb))
         if self.config.get("cuda_graphs", False):
             self._enable_stage_graphs(mb)
+
+    def _enable_model_graphs(self, mb: int):
+        """``cuda_graphs: true`` without a pipeline: capture the whole model's micro-batch forward + backward."""
+        if not (torch.cuda.is_available() and str(self.device).startswith("cuda")):
+            return
+        is_ddp = hasattr(self.model, "bucket_manager") and hasattr(self.model, "model")
+        inner = self.model.model if is_ddp else self.model
+        shape = (mb, int(self.config.get("in_channels", 1)), int(self.config.get("img_size", 28)),
+                 int(self.config.get("img_size", 28)))
+        try:
+            if is_ddp:
+                self.model.require_backward_grad_sync = False
+            inner.train()
+            sample = torch.randn(shape, device=self.device, dtype=self.dtype)
+            graphed = torch.cuda.make_graphed_callables(inner, (sample,), num_warmup_iters=3)
+            if is_ddp:
+                self.model.model = graphed
+            else:
+                self.model = graphed
+            self.graphed = True
+        except Exception as e:  # noqa: BLE001 — capture is an optimisation; report and stay eager
+            print(f"[quintnet_b200] CUDA-graph capture of the model failed, running eagerly: {type(e).__name__}: {str(e)[:300]}",
+                  flush=True)
+            self.graphed = False
+        finally:
+            if is_ddp:
+                self.model.require_backward_grad_sync = True
+        zero_grads(self.model, self.optimizer)
 
     def _enable_stage_graphs(self, mb: int):
         """``cuda_graphs: true`` — graph the per-micro-batch stage body (forward + backward): see
