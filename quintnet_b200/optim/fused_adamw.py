@@ -23,6 +23,7 @@ from ..ops import optim_ops
 
 class FusedAdamW(torch.optim.Optimizer):
     owns_flat_grads = True
+    accepts_grad_scale = True          # step(grad_scale=<device scalar>) multiplies the gradients inside the kernel
 
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 1e-3, betas=(0.9, 0.999),
                  eps: float = 1e-8, weight_decay: float = 0.01, buckets: Optional[List[GradientBucket]] = None,

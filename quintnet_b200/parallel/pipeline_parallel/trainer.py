@@ -93,9 +93,18 @@ class PipelineTrainer:
             stage.sync_tied_weights_grad()
 
     def clip_and_step(self) -> None:
-        from ...optim.utils import clip_grad_norm_global, zero_grads
+        from ...optim.utils import clip_grad_norm_global, global_grad_norm, zero_grads
         opt = self.optimizer
         if self.max_grad_norm > 0 and not getattr(opt, "handles_grad_clipping", False):
+            if getattr(opt, "accepts_grad_scale", False):
+                # the clip coefficient rides into the fused AdamW kernel as a device scalar: no pass over the gradients
+                # to scale them (and no host read of the norm)
+                params = [p for p in self.model.parameters()]
+                norm = global_grad_norm(params, self.pg_manager)
+                coef = None if norm is None else (self.max_grad_norm / (norm + 1e-6)).clamp(max=1.0)
+                opt.step(grad_scale=coef)
+                zero_grads(self.model, opt)
+                return
             clip_grad_norm_global(self.model.parameters(), self.max_grad_norm, self.pg_manager)
         opt.step()
         zero_grads(self.model, opt)
