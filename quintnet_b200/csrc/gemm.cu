@@ -84,6 +84,8 @@ struct TpComm {
   __nv_bfloat16* stage[TP_MAX];       // RS: every rank's staging buffer [world][slabs_per_rank] x 4 KB slab images
   uint32_t* rs_flags[TP_MAX];         // RS: every rank's flags: [kAgDoneBase + src] = "all of src's partial slabs for this rank
                                       // have landed", [kLocalCntBase] = this rank's epilogue-warp arrival counter
+  uint32_t rs_parts;                  // RS: number of separately published row parts per owner (1 or kAgParts)
+  uint32_t ag_parts;                  // AG pump: number of separately published shard parts (1 or kAgParts)
   uint32_t ag_mode;                   // AG_PUMP: one bulk-copy pump thread per CTA (default); AG_LSU: two push warps
                                       // per CTA with 16-byte stores (round-1 kernel, kept for A/B timing);
                                       // AG_EXTERNAL: the shard is copied by someone else (copy engine on a side
@@ -93,7 +95,10 @@ struct TpComm {
 };
 
 constexpr uint32_t kAgDoneBase = 200000;      // flag index of the per-source "whole shard has landed" flags (external push)
-constexpr uint32_t kLocalCntBase = kAgDoneBase + 32;   // index of this rank's own grid-arrival counter (same flag buffer)
+constexpr uint32_t kAgParts = 4;              // AG: the shard is published in this many row-contiguous parts (pieces are dealt
+                                              // in address order, so part q of every source completes at ~(q+1)/4 of the
+                                              // transfer and the consumer can start on it while the rest is in flight)
+constexpr uint32_t kLocalCntBase = kAgDoneBase + 64;   // index of this rank's own grid-arrival counters (same flag buffer)
 constexpr uint32_t kPumpSlot = 8192;          // AG pump: bytes per ring slot
 constexpr uint32_t kPumpRing = 4;             // 4 x 8 KB, loads issued kPumpAhead pieces ahead of the stores
 constexpr uint32_t kPumpAhead = 2;
@@ -227,7 +232,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t mb128 = m_blk * kMbPerTile + cta_rank;          // this CTA's 128-row block of A
           a_remote = (mb128 / tc.mb_per_rank) != static_cast<uint32_t>(tc.rank);
           if (a_remote && !(tc.debug & 4u)) {   // the peer's pushes of these 128 rows must have landed
-            if (tc.ag_mode != AG_LSU) {   // pump / external: ONE flag per source rank = "its whole shard has landed"
+            if (tc.ag_mode == AG_PUMP) {  // one flag per (source rank, shard part): "that part of its shard has landed"
+              const uint32_t srcr = mb128 / tc.mb_per_rank;
+              const uint32_t part = tc.ag_parts > 1 ? (mb128 % tc.mb_per_rank) * tc.ag_parts / tc.mb_per_rank : 0u;
+              if (lane == 0) wait_flag_ge(tc.ag_flags[tc.rank] + kAgDoneBase + srcr * kAgParts + part, tc.seq);
+            } else if (tc.ag_mode == AG_EXTERNAL) {   // copy engine: ONE flag per source rank
               if (lane == 0) wait_flag_ge(tc.ag_flags[tc.rank] + kAgDoneBase + mb128 / tc.mb_per_rank, tc.seq);
             } else if (lane < 16) {
               wait_flag_ge(tc.ag_flags[tc.rank] + mb128 * 16 + lane, tc.seq);                // 16 8-row units in parallel
@@ -388,24 +397,65 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
         cnt += n_mine;
       };
-      run(src, shard_off, true, mine, shard_bytes);
-      tma_store_wait_all<0>();                       // every piece of this CTA has been performed at its destinations
-      fence_proxy_async_all();
-      __threadfence_system();
-      uint32_t* lcnt = tc.ag_flags[tc.rank] + kLocalCntBase;
-      uint32_t prev;
-      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(lcnt) : "memory");
-      if (prev == gridDim.x - 1) {                   // last pump of the grid: the whole shard is out
-        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(lcnt), "r"(0u) : "memory");
-        __threadfence_system();
-        for (int pr = 1; pr < tc.world; ++pr)
-          st_relaxed_sys(tc.ag_flags[(tc.rank + pr) % tc.world] + kAgDoneBase + tc.rank, tc.seq);
+      // part boundaries: when this CTA has stored its last piece of part q, it waits for its store groups, fences and
+      // arrives on the part's local counter; the last arrival of the grid publishes "part q of rank r has landed"
+      {
+        const uint32_t parts = tc.ag_parts;
+        const size_t part_bytes = shard_bytes / parts;             // (multiple of 128 rows: checked on the host)
+        uint32_t* lcnt = tc.ag_flags[tc.rank] + kLocalCntBase;
+        uint32_t cur = 0;                                          // first part not yet signalled by this CTA
+        auto arrive_upto = [&](uint32_t upto) {                    // signal parts [cur, upto)
+          if (upto <= cur) return;
+          tma_store_wait_all<0>();                                 // every store this CTA issued so far has been performed
+          fence_proxy_async_all();
+          __threadfence_system();
+          for (uint32_t q = cur; q < upto; ++q) {
+            uint32_t prev;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(lcnt + q) : "memory");
+            if (prev == gridDim.x - 1) {                           // last pump of the grid for this part
+              asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(lcnt + q), "r"(0u) : "memory");
+              __threadfence_system();
+              for (int pr = 1; pr < tc.world; ++pr)
+                st_relaxed_sys(tc.ag_flags[(tc.rank + pr) % tc.world] + kAgDoneBase + tc.rank * kAgParts + q, tc.seq);
+            }
+          }
+          cur = upto;
+        };
+        // same pipelined loop as run(), with the part check after each store
+        for (uint32_t it = 0; it < mine + kPumpAhead; ++it) {
+          if (it < mine) {
+            const size_t off = static_cast<size_t>(blockIdx.x + it * gridDim.x) * kPumpSlot;
+            const uint32_t bytes = static_cast<uint32_t>(min(static_cast<size_t>(kPumpSlot), shard_bytes - off));
+            const uint32_t slot = (cnt + it) % kPumpRing;
+            tma_store_wait_read<kPumpRing - kPumpAhead - 1>();
+            mbar_arrive_expect_tx(&pump_bar[slot], bytes);
+            bulk_load_1d(smem_ring + slot * kPumpSlot, src + off, bytes, &pump_bar[slot]);
+          }
+          if (it >= kPumpAhead) {
+            const uint32_t j = it - kPumpAhead;
+            const size_t off = static_cast<size_t>(blockIdx.x + j * gridDim.x) * kPumpSlot;
+            const uint32_t bytes = static_cast<uint32_t>(min(static_cast<size_t>(kPumpSlot), shard_bytes - off));
+            const uint32_t slot = (cnt + j) % kPumpRing;
+            uint8_t* buf = smem_ring + slot * kPumpSlot;
+            mbar_wait(&pump_bar[slot], ((cnt + j) / kPumpRing) & 1);
+            for (int pr = 1; pr < tc.world; ++pr)
+              bulk_store_1d(reinterpret_cast<uint8_t*>(tc.gather[(tc.rank + pr) % tc.world]) + shard_off + off, buf, bytes);
+            bulk_store_1d(local_dst + shard_off + off, buf, bytes);
+            tma_store_commit();
+            // the next piece of this CTA (if any) starts at off + gridDim.x * kPumpSlot: parts below it are complete here
+            const size_t next_off = off + static_cast<size_t>(gridDim.x) * kPumpSlot;
+            if (parts > 1) arrive_upto(next_off >= shard_bytes ? parts : static_cast<uint32_t>(next_off / part_bytes));
+          }
+        }
+        cnt += mine;
+        arrive_upto(parts);                                        // (CTAs without pieces, or parts == 1)
       }
       // second duty (background): peers' rows, gather buffer -> x_full, once their shards have landed
       if (tc.x_full != nullptr && !(tc.debug & 4u)) {
         for (int pr = 1; pr < tc.world; ++pr) {
           const uint32_t srcr = (tc.rank + pr) % tc.world;
-          wait_flag_ge(tc.ag_flags[tc.rank] + kAgDoneBase + srcr, tc.seq);
+          for (uint32_t q = 0; q < tc.ag_parts; ++q)
+            wait_flag_ge(tc.ag_flags[tc.rank] + kAgDoneBase + srcr * kAgParts + q, tc.seq);
           fence_proxy_async_all();
           const uint32_t m2 = npieces > blockIdx.x ? (npieces - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
           run(reinterpret_cast<const uint8_t*>(tc.gather[tc.rank]) + static_cast<size_t>(srcr) * shard_bytes,
@@ -454,22 +504,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // fences once and arrives on a local counter; the last of the grid's epilogue warps publishes ONE flag per peer:
     // "every partial slab rank r owes you has landed".  Own tiles come last, so that flag is normally up already.
     uint32_t rs_slab = 0;
-    bool rs_signaled = false, rs_peers_ready = false;
-    auto rs_signal = [&]() {                   // lane 0 only
-      if (rs_signaled) return;
-      rs_signaled = true;
+    // Publication is per (owner, row part): the tile order walks the owners' row ranges in sequence (peers first, own rows
+    // last; part boundaries coincide with tile-group boundaries), so "key" = owner-order * parts + part is monotone along
+    // the loop.  A warp arrives on key k's counter when it moves past it; the grid's last arrival tells that owner
+    // "part q of rank r's partials has landed" — the owner starts reducing its first rows while the peers are still
+    // producing the later parts.
+    uint32_t rs_cur = 0, rs_ready = 0;         // first key not yet signalled / first own part not yet confirmed
+    const uint32_t rs_keys = (tc.world - 1) * tc.rs_parts;
+    auto rs_arrive_upto = [&](uint32_t upto) { // lane 0 only
+      if (upto <= rs_cur) return;
       tma_store_wait_all<0>();
       fence_proxy_async_all();
       __threadfence_system();
       uint32_t* lcnt = tc.rs_flags[tc.rank] + kLocalCntBase;
-      uint32_t prev;
-      asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(lcnt) : "memory");
-      if (prev == gridDim.x * 8 - 1) {         // last epilogue warp of the grid
-        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(lcnt), "r"(0u) : "memory");
-        __threadfence_system();
-        for (int pr = 1; pr < tc.world; ++pr)
-          st_relaxed_sys(tc.rs_flags[(tc.rank + pr) % tc.world] + kAgDoneBase + tc.rank, tc.seq);
+      for (uint32_t k = rs_cur; k < upto; ++k) {
+        uint32_t prev;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(prev) : "l"(lcnt + k) : "memory");
+        if (prev == gridDim.x * 8 - 1) {       // last epilogue warp of the grid for this key
+          asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(lcnt + k), "r"(0u) : "memory");
+          __threadfence_system();
+          const uint32_t dst = (tc.rank + 1 + k / tc.rs_parts) % tc.world;
+          st_relaxed_sys(tc.rs_flags[dst] + kAgDoneBase + tc.rank * kAgParts + k % tc.rs_parts, tc.seq);
+        }
       }
+      rs_cur = upto;
     };
     for (uint32_t work = worker; work < num_work; work += n_cta) {
       const uint32_t tile = work / splits;
@@ -527,15 +585,15 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           uint64_t* ab = &aux_bar[warp - kEpiWarp0];
           ++rs_slab;
           if (lane == 0) {
-            if (mine) rs_signal();                 // everything this warp owes its peers is out before it starts waiting
+            const uint32_t part = (mb128 % tc.mb_per_rank) * tc.rs_parts / tc.mb_per_rank;
+            // everything this warp owed for the keys before this slab's is out
+            rs_arrive_upto(mine ? rs_keys : ((owner + tc.world - tc.rank - 1) % tc.world) * tc.rs_parts + part);
             if (mine && !(tc.debug & 1u)) {
               tma_store_wait_read<0>();            // both staging buffers are free
               const uint32_t src = (tc.rank + 1) % tc.world;       // first peer's partial: load overlaps the TMEM read
-              if (!rs_peers_ready) {               // once per warp: every peer's partial slabs for this rank have landed
+              for (; rs_ready <= part; ++rs_ready)     // every peer's partial slabs for this part of my rows have landed
                 for (int pr = 1; pr < tc.world; ++pr)
-                  wait_flag_ge(tc.rs_flags[tc.rank] + kAgDoneBase + (tc.rank + pr) % tc.world, tc.seq);
-                rs_peers_ready = true;
-              }
+                  wait_flag_ge(tc.rs_flags[tc.rank] + kAgDoneBase + ((tc.rank + pr) % tc.world) * kAgParts + rs_ready, tc.seq);
               fence_proxy_async_all();
               mbar_arrive_expect_tx(ab, 4096);
               bulk_load_1d(pbuf, reinterpret_cast<const uint8_t*>(tc.stage[tc.rank]) +
@@ -749,7 +807,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
-    if constexpr (FUSE == FUSE_RS) { if (lane == 0) rs_signal(); }
+    if constexpr (FUSE == FUSE_RS) { if (lane == 0) rs_arrive_upto(rs_keys); }
     if (lane == 0) tma_store_wait_all<0>();
   }
 
@@ -1048,6 +1106,9 @@ static int fill_comm(TpComm& c, int rank, int world, unsigned seq, int M) {
   c.debug = dbg ? static_cast<uint32_t>(atoi(dbg)) : 0u;
   const char* mode = getenv("QN_TP_AG_MODE");                // "pump" (default) | "lsu" | "ce" (copy engine, Python side)
   c.ag_mode = (mode && mode[0] == 'c') ? AG_EXTERNAL : (mode && mode[0] == 'l') ? AG_LSU : AG_PUMP;
+  const char* parts = getenv("QN_TP_AG_PARTS");              // 1 = single done-flag per source (A/B timing)
+  c.ag_parts = (c.mb_per_rank % kAgParts == 0 && !(parts && atoi(parts) == 1)) ? kAgParts : 1u;
+  c.rs_parts = 1;                                            // set by the RS launcher once the tile grouping is known
   return 0;
 }
 // m-blocks per rasterisation group: the largest of 8/4/2/1 that divides the tile rows of one rank, so that no group
@@ -1133,6 +1194,12 @@ extern "C" int qn_gemm_rs_bf16(const void* a, const void* b, void* c_local, void
   if ((rc = make_tmap(&ta, a, M, K, lda, 64, BLOCK_M))) return rc;
   const bool two_cta = tp_cta_pairs() && (comm.rows_per_rank % 256) == 0 && use_cta_pairs(M, N, block_n, 1, 0);
   p.group_m = fused_group_m(comm.mb_per_rank / (two_cta ? 2 : 1));
+  {
+    // row parts must be whole tile groups, so that the (owner, part) key is monotone along every warp's tile loop
+    const uint32_t tr = comm.mb_per_rank / (two_cta ? 2 : 1);
+    const char* parts = getenv("QN_TP_RS_PARTS");
+    comm.rs_parts = (tr % kAgParts == 0 && (tr / kAgParts) % p.group_m == 0 && !(parts && atoi(parts) == 1)) ? kAgParts : 1u;
+  }
   if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, two_cta ? 128 : block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
   if (rc) return rc;
   if ((rc = make_tmap(&tcm, c_local, comm.rows_per_rank, N, ldc, 64, 32))) return rc;

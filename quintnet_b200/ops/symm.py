@@ -278,8 +278,11 @@ _oneshot: Dict[int, _OneShotWorkspace] = {}
 
 
 def oneshot_ok(x: torch.Tensor, group) -> bool:
+    # TP-sized groups only: at 8 ranks the two-shot NVLS kernel (24 us) and NCCL (38 us) both beat the one-shot
+    # kernel's 7 peer reads per element (48 us; profiles/r2_allreduce_sweep_8gpu.txt)
     return (x.is_cuda and x.dtype in _DT and x.numel() * x.element_size() <= ONESHOT_MAX_BYTES
-            and "allreduce" in native._enabled_set() and available(group))
+            and "allreduce" in native._enabled_set() and available(group)
+            and dist.get_world_size(group) <= 4)
 
 
 def all_reduce_small(x: torch.Tensor, group, scale: float = 1.0) -> torch.Tensor:

@@ -140,6 +140,7 @@ def _run_rs(world, M, N, K, b_mn, with_bias, pairs, launches=3):
     (2, 2048, 512, 1024, True, EPI_NONE),            # c_proj dgrad (B MN-major)
     (2, 2048, 1024, 768, True, EPI_MUL_AUX),         # mlp-proj dgrad ⊙ gelu', K = 768 (12 KB pump units)
     (4, 4096, 512, 1280, False, EPI_NONE),           # world 4, K = 1280 (20 KB units -> two pump pieces)
+    (2, 16384, 512, 1024, True, EPI_NONE),           # bench-size shard (8192 rows): four separately published parts
 ])
 def test_ag_gemm_loopback(world, M, N, K, b_mn, epi, pairs, mode):
     torch.manual_seed(0)
@@ -154,6 +155,8 @@ def test_ag_gemm_loopback(world, M, N, K, b_mn, epi, pairs, mode):
     (2, 2048, 1024, 1536, True, False),              # c_attn dgrad (B MN-major)
     (2, 2048, 1000, 512, False, True),               # N not a multiple of 64 (clipped last chunk)
     (4, 4096, 768, 256, False, True),                # world 4: three staged partials per slab
+    (2, 16384, 1024, 512, False, True),              # bench-size shard: per-part publication (4 parts per owner)
+    (4, 16384, 512, 256, False, True),               # world 4 with parts: 12 (owner, part) keys per rank
 ])
 def test_gemm_rs_loopback(world, M, N, K, b_mn, with_bias, pairs):
     torch.manual_seed(0)
