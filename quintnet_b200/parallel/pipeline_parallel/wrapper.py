@@ -90,7 +90,7 @@ class PipelineParallelWrapper(nn.Module):
             eager = self.local_module
             was_training = eager.training
             eager.train()
-            graphed = torch.cuda.make_graphed_callables(eager, (sample,), num_warmup_iters=3)
+            graphed = torch.cuda.make_graphed_callables(eager, (sample,), num_warmup_iters=3, allow_unused_input=True)
             eager.train(was_training)
             self.local_module = graphed
             self._graphed_shape = tuple(input_shape)

@@ -143,7 +143,7 @@ class Trainer(_TrainerBase):
                 self.model.require_backward_grad_sync = False
             inner.train()
             sample = torch.randn(shape, device=self.device, dtype=self.dtype)
-            graphed = torch.cuda.make_graphed_callables(inner, (sample,), num_warmup_iters=3)
+            graphed = torch.cuda.make_graphed_callables(inner, (sample,), num_warmup_iters=3, allow_unused_input=True)
             if is_ddp:
                 self.model.model = graphed
             else:

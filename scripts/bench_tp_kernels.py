@@ -101,6 +101,6 @@ os.environ["QN_TP_2CTA"] = "1"
 os.environ["QN_TP_DEBUG"] = "0"
 if rank == 0:
     os.makedirs("gpurun_out", exist_ok=True)
-    json.dump(out, open("gpurun_out/r2_tp_kernel_times.json", "w"), indent=1)
+    json.dump(out, open(os.environ.get("QN_BENCH_TP_OUT", "gpurun_out/r2_tp_kernel_times.json"), "w"), indent=1)
 dist.barrier()
 dist.destroy_process_group()

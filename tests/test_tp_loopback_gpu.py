@@ -68,6 +68,7 @@ def _run_ag(world, M, N, K, b_mn, epi, pairs, mode, launches=3):
         # odd launches also ask for the private gathered-operand tensor (forward mode), even ones use the buffer view
         xfull = [torch.zeros(M, K, dtype=torch.bfloat16, device="cuda") if (mode == "pump" and seq % 2 == 1) else None
                  for _ in range(world)]
+        torch.cuda.synchronize()                             # the zero-fills above ran on the default stream
         for r in range(world):
             rc = lib.qn_gemm_ag_bf16(xs[r].data_ptr(), _ptrs(gather[par]), _ptrs(flags), r, world, seq, ws[r].data_ptr(),
                                      ys[r].data_ptr(), M, N, K, ws[r].stride(0), N, int(b_mn), epi,
