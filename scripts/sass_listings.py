@@ -33,8 +33,8 @@ for b in blocks:
     if not m:
         continue
     name = m.group(1)
-    insts = re.findall(r"/\*[0-9a-f]{4}\*/\s+([^;]+);", b)
-    cnt = {k: sum(1 for i in insts if k in i) for k in KEYS}
+    insts = re.findall(r"/\*[0-9a-f]{4,6}\*/\s+([^;]+);", b)
+    cnt = {k: sum(1 for i in insts if re.search(r"(?<![A-Z])" + re.escape(k), i)) for k in KEYS}
     census.append((name, len(insts), cnt))
     for fname, rx in FAMILIES.items():
         if re.search(rx, name):
