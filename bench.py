@@ -549,7 +549,10 @@ def run_vit(args):
         from quintnet_b200 import Trainer, get_strategy, init_process_groups
         from quintnet_b200.models import Model
         cfg.update(dtype="float32" if args.cpu else "bfloat16", tp_method="paired",
-                   cuda_graphs=(not args.cpu) and os.environ.get("QN_VIT_GRAPHS", "1") == "1")
+                   # CUDA graphs by default only where they were measured (pure pipeline meshes: pp2 9.5k img/s vs
+                   # 1.7k eager); QN_VIT_GRAPHS=1 forces them on, =0 off
+                   cuda_graphs=(not args.cpu) and os.environ.get(
+                       "QN_VIT_GRAPHS", "1" if (tp == 1 and dp == 1 and pp > 1) else "0") == "1")
         dtype_name = "fp32" if args.cpu else "bf16"
     pg = init_process_groups(cfg["device_type"], cfg["mesh_dim"], cfg["mesh_name"])
     g = torch.Generator().manual_seed(100 + pg.get_coordinates_tensor_search(rank)[0])

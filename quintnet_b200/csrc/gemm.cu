@@ -1106,8 +1106,12 @@ static int fill_comm(TpComm& c, int rank, int world, unsigned seq, int M) {
   c.debug = dbg ? static_cast<uint32_t>(atoi(dbg)) : 0u;
   const char* mode = getenv("QN_TP_AG_MODE");                // "pump" (default) | "lsu" | "ce" (copy engine, Python side)
   c.ag_mode = (mode && mode[0] == 'c') ? AG_EXTERNAL : (mode && mode[0] == 'l') ? AG_LSU : AG_PUMP;
-  const char* parts = getenv("QN_TP_AG_PARTS");              // 1 = single done-flag per source (A/B timing)
-  c.ag_parts = (c.mb_per_rank % kAgParts == 0 && !(parts && atoi(parts) == 1)) ? kAgParts : 1u;
+  // Default: ONE done-flag per source.  Publishing the shard in kAgParts parts (QN_TP_AG_PARTS=4) lets the consumer
+  // start on the first rows while the rest is in flight, but every part costs each pump a store-group drain plus a
+  // system fence, and the pump is the critical path: measured slower (c_attn 75.6 vs 66.9 us, tp2 step 473 vs 455 ms;
+  // profiles/r2_tp_kernel_times.json vs r2_tp_kernel_times_1part.json).
+  const char* parts = getenv("QN_TP_AG_PARTS");
+  c.ag_parts = (c.mb_per_rank % kAgParts == 0 && parts && atoi(parts) == static_cast<int>(kAgParts)) ? kAgParts : 1u;
   c.rs_parts = 1;                                            // set by the RS launcher once the tile grouping is known
   return 0;
 }
@@ -1198,7 +1202,8 @@ extern "C" int qn_gemm_rs_bf16(const void* a, const void* b, void* c_local, void
     // row parts must be whole tile groups, so that the (owner, part) key is monotone along every warp's tile loop
     const uint32_t tr = comm.mb_per_rank / (two_cta ? 2 : 1);
     const char* parts = getenv("QN_TP_RS_PARTS");
-    comm.rs_parts = (tr % kAgParts == 0 && (tr / kAgParts) % p.group_m == 0 && !(parts && atoi(parts) == 1)) ? kAgParts : 1u;
+    comm.rs_parts = (tr % kAgParts == 0 && (tr / kAgParts) % p.group_m == 0 && parts && atoi(parts) == static_cast<int>(kAgParts))
+                        ? kAgParts : 1u;   // opt-in (QN_TP_RS_PARTS=4): measured slower than one flag per owner, see fill_comm
   }
   if (!b_mn) rc = make_tmap(&tb, b, N, K, ldb, 64, two_cta ? 128 : block_n); else rc = make_tmap(&tb, b, K, N, ldb, 64, BLOCK_K);
   if (rc) return rc;

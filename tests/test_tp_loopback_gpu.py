@@ -32,14 +32,15 @@ def _rnd(*shape, scale=1.0):
     return (torch.randn(*shape, device="cuda") * scale).to(torch.bfloat16)
 
 
-def _set_env(pairs, mode):
+def _set_env(pairs, mode, parts=1):
     os.environ["QN_TP_2CTA"] = "1" if pairs else "0"
     os.environ["QN_TP_AG_MODE"] = mode
+    os.environ["QN_TP_AG_PARTS"] = os.environ["QN_TP_RS_PARTS"] = str(parts)   # 4 = opt-in per-part publication
 
 
 @pytest.fixture(autouse=True)
 def _restore_env():
-    keep = {k: os.environ.get(k) for k in ("QN_TP_2CTA", "QN_TP_AG_MODE")}
+    keep = {k: os.environ.get(k) for k in ("QN_TP_2CTA", "QN_TP_AG_MODE", "QN_TP_AG_PARTS", "QN_TP_RS_PARTS")}
     yield
     for k, v in keep.items():
         if v is None:
@@ -59,7 +60,7 @@ def _run_ag(world, M, N, K, b_mn, epi, pairs, mode, launches=3):
     flags = [torch.zeros(1 << 18, dtype=torch.int32, device="cuda") for _ in range(world)]
     streams = [torch.cuda.Stream() for _ in range(world)]
     cap = (148 // world) & ~1
-    _set_env(pairs, mode)
+    _set_env(pairs, mode, 4 if M >= 16384 else 1)             # bench-size cases also cover the per-part protocol
     torch.cuda.synchronize()
     for seq in range(1, launches + 1):                       # several launches: double-buffered workspaces + seq flags
         ys = [torch.empty(M, N, dtype=torch.bfloat16, device="cuda") for _ in range(world)]
@@ -112,7 +113,7 @@ def _run_rs(world, M, N, K, b_mn, with_bias, pairs, launches=3):
     flags = [torch.zeros(1 << 18, dtype=torch.int32, device="cuda") for _ in range(world)]
     streams = [torch.cuda.Stream() for _ in range(world)]
     cap = (148 // world) & ~1
-    _set_env(pairs, "pump")
+    _set_env(pairs, "pump", 4 if M >= 16384 else 1)
     torch.cuda.synchronize()
     for seq in range(1, launches + 1):
         ys = [torch.empty(rows, N, dtype=torch.bfloat16, device="cuda") for _ in range(world)]
