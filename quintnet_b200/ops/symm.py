@@ -18,6 +18,7 @@ Rendezvous back-ends, tried in order:
 """
 from __future__ import annotations
 
+import bisect
 import ctypes
 import os
 from typing import Dict, List, Optional, Tuple
@@ -81,6 +82,7 @@ class SymmBuffer:
 
 
 _registry: List[SymmBuffer] = []
+_sorted_bases = None            # (sorted base pointers, buffers in that order): lookup() is a bisect, not a scan
 _pads: Dict[Tuple[int, str], SymmBuffer] = {}
 _disabled_reason: Optional[str] = None
 _pad_configured = False
@@ -91,8 +93,14 @@ def lookup(t: torch.Tensor) -> Optional[Tuple[SymmBuffer, int]]:
     if not t.is_cuda:
         return None
     p = t.data_ptr()
-    for b in _registry:
-        if b.base <= p < b.base + b.nbytes:
+    global _sorted_bases
+    if _sorted_bases is None or len(_sorted_bases[0]) != len(_registry):     # rebuilt only when a buffer was added
+        order = sorted(_registry, key=lambda b: b.base)
+        _sorted_bases = ([b.base for b in order], order)
+    i = bisect.bisect_right(_sorted_bases[0], p) - 1
+    if i >= 0:
+        b = _sorted_bases[1][i]
+        if p < b.base + b.nbytes:
             return b, p - b.base
     return None
 

@@ -11,7 +11,7 @@ bytes instead of 12·N.  One optimizer step is two fused phases:
   B. **clip · AdamW on the shard · all-gather** of the updated parameters.
 
 On B200 each phase is one hand-written sm_100a kernel per bucket that does the
-collective itself over NVLink peer memory (``csrc/zero1.cu``: phase A pulls the
+collective itself over NVLink peer memory (``csrc/comm.cu``, ``reduce_scatter_sqnorm_kernel`` / ``adamw_allgather_kernel``: phase A pulls the
 owned slice from every peer's symmetric gradient buffer, phase B pushes the
 updated bf16 parameters into every peer's symmetric parameter buffer).  On
 CPU/gloo (and as the oracle in tests) the same two phases run on

@@ -17,6 +17,8 @@ FAMILIES = {   # file name -> mangled-name regex
     "layernorm_fwd_bf16_dropout": r"layernorm_fwd_kernelI13__nv_bfloat16Li4ELb1EEE",
     "adamw_bf16param_f32grad": r"adamw_kernelI13__nv_bfloat16fEE",
     "ce_fwd_bwd": r"ce_fwd_bwd_kernel",
+    "gemm_mxfp8_block_scaled": r"gemm_mxfp8_kernel", "quantize_mxfp8": r"quantize_mxfp8_kernel",
+    "gemm_fp8_rowwise_cta_pair": r"gemm_bf16_kernelILj256ELb0ELb0ELi0ELb1ELb0ELb1EEE",
     "allreduce_two_shot_nvls_bf16": r"allreduce_kernelI13__nv_bfloat16Lb1EEE",
     "allreduce_two_shot_p2p_bf16": r"allreduce_kernelI13__nv_bfloat16Lb0EEE",
     "allreduce_oneshot_nvls_bf16": r"allreduce_oneshot_kernelI13__nv_bfloat16Lb1EEE",
@@ -26,7 +28,7 @@ FAMILIES = {   # file name -> mangled-name regex
 txt = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
 blocks = re.split(r"\n(?=\s+Function : )", txt)
 census = []
-KEYS = ["UTCHMMA", "UTCQMMA", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "UBLKRED", "SYNCS", "LDGMC", "STG.E.128.STRONG.SYS",
+KEYS = ["UTCHMMA", "UTCQMMA", "UTCCP", "UTCBAR", "LDTM", "UTMALDG", "UTMASTG", "UBLKCP", "UBLKRED", "SYNCS", "LDGMC", "STG.E.128.STRONG.SYS",
         "MEMBAR.SC.SYS", "MEMBAR.ALL.SYS", "LDG.E.STRONG.SYS", "STG.E.STRONG.SYS", "HMMA", "RED.E.ADD.F32"]
 for b in blocks:
     m = re.match(r"\s+Function : (\S+)", b)
@@ -51,7 +53,7 @@ for b in blocks:
                 f.write("\n".join(keep) + "\n")
 with open(os.path.join(out, "CENSUS.md"), "w") as f:
     f.write("# SASS mnemonic census of every kernel in libquintnet_b200.so (sm_100a)\n\n"
-            "UTC*MMA = tcgen05.mma, LDTM = tcgen05.ld, UTMALDG/UTMASTG = TMA tensor copies, UBLKCP = 1-D bulk async copy "
+            "UTC*MMA = tcgen05.mma, UTCCP = tcgen05.cp (block-scale factors smem -> TMEM), LDTM = tcgen05.ld, UTMALDG/UTMASTG = TMA tensor copies, UBLKCP = 1-D bulk async copy "
             "(the fused TP kernels' NVLink transport), LDGMC = multimem.ld_reduce (NVLS in-switch reduction); multimem.st has no mnemonic of its own — it is the "
             "`STG.E.128.STRONG.SYS` on the multicast-mapped address; "
             "`*.STRONG.SYS` / MEMBAR.*.SYS = system-scope peer flags.\n\n| kernel | SASS instrs | " + " | ".join(KEYS) + " |\n|---|---|" + "---|" * len(KEYS) + "\n")
