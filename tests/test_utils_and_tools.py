@@ -312,3 +312,34 @@ def test_cluster_workflow_on_a_volume_directory(tmp_path):
     assert r.returncode == 0 and (tmp_path / "dl" / "final_model_merged.pt").exists()
     r = run("test-weight-shapes", "--model", "gpt2_base", "--tp", "2", "--pp", "2")
     assert r.returncode == 0, r.stderr[-800:]
+
+
+def test_symmetric_buffer_lookup_bisects_the_registry():
+    """ops.symm.lookup maps a data pointer to (buffer, byte offset) by bisecting the sorted base addresses."""
+    import quintnet_b200.ops.symm as symm
+
+    class Buf:
+        def __init__(self, base, n):
+            self.base, self.nbytes = base, n
+
+    class Ptr:
+        is_cuda = True
+
+        def __init__(self, p):
+            self.p = p
+
+        def data_ptr(self):
+            return self.p
+
+    saved, symm._registry[:] = list(symm._registry), [Buf(5000, 100), Buf(1000, 50), Buf(3000, 10)]
+    symm._sorted_bases = None
+    try:
+        for p, want in [(1000, (1000, 0)), (1049, (1000, 49)), (1050, None), (999, None), (3005, (3000, 5)),
+                        (5099, (5000, 99)), (5100, None)]:
+            r = symm.lookup(Ptr(p))
+            assert (None if r is None else (r[0].base, r[1])) == want, p
+        symm._registry.append(Buf(7000, 10))                 # a later allocation is picked up
+        assert symm.lookup(Ptr(7003))[1] == 3
+    finally:
+        symm._registry[:] = saved
+        symm._sorted_bases = None
