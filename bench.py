@@ -345,7 +345,7 @@ def run_ours(args):
                 with open(args.parity_out, "w") as f:
                     json.dump(rec, f)
         dist.barrier()
-        dist.destroy_process_group()
+        shutdown()
         return
 
     for _ in range(args.warmup):
@@ -386,7 +386,7 @@ def run_ours(args):
                  "virtual_pipeline_stages": cfg.get("virtual_pipeline_stages", 1)}
         emit(args, mesh, M, ms, e2e, clocks, launches, "ours", "fp32" if args.cpu else "bf16", extra)
     dist.barrier()
-    dist.destroy_process_group()
+    shutdown()
 
 
 # --------------------------------------------------------------------------------------- reference
@@ -514,7 +514,7 @@ def _run_reference(args, ref_root):
                 extra["precision_errors"] = errors
             emit(args, mesh, M, ms, e2e, clocks, 0, "reference", prec, extra)
     dist.barrier()
-    dist.destroy_process_group()
+    shutdown()
 
 
 # --------------------------------------------------------------------------------- ViT-MNIST (secondary)
@@ -549,10 +549,11 @@ def run_vit(args):
         from quintnet_b200 import Trainer, get_strategy, init_process_groups
         from quintnet_b200.models import Model
         cfg.update(dtype="float32" if args.cpu else "bfloat16", tp_method="paired",
-                   # CUDA graphs by default only where they were measured (pure pipeline meshes: pp2 9.5k img/s vs
-                   # 1.7k eager); QN_VIT_GRAPHS=1 forces them on, =0 off
+                   # CUDA graphs by default only on the meshes where they were measured (images/s, eager -> graphed:
+                   # one GPU 1.9k -> 6.3k, dp2 6.3k, tp2 7.2k, pp2 1.7k -> 9.5k); multi-axis meshes stay eager unless
+                   # QN_VIT_GRAPHS=1 (=0 forces eager everywhere)
                    cuda_graphs=(not args.cpu) and os.environ.get(
-                       "QN_VIT_GRAPHS", "1" if (tp == 1 and dp == 1 and pp > 1) else "0") == "1")
+                       "QN_VIT_GRAPHS", "1" if sum(a > 1 for a in (dp, tp, pp)) <= 1 else "0") == "1")
         dtype_name = "fp32" if args.cpu else "bf16"
     pg = init_process_groups(cfg["device_type"], cfg["mesh_dim"], cfg["mesh_name"])
     g = torch.Generator().manual_seed(100 + pg.get_coordinates_tensor_search(rank)[0])
@@ -602,7 +603,23 @@ def run_vit(args):
                           "parallelism": f"dp{dp}tp{tp}pp{pp}", "grad_acc_steps": M}, "clocks": clocks}
         print(json.dumps(out), flush=True)
     dist.barrier()
+    shutdown()
+
+
+def shutdown():
+    """destroy_process_group with a deadline: with CUDA graphs that captured collectives still alive the NCCL teardown
+    was seen to block after the result line had been printed (ViT tp2, round-2 trip 16) — results are out by now, so
+    a stuck teardown ends the process instead of hanging the launcher."""
+    import threading
+    import torch.distributed as dist
+    sys.stdout.flush()
+    if not dist.is_initialized():
+        return
+    t = threading.Timer(20.0, lambda: os._exit(0))
+    t.daemon = True
+    t.start()
     dist.destroy_process_group()
+    t.cancel()
 
 
 def check_parity(a_path, b_path, tol):
@@ -618,6 +635,9 @@ def check_parity(a_path, b_path, tol):
 
 def main():
     args = parse_args()
+    if os.environ.get("QN_BENCH_HANG_DUMP_S"):        # diagnosis: dump every thread's Python stack and exit if still running
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["QN_BENCH_HANG_DUMP_S"]), exit=True)
     if args.check_parity:
         sys.exit(check_parity(args.check_parity[0], args.check_parity[1], args.parity_tol))
     if args.parity_steps > 0:
