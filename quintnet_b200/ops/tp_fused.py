@@ -94,12 +94,12 @@ def can_fuse(rows_total: int, group, *dims) -> bool:
 # the producer of x_local, a side stream copies the shard into every peer's gather buffer with cudaMemcpyAsync and
 # publishes one flag per destination; the AG->GEMM kernel then runs without push warps and only acquires that flag
 # before its first remote tile.  No SM, register or L1 involvement in the transfer.
-_AG_MODE_CE = os.environ.get("QN_TP_AG_MODE", "") == "ce"
-
 
 def _ag_mode() -> str:
     """Read per call (the micro-benchmarks switch modes at run time); must mirror fill_comm() in csrc/gemm.cu."""
     return {"c": "ce", "l": "lsu"}.get((os.environ.get("QN_TP_AG_MODE") or "pump")[:1], "pump")
+
+
 _cudart = None
 
 
