@@ -129,6 +129,11 @@ class GPT2Trainer(_TrainerBase):
         if reporter and self.step_logger is None and self.config.get("log_jsonl"):
             self.step_logger = StepLogger(self.config["log_jsonl"], rank=0)
         tokens_per_step = int(self.config["batch_size"]) * self.max_seq_length
+        mc = self.model_config
+        # model FLOPs per token (fwd + bwd): 6 x (12 E^2 per block + tied lm_head V E) + causal attention 6 T E per block
+        flops_per_token = None if mc is None else (
+            6.0 * (mc.n_layer * 12 * mc.n_embd ** 2 + mc.vocab_size * mc.n_embd)
+            + mc.n_layer * 6.0 * self.max_seq_length * mc.n_embd)
         for step in range(n_steps):
             t_step = time.perf_counter()
             loss, ppl = self.train_step()
@@ -140,6 +145,10 @@ class GPT2Trainer(_TrainerBase):
                     dt = time.perf_counter() - t_step
                     self.step_logger.log(step=self.global_step, loss=loss, ppl=ppl, step_ms=dt * 1e3,
                                          tokens_per_s=tokens_per_step / dt,
+                                         model_tflops=(flops_per_token * tokens_per_step / dt / 1e12
+                                                       if flops_per_token else None),
+                                         max_mem_gb=(torch.cuda.max_memory_allocated(self.device) / 2 ** 30
+                                                     if str(self.device).startswith("cuda") else None),
                                          lr=self.optimizer.param_groups[0]["lr"] if hasattr(self.optimizer, "param_groups") else None)
             si = int(self.config.get("save_interval", 0) or 0)
             if si and self.global_step % si == 0:

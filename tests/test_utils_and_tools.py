@@ -154,6 +154,7 @@ def test_gpt2_finetune_example_cpu(tmp_path, virtual):
     rows = [json.loads(l) for l in (tmp_path / "train.jsonl").read_text().splitlines()]
     steps = [r for r in rows if "step" in r and "loss" in r]
     assert len(steps) == 4 and all(r["tokens_per_s"] > 0 and r["step_ms"] > 0 for r in steps)    # 32 samples / batch 8
+    assert all(r["model_tflops"] > 0 and r["max_mem_gb"] is None for r in steps)                 # CPU run: no device memory
     assert [r["step"] for r in rows if "step" in r and "val_loss" in r] == [2, 4]                # eval_interval = 2
     assert any("val_loss" in r for r in rows)                                                    # epoch record (rank 0)
 
