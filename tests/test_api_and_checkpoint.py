@@ -234,6 +234,52 @@ def test_bench_reference_arm_reports_unavailable_without_gpu():
     assert rec["impl"] == "reference" and "unavailable" in rec
 
 
+def test_bench_parity_mode_cpu(tmp_path):
+    """`bench.py --parity-steps` + `--check-parity` (the plumbing `tests/test_parity_gpu.py` relies on): the same seeded
+    global batch gives the same loss curve on one rank, on dp2 + ZeRO-1 and on pp2 (gloo)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    common = ["--cpu", "--parity-steps", "2", "--steps", "1", "--warmup", "1"]
+    one = str(tmp_path / "n1.json")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), *common, "--parity-out", one],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-1500:]
+    for i, mesh in enumerate(("2,1,1", "1,1,2")):
+        two = str(tmp_path / f"n2_{i}.json")
+        out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                              "--master-addr", "127.0.0.1", "--master-port", str(29921 + i), os.path.join(root, "bench.py"),
+                              *common, "--gpus", "2", "--mesh", mesh, "--parity-out", two],
+                             capture_output=True, text=True, timeout=600, cwd=root)
+        assert out.returncode == 0, out.stderr[-1500:]
+        chk = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--check-parity", one, two, "--parity-tol", "1e-3"],
+                             capture_output=True, text=True, timeout=120, cwd=root)
+        assert chk.returncode == 0, chk.stdout + chk.stderr[-500:]
+        rec = json.loads(chk.stdout.strip().splitlines()[-1])
+        assert rec["parity"] == "ok" and rec["max_abs_diff"] < 1e-3
+    # a curve that differs is reported as a failure (non-zero exit)
+    bad = json.load(open(one))
+    bad["losses"] = [x + 1.0 for x in bad["losses"]]
+    json.dump(bad, open(str(tmp_path / "bad.json"), "w"))
+    chk = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--check-parity", one, str(tmp_path / "bad.json")],
+                         capture_output=True, text=True, timeout=120, cwd=root)
+    assert chk.returncode != 0
+
+
+def test_bench_vit_arm_cpu():
+    """`bench.py --workload vit` (BASELINE config #2's harness) prints the contract line through Trainer's step loop."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--workload", "vit", "--cpu", "--steps", "2",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-1500:]
+    rec = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    assert rec["value"] > 0 and rec["images_per_s"] > 0 and rec["config"]["seq_len"] == 50 and rec["steps"] == 2
+
+
 _REFERENCE_MODULES = """GPT2_Trainer coordinators coordinators.data_parallel_coordinator coordinators.dp_pp_coordinator
 coordinators.dp_tp_coordinator coordinators.hybrid_3d_coordinator coordinators.main_coordinator
 coordinators.pipeline_parallel_coordinator coordinators.tensor_parallel_coordinator coordinators.tp_pp_coordinator core
