@@ -265,15 +265,17 @@ def test_check_weight_shapes_tool(tmp_path, capsys):
     assert "shard shapes match" in capsys.readouterr().out
 
 
-def test_reference_readme_launch_lines_work():
+def test_reference_readme_launch_lines_work(tmp_path):
     """The reference README's launch line, verbatim apart from the CPU flags: ``-m QuintNet.examples.simple_dp`` with
     ``--config QuintNet/examples/dp_config.yaml``."""
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29612", "-m", "QuintNet.examples.simple_dp", "--config", "QuintNet/examples/dp_config.yaml",
            "--cpu", "--synthetic", "--epochs", "1", "--samples", "64"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    env = dict(os.environ, QUINTNET_OUTPUT_DIR=str(tmp_path))      # the relative config path needs cwd = repo root;
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)   # the checkpoint does not
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
     assert "Train Loss:" in out.stdout
+    assert (tmp_path / "model_checkpoint.pt").exists() and not os.path.exists(os.path.join(ROOT, "model_checkpoint.pt"))
 
 
 def test_cluster_workflow_on_a_volume_directory(tmp_path):
