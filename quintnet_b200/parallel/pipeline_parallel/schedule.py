@@ -66,6 +66,16 @@ class PipelineSchedule(ABC):
                                     dtype=dtype, is_first_stage=t.is_first_stage,
                                     is_last_stage=t.is_last_stage, tensor=tensor, shapes=shapes)
 
+    def _defer_forward_recv(self) -> bool:
+        """True when this stage runs sequence-parallel tensor parallelism (the fused TP kernels): see the 1F1B steady
+        state.  ``QN_PP_PREPOST_FWD=1`` / ``0`` forces pre-posting on / off (A/B timing)."""
+        import os
+        v = os.environ.get("QN_PP_PREPOST_FWD")
+        if v in ("0", "1"):
+            return v == "0"
+        stage = unwrap_stage(self.trainer.model)
+        return bool(getattr(stage, "sequence_parallel", False))      # the stage sets it only when its tp group is > 1
+
     def _bidir(self, op, send, device, dtype, shapes):
         t = self.trainer
         return bidirectional_pipeline_communicate(operation=op, pp_group=t.pp_group, pp_rank=t.rank,
@@ -189,6 +199,12 @@ class OneFOneBSchedule(PipelineSchedule):
         # the NEXT micro-batch are both posted before the backward runs, so they arrive on the communication streams
         # (one communicator per direction, see core/communication.py) while this stage computes; sends stay in flight.
         kw = dict(pp_group=t.pp_group, pp_rank=t.rank, is_first_stage=t.is_first_stage, is_last_stage=t.is_last_stage)
+        # A posted receive is a RESIDENT NCCL kernel until its data arrives.  The fused TP kernels (AG->GEMM / GEMM->RS)
+        # are persistent grids that need every one of their CTAs to run before the tp peer can finish, so an NCCL CTA
+        # parked on an SM for the length of a backward pass can stall them until the neighbouring stage delivers.  With
+        # sequence-parallel TP the next activation is therefore posted AFTER the backward (its 16 MB transfer is ~50 us
+        # of a ~10 ms backward: nothing to hide); without TP it stays pre-posted.
+        defer_fwd_recv = self._defer_forward_recv()
         x = self._comm("recv_forward", device, dtype, tensor_shapes) if n_steady > 0 else None
         for i in range(n_steady):
             last = i == n_steady - 1
@@ -196,13 +212,17 @@ class OneFOneBSchedule(PipelineSchedule):
             if not t.is_last_stage:
                 post_send("forward", tensor=y, **kw)
             g_pending = post_recv("backward", device=device, dtype=dtype, shapes=tensor_shapes, **kw)
-            x_pending = None if last else post_recv("forward", device=device, dtype=dtype, shapes=tensor_shapes, **kw)
+            x_pending = None
+            if not last and not defer_fwd_recv:
+                x_pending = post_recv("forward", device=device, dtype=dtype, shapes=tensor_shapes, **kw)
             inputs.append(x)
             outputs.append(y)
             bx, by = inputs.pop(0), outputs.pop(0)
             gx = self._backward_step(bx, by, g_pending.wait(), M)
             if not t.is_first_stage:
                 post_send("backward", tensor=gx, **kw)
+            if not last and defer_fwd_recv:
+                x_pending = post_recv("forward", device=device, dtype=dtype, shapes=tensor_shapes, **kw)
             x = x_pending.wait() if x_pending is not None else None
 
         for _ in range(n_warm):
