@@ -246,12 +246,15 @@ def test_bench_parity_mode_cpu(tmp_path):
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), *common, "--parity-out", one],
                          capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stderr[-1500:]
-    for i, mesh in enumerate(("1,1,2",)):
+    # pp2 twice: next-activation receive pre-posted before the backward (QN_PP_PREPOST_FWD=1) and posted after it (=0,
+    # the order used with sequence-parallel TP) — both orders of the 1F1B steady state must give the same curve
+    for i, (mesh, prepost) in enumerate((("1,1,2", "1"), ("1,1,2", "0"))):
         two = str(tmp_path / f"n2_{i}.json")
         out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                               "--master-addr", "127.0.0.1", "--master-port", str(29921 + i), os.path.join(root, "bench.py"),
                               *common, "--gpus", "2", "--mesh", mesh, "--parity-out", two],
-                             capture_output=True, text=True, timeout=600, cwd=root)
+                             capture_output=True, text=True, timeout=600, cwd=root,
+                             env=dict(os.environ, QN_PP_PREPOST_FWD=prepost))
         assert out.returncode == 0, out.stderr[-1500:]
         chk = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--check-parity", one, two, "--parity-tol", "1e-3"],
                              capture_output=True, text=True, timeout=120, cwd=root)
